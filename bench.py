@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- annotation x cell z-scores per second (50 background iterations).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+A "step" is one pass of the hot path (compute_deviations_core: counts layout, annotation
+preparation, gather-contraction with fused epilogue, variability merge, ABI layout) over one
+batch of synthetic scATAC input: BASELINE.json config 2 (100k peaks x 10k cells, ~3 % nonzero,
+870 motif-like annotations, 50 background iterations) per GPU -- weak scaling, cells shard.
+
+  value : device-timed (CUDA events on the library's stream), inputs resident in HBM.
+  e2e   : the same metric through the C ABI with pinned HOST buffers, every step paying the
+          H2D of counts / annotations / background / expectation and the D2H of both K x N
+          result matrices.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "annotation_x_cell_zscores_per_sec_50bg"
+UNIT = "z-scores/s"
+WORKLOAD = "cfg2_scatac_motifs"
+NITER = 50
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks_json():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_workload(rank, cells, quick):
+    from chromvar_b200 import synthetic
+    t0 = time.time()
+    if quick:
+        d = synthetic.make_config("small", seed_offset=rank)
+        name = "small"
+    else:
+        over = {"N": cells} if cells else {}
+        d = synthetic.make_config(WORKLOAD, seed_offset=rank, **over)
+        name = WORKLOAD
+    log("[bench] rank %d: synthetic %s %s nnz=%d (%.1fs)" % (rank, name, d["counts"].shape, d["counts"].nnz,
+                                                            time.time() - t0))
+    return d, name
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference algorithm (the reference's R path cannot run:
+# no R on this image).  Only this leg and cpu_baseline execute anything under oracle/.
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(d, bg, e, anno_slice, workers):
+    from oracle import chromvar_oracle as orc
+    ptr, idx = d["annoptr"], d["annoidx"]
+    sets = [idx[ptr[k]:ptr[k + 1]].astype(np.int64) for k in anno_slice]
+    t0 = time.perf_counter()
+    orc.deviations_task_farm(d["counts"], sets, bg, e, workers)
+    return time.perf_counter() - t0
+
+
+def host_background(d, rng):
+    """A background matrix for the reference arm when no GPU sampler is available: peaks with a
+    similar fragment total (what the sampler's bins encode), cheap and deterministic."""
+    fpp = np.asarray(d["counts"].sum(axis=1)).ravel()
+    order = np.argsort(fpp, kind="stable")
+    rank_of = np.empty_like(order)
+    rank_of[order] = np.arange(order.size)
+    P = fpp.size
+    jitter = rng.integers(-200, 201, size=(P, NITER))
+    pos = np.clip(rank_of[:, None] + jitter, 0, P - 1)
+    return np.asfortranarray((order[pos] + 1).astype(np.int32))
+
+
+def run_reference(args):
+    rank, ws = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    d, name = make_workload(0, args.cells, args.quick)
+    C = d["counts"]
+    P, N = C.shape
+    K = len(d["annoptr"]) - 1
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    bg = host_background(d, np.random.default_rng(20173))
+    workers = os.cpu_count() or 1
+    S = max(1, min(K, workers))
+    times = []
+    for s in range(args.warmup + args.steps):
+        sl = [(s * S + j) % K for j in range(S)]
+        dt = cpu_reference_step(d, bg, e, sl, workers)
+        log("[bench/reference] step %d: %d annotations x %d cells in %.2fs" % (s, S, N, dt))
+        if s >= args.warmup:
+            times.append(dt)
+    tot = float(np.sum(times))
+    value = S * N * len(times) / tot
+    sample = "%d of %d annotations x all %d cells per step, fork pool of %d workers" % (S, K, N, workers)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
+                   "niterations": NITER, "nnz": int(C.nnz)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of the reference algorithm (scipy fp64, per-annotation "
+                                 "sparse products incl. the per-annotation colSums, fork pool = "
+                                 "MulticoreParam); not a chromVAR R timing: R is not installed here"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from chromvar_b200 import _lib, distributed as cvd
+
+    rank, ws, local = cvd.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    eng = _lib.Handle(local, seed=20173)
+    d, name = make_workload(rank, args.cells, args.quick)
+    C = d["counts"]
+    P, N = C.shape
+    K = len(d["annoptr"]) - 1
+    nnz = int(C.nnz)
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    h_colptr, h_rowidx, h_x = pin(C.indptr.astype(np.int64)), pin(C.indices.astype(np.int32)), pin(C.data.astype(np.float64))
+    h_ptr, h_idx = pin(d["annoptr"]), pin(d["annoidx"].astype(np.int32))
+
+    # ---- setup (untimed): counts -> HBM, global per-peak totals, expectation, background -------
+    eng.set_counts_csc(P, N, h_colptr, h_rowidx, h_x)
+    cvd.allreduce_peak_totals(eng)                       # NCCL all-reduce of int64[P+1] when ws > 1
+    t0 = time.perf_counter()
+    e = eng.expectations()
+    t_exp = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    bg = eng.background_peaks(d["bias"], NITER, 0.1, 50)
+    t_bg = time.perf_counter() - t0
+    bg_ms_dev = eng.stats()["ms_background"]
+    h_bg, h_e = pin(bg), pin(e)
+    eng.deviations_upload(h_ptr, h_idx, h_bg, h_e, index_base=1)
+
+    ext = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        eng.deviations_compute(rebuild_counts_layout=True, keep_sums=False)
+        if ws > 1:
+            cvd.gather_variability(eng)                  # reduction 2 (K x 4 doubles)
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    step_ms, contract_ms, stage_acc = [], [], np.zeros(4)
+    upd = bytes_alg = 0
+    for _ in range(args.steps):
+        with torch.cuda.stream(ext):
+            flush.zero_()                                # L2 flush between timed iterations
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(ext)
+        step()
+        ev1.record(ext)
+        ev1.synchronize()
+        step_ms.append(ev0.elapsed_time(ev1))
+        st = eng.stats()
+        contract_ms.append(st["ms_contract"])
+        stage_acc += [st["ms_counts_layout"], st["ms_anno_prep"], st["ms_contract"], st["ms_finalize"]]
+        upd, bytes_alg = st["contract_updates"], st["contract_bytes"]
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.stats()["kernel_launches"] - launches0
+    total_ms = float(np.sum(step_ms))
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = K * N * ws * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e through the C ABI with pinned host buffers ---------------------------------------------
+    out = dict(dev=pin(np.empty((K, N), np.float64, order="F").ravel(order="K")).reshape((K, N), order="F"),
+               z=pin(np.empty((K, N), np.float64, order="F").ravel(order="K")).reshape((K, N), order="F"),
+               matches=np.empty(K), overlap=np.empty(K), variability=np.empty(K))
+
+    def e2e_step():
+        eng.set_counts_csc(P, N, h_colptr, h_rowidx, h_x)              # H2D counts + K1
+        if ws > 1:
+            cvd.allreduce_peak_totals(eng)
+        eng.deviations_upload(h_ptr, h_idx, h_bg, h_e, index_base=1)   # H2D annotations, bg, expectation
+        eng.deviations_compute(rebuild_counts_layout=False, keep_sums=False)
+        eng.deviations_download(out=out)                                # D2H dev, z (+ K-vectors)
+        if ws > 1:
+            cvd.gather_variability(eng)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 5))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = K * N * ws * n_e2e / float(te.item())
+    h2d = h_colptr.nbytes + h_rowidx.nbytes + h_x.nbytes + h_ptr.nbytes + h_idx.nbytes + h_bg.nbytes + h_e.nbytes
+    d2h = 2 * K * N * 8 + 3 * K * 8
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (k_contract) ------------------------------------------------
+    peaks, peaks_kind = peaks_json()
+    c_ms = float(np.mean(contract_ms))
+    achieved = bytes_alg / (c_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+            "peak_kind": peaks_kind, "ms_per_launch": c_ms, "algorithmic_bytes_per_launch": int(bytes_alg),
+            "updates_per_launch": int(upd), "share_of_step": c_ms / (total_ms / args.steps)}
+
+    # ---- CPU baseline beside it (N=1 only): bounded sample of the same workload ---------------
+    cpu = None
+    if ws == 1 and not args.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        S = max(1, min(K, 2 * workers))
+        dt = cpu_reference_step(d, bg, e, list(range(S)), workers)
+        cpu = {"value": S * N / dt, "unit": UNIT, "cores": workers, "kind": "port",
+               "sample": "%d of %d annotations x all %d cells, fork pool of %d workers, %.1fs" % (S, K, N, workers, dt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 sums, f64 epilogue", "data": "synthetic",
+        "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
+                   "niterations": NITER, "nnz_per_gpu": nnz, "nnz_annotations": int(d["annoptr"][-1]),
+                   "l2": "256 MB flush write between timed steps", "cell_tile": eng.stats()["cell_tile"]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "stages_ms": dict(zip(["counts_layout", "anno_prep", "contract", "finalize"],
+                              (stage_acc / args.steps).round(4).tolist())),
+        "other_paths": {"getBackgroundPeaks_ms_device": bg_ms_dev, "getBackgroundPeaks_ms_wall": 1e3 * t_bg,
+                        "sampled_indices_per_s": P * NITER / max(t_bg, 1e-9),
+                        "computeExpectations_ms_wall": 1e3 * t_exp},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (default: config 2's 10000)")
+    ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and not args.quick and args.impl == "ours":
+        log("[bench] warning: fewer than 3 warm-up steps")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,671 @@
+// compute_deviations_core on the GPU: the whole bplapply fan-out over compute_deviations_single
+// (R/compute_deviations.R:355-408, 451-537) as
+//   k_bg_prepare   background matrix -> [P][B] 0-based, validated            (:365, :493-494)
+//   k_anno_stats   expected-fraction table E[k][0..B], overlap, matches      (:488, :502-503, :506)
+//   k_contract     observed + B background sums for one (annotation, cell tile) in shared
+//                  memory (row-gather SpMM over the cell-tiled counts layout) with the fused
+//                  fp64 epilogue: raw deviations, mean / sd over iterations, bias-corrected
+//                  deviation, z, NA mask, and the per-annotation variability partials
+//                  (:486-520; src/utils.cpp:9-25)
+//   k_var_merge    variability partials -> row SD of z
+//   k_transpose    [K][N] -> K x N column-major (ABI layout)
+#include <algorithm>
+#include <numeric>
+
+#include "cv_internal.cuh"
+
+#define CV_ENTRY_VAL_BITS 20
+#define CV_ENTRY_VAL_MASK 0xFFFFFu
+#define CONTRACT_THREADS 512
+#define STATS_THREADS 512
+
+enum { FLAG_BADIDX = 8u };
+
+static double wall_ms() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// =========================================================================================
+// input preparation
+// =========================================================================================
+// bg_raw: P x B column-major with index_base  ->  bgT[p][i] 0-based (row-major).
+__global__ void __launch_bounds__(256)
+k_bg_prepare(const int32_t* __restrict__ bg_raw, int P, int B, int base,
+             int32_t* __restrict__ bgT, uint32_t* __restrict__ flags) {
+  __shared__ int32_t tile[32][33];
+  int p0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  bool bad = false;
+  for (int r = ty; r < 32; r += 8) {   // r: iteration within tile, tx: peak within tile
+    int p = p0 + tx, i = i0 + r;
+    int32_t v = 0;
+    if (p < P && i < B) {
+      v = bg_raw[(int64_t)i * P + p] - base;
+      if (v < 0 || v >= P) { bad = true; v = 0; }
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {   // r: peak within tile, tx: iteration within tile
+    int p = p0 + r, i = i0 + tx;
+    if (p < P && i < B) bgT[(int64_t)p * B + i] = tile[tx][r];
+  }
+  if (bad) atomicOr(flags, FLAG_BADIDX);
+}
+
+__global__ void k_anno_prepare(const int32_t* __restrict__ in, int64_t n, int P, int base,
+                               int32_t* __restrict__ out, uint32_t* __restrict__ flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t v = in[i] - base;
+  if (v < 0 || v >= P) { atomicOr(flags, FLAG_BADIDX); v = 0; }
+  out[i] = v;
+}
+
+// One CTA per annotation (strided): expected-fraction table, overlap, matches.
+//   etab[k][0] = sum_{p in set} e[p]                     (tf_vec %*% expectation, :488)
+//   etab[k][i] = sum_{p in set} e[bg[p,i]]               (sample_mat %*% expectation, :502)
+//   overlap[k] = mean_i( sum_{p in set} mult_set(bg[p,i]) ) / #set      (:506, :477-478)
+//   matches[k] = #set / P                                (:533)
+// mark: int32[gridDim.x][P], all zero on entry and on exit.
+__global__ void __launch_bounds__(STATS_THREADS)
+k_anno_stats(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx,
+             const int32_t* __restrict__ bgT, const double* __restrict__ e, int P, int B, int K,
+             int32_t* __restrict__ mark, double* __restrict__ etab, double* __restrict__ overlap,
+             double* __restrict__ matches) {
+  extern __shared__ double s_part[];   // [nwarps][I]
+  __shared__ unsigned long long s_ov[STATS_THREADS / 32];
+  const int I = B + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = STATS_THREADS / 32;
+  int32_t* mk = mark + (int64_t)blockIdx.x * P;
+  for (int k = blockIdx.x; k < K; k += gridDim.x) {
+    int64_t beg = annoptr[k], end = annoptr[k + 1];
+    for (int64_t idx = beg + threadIdx.x; idx < end; idx += STATS_THREADS)
+      atomicAdd(mk + annoidx[idx], 1);
+    __syncthreads();
+    unsigned long long ov = 0;
+    for (int j0 = 0; j0 < I; j0 += 32) {
+      int j = j0 + lane;
+      double se = 0.0;
+      if (j < I) {
+        for (int64_t idx = beg + warp; idx < end; idx += nwarps) {
+          int p = __ldg(annoidx + idx);
+          int q = (j == 0) ? p : __ldg(bgT + (int64_t)p * B + (j - 1));
+          se += __ldg(e + q);
+          if (j > 0) ov += (unsigned long long)mk[q];
+        }
+        s_part[warp * I + j] = se;
+      }
+    }
+    ov = warp_sum<unsigned long long>(ov);
+    if (lane == 0) s_ov[warp] = ov;
+    __syncthreads();
+    for (int j = threadIdx.x; j < I; j += STATS_THREADS) {
+      double s = 0.0;
+      for (int w = 0; w < nwarps; ++w) s += s_part[w * I + j];
+      etab[(int64_t)k * I + j] = s;
+    }
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int w = 0; w < nwarps; ++w) tot += s_ov[w];
+      double cnt = (double)(end - beg);
+      matches[k] = cnt / (double)P;
+      overlap[k] = (end > beg) ? ((double)tot / (double)B) / cnt : cv_na_real();
+    }
+    for (int64_t idx = beg + threadIdx.x; idx < end; idx += STATS_THREADS) mk[annoidx[idx]] = 0;
+    __syncthreads();
+  }
+}
+
+// =========================================================================================
+// K5b + K6 + K7: the gather-contraction with fused epilogue.
+// One work item = (annotation k, cell tile t).  Shared memory holds acc[B+1][W] integer sums:
+// row 0 = observed, row i = background iteration i.  A warp takes one peak p of the set at a
+// time: its lanes fetch the B+1 source rows q_j (q_0 = p, q_j = bg[p][j]) and their extents
+// in tile t's row layout, then every row's entries (cell_in_tile, count) are loaded
+// coalesced, 32 per warp instruction, and added into acc[j][cell] with shared-memory atomics.
+// =========================================================================================
+struct ContractParams {
+  int P, N, K, B, W, T;
+  int64_t n_items;
+  const int64_t* annoptr;
+  const int32_t* annoidx;
+  const int32_t* bgT;
+  const uint32_t* rowptr;    // [T*P + 1]
+  const uint32_t* entries;
+  const double* etab;        // [K][B+1]
+  const double* fps;         // [N]
+  const int32_t* order;      // [K] annotations by decreasing set size
+  uint32_t* work_ctr;
+  double* dev_rm;            // [K][N]
+  double* z_rm;              // [K][N]
+  double* varpart;           // [K][T][4]  n_finite, mean, M2, n_nonfinite
+  long long* obs;            // [K][N] or null
+  long long* samp;           // [K][B][N] or null
+  unsigned long long* upd_ctr;   // visited entries (instrumentation), may be null
+};
+
+struct Welford {
+  double n, mean, m2;
+};
+__device__ __forceinline__ void welford_add(Welford& w, double x) {
+  w.n += 1.0;
+  double d = x - w.mean;
+  w.mean += d / w.n;
+  w.m2 += d * (x - w.mean);
+}
+__device__ __forceinline__ Welford welford_merge(const Welford& a, const Welford& b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Welford r;
+  r.n = a.n + b.n;
+  double d = b.mean - a.mean;
+  r.mean = a.mean + d * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+  return r;
+}
+
+template <typename AccT>
+__device__ __forceinline__ void acc_add(AccT* p, uint32_t v);
+template <>
+__device__ __forceinline__ void acc_add<int>(int* p, uint32_t v) { atomicAdd(p, (int)v); }
+template <>
+__device__ __forceinline__ void acc_add<long long>(long long* p, uint32_t v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
+template <typename AccT>
+__global__ void __launch_bounds__(CONTRACT_THREADS, 1)
+k_contract(const ContractParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AccT* acc = reinterpret_cast<AccT*>(smem_raw);
+  __shared__ int s_item;
+  __shared__ double s_winv[1024 + 1];            // 1 / E[k][i]; B <= 1024
+  __shared__ double s_w[CONTRACT_THREADS / 32][4];
+  const unsigned full = 0xffffffffu;
+  const int I = prm.B + 1, W = prm.W, B = prm.B, P = prm.P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = CONTRACT_THREADS / 32;
+  constexpr int U = 8;
+  uint32_t visited = 0;   // entries visited by this thread (instrumentation; < 2^32 per thread)
+
+  for (;;) {
+    if (threadIdx.x == 0) s_item = (int)atomicAdd(prm.work_ctr, 1u);
+    __syncthreads();
+    const int64_t item = s_item;
+    if (item >= prm.n_items) break;
+    const int t = (int)(item / prm.K);
+    const int k = prm.order[item - (int64_t)t * prm.K];
+    const int64_t beg = prm.annoptr[k], end = prm.annoptr[k + 1];
+    const int c0 = t * W;
+    const int ncell = min(W, prm.N - c0);
+
+    // ---- zero the accumulators, stage 1/E ------------------------------------------------
+    {
+      uint4* a4 = reinterpret_cast<uint4*>(acc);
+      const int n4 = (int)(((size_t)I * W * sizeof(AccT)) >> 4);
+      for (int i = threadIdx.x; i < n4; i += CONTRACT_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < I; i += CONTRACT_THREADS)
+        s_winv[i] = 1.0 / prm.etab[(int64_t)k * I + i];
+    }
+    __syncthreads();
+
+    // ---- gather-contraction ---------------------------------------------------------------
+    const uint32_t* __restrict__ rp = prm.rowptr + (int64_t)t * P;
+    const uint32_t* __restrict__ ent_base = prm.entries;
+    for (int64_t idx = beg + warp; idx < end; idx += NW) {
+      const int p = __ldg(prm.annoidx + idx);
+      const int32_t* __restrict__ bgrow = prm.bgT + (int64_t)p * B;
+      for (int j0 = 0; j0 < I; j0 += 32) {
+        const int j = j0 + lane;
+        uint32_t s = 0, e = 0;
+        if (j < I) {
+          const int q = (j == 0) ? p : __ldg(bgrow + (j - 1));
+          s = __ldg(rp + q);
+          e = __ldg(rp + q + 1);
+        }
+        const int nj = min(32, I - j0);
+        AccT* accj = acc + (size_t)j0 * W;
+        for (int jj = 0; jj < nj; jj += U) {
+          uint32_t ent[U];
+          uint32_t longrows = 0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t sj = __shfl_sync(full, s, jj + u);
+            const uint32_t ej = __shfl_sync(full, e, jj + u);
+            const uint32_t x = sj + lane;
+            ent[u] = (x < ej) ? __ldg(ent_base + x) : 0u;
+            longrows |= (ej - sj > 32u) ? (1u << u) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (ent[u]) {
+              acc_add<AccT>(accj + (size_t)(jj + u) * W + (ent[u] >> CV_ENTRY_VAL_BITS),
+                            ent[u] & CV_ENTRY_VAL_MASK);
+              ++visited;
+            }
+          }
+          if (longrows) {   // warp-uniform: rows with more than 32 entries in this tile
+            for (int u = 0; u < U; ++u) {
+              if (!(longrows & (1u << u))) continue;
+              const uint32_t sj = __shfl_sync(full, s, jj + u);
+              const uint32_t ej = __shfl_sync(full, e, jj + u);
+              for (uint32_t x = sj + 32u + lane; x < ej; x += 32u) {
+                const uint32_t en = __ldg(ent_base + x);
+                acc_add<AccT>(accj + (size_t)(jj + u) * W + (en >> CV_ENTRY_VAL_BITS),
+                              en & CV_ENTRY_VAL_MASK);
+                ++visited;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- fused epilogue (fp64 from exact integer sums) -----------------------------------
+    Welford wf = {0.0, 0.0, 0.0};
+    double nonfinite = 0.0;
+    const bool empty = (end == beg);
+    const double E0 = prm.etab[(int64_t)k * I];
+    for (int c = threadIdx.x; c < ncell; c += CONTRACT_THREADS) {
+      const int64_t o = (int64_t)k * prm.N + c0 + c;
+      double devv, zv;
+      if (empty) {
+        devv = zv = cv_na_real();                       // :458-461
+      } else {
+        const double fpsv = prm.fps[c0 + c];
+        const double expected = E0 * fpsv;              // :488
+        const double rf = 1.0 / fpsv;
+        const double obs_dev = ((double)acc[c] - expected) / expected;   // :489
+        double sum = 0.0;
+        for (int i = 1; i <= B; ++i) {
+          // (sampled - sampled_expected) / sampled_expected, sampled_expected = E_i * fps (:502-504)
+          const double d = (double)acc[(size_t)i * W + c] * s_winv[i] * rf - 1.0;
+          sum += d;
+        }
+        const double mean = sum / (double)B;            // :511
+        double ss = 0.0;
+        for (int i = 1; i <= B; ++i) {
+          const double d = (double)acc[(size_t)i * W + c] * s_winv[i] * rf - 1.0;
+          ss += (d - mean) * (d - mean);
+        }
+        const double sd = sqrt(ss / (double)(B - 1));   // :512
+        devv = obs_dev - mean;                          // :514
+        zv = devv / sd;                                 // :515
+        if (expected < 1.0) devv = zv = cv_na_real();   // :509, :517-520 (threshold = 1)
+      }
+      prm.dev_rm[o] = devv;
+      prm.z_rm[o] = zv;
+      if (isfinite(zv)) welford_add(wf, zv); else nonfinite += 1.0;
+      if (prm.obs) prm.obs[o] = (long long)acc[c];
+      if (prm.samp)
+        for (int i = 1; i <= B; ++i)
+          prm.samp[((int64_t)k * B + (i - 1)) * prm.N + c0 + c] = (long long)acc[(size_t)i * W + c];
+    }
+    // variability partial of this (k, t): deterministic tree merge
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Welford b;
+      b.n = __shfl_xor_sync(full, wf.n, o);
+      b.mean = __shfl_xor_sync(full, wf.mean, o);
+      b.m2 = __shfl_xor_sync(full, wf.m2, o);
+      // merge in a lane-symmetric order so both partners get bit-identical results
+      wf = (lane & o) ? welford_merge(b, wf) : welford_merge(wf, b);
+      nonfinite += __shfl_xor_sync(full, nonfinite, o);
+    }
+    if (lane == 0) {
+      s_w[warp][0] = wf.n; s_w[warp][1] = wf.mean; s_w[warp][2] = wf.m2; s_w[warp][3] = nonfinite;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      Welford tot = {0.0, 0.0, 0.0};
+      double nf = 0.0;
+      for (int w = 0; w < NW; ++w) {
+        Welford b = {s_w[w][0], s_w[w][1], s_w[w][2]};
+        tot = welford_merge(tot, b);
+        nf += s_w[w][3];
+      }
+      double* vp = prm.varpart + ((int64_t)k * prm.T + t) * 4;
+      vp[0] = tot.n; vp[1] = tot.mean; vp[2] = tot.m2; vp[3] = nf;
+    }
+    __syncthreads();
+  }
+  if (prm.upd_ctr) {
+    unsigned long long v64 = warp_sum<unsigned long long>((unsigned long long)visited);
+    if (lane == 0 && v64) atomicAdd(prm.upd_ctr, v64);
+  }
+}
+
+// min(rowSums) > 0 check of compute_deviations_core (R/compute_deviations.R:362-363)
+__global__ void k_check_zero_peaks(const unsigned long long* __restrict__ peak_tot, int P,
+                                   uint32_t* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P && peak_tot[i] == 0ull) atomicOr(flags, 16u);
+}
+
+// varpart[K][T][4] -> varfinal[K][4], variab[K] = sqrt(M2 / (n - 1)) over finite entries
+// (row_sds(z, na_rm = TRUE), src/utils.cpp:18-24: NaN when <= 1 finite value)
+__global__ void k_var_merge(const double* __restrict__ varpart, int K, int T,
+                            double* __restrict__ varfinal, double* __restrict__ variab) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  Welford tot = {0.0, 0.0, 0.0};
+  double nf = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const double* vp = varpart + ((int64_t)k * T + t) * 4;
+    Welford b = {vp[0], vp[1], vp[2]};
+    tot = welford_merge(tot, b);
+    nf += vp[3];
+  }
+  varfinal[k * 4 + 0] = tot.n; varfinal[k * 4 + 1] = tot.mean;
+  varfinal[k * 4 + 2] = tot.m2; varfinal[k * 4 + 3] = nf;
+  variab[k] = tot.n > 1.0 ? sqrt(tot.m2 / (tot.n - 1.0)) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// in: [R][C] row-major -> out: [C][R] row-major (= R x C column-major)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_transpose(const T* __restrict__ in, T* __restrict__ out, int64_t R, int64_t C) {
+  __shared__ T tile[32][33];
+  int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (r0 + r < R && c0 + tx < C) tile[r][tx] = in[(r0 + r) * C + c0 + tx];
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8)
+    if (c0 + c < C && r0 + tx < R) out[(c0 + c) * R + r0 + tx] = tile[tx][c];
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+int cv_choose_tile(cv_handle* h, int B, int acc_bytes, int* W_out) {
+  const int I = B + 1;
+  // static shared memory of k_contract: s_winv (8200 B) + s_w + s_item, rounded up
+  const int budget = h->max_smem_optin - 10 * 1024;
+  int W = budget / (I * acc_bytes);
+  W = (W / 32) * 32;
+  if (W > 4096) W = 4096;
+  int64_t nround = ((h->N + 31) / 32) * 32;
+  if (W > nround) W = (int)nround;
+  if (W < 32)
+    CV_FAIL(h, CV_ERR_UNSUPPORTED,
+            "niterations = %d needs more shared memory than one SM has for a 32-cell tile", B);
+  *W_out = W;
+  return CV_OK;
+}
+
+extern "C" int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* annoptr,
+                                    const int32_t* annoidx, int index_base, const int32_t* bg,
+                                    int B, const double* expectation) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  h->have_anno = false;
+  h->have_results = false;
+  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
+  if (K < 1 || !annoptr) CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid");
+  if (K > 0x7fffffff) CV_FAIL(h, CV_ERR_UNSUPPORTED, "K must be < 2^31");
+  if (index_base != 0 && index_base != 1) CV_FAIL(h, CV_ERR_INVALID, "index_base must be 0 or 1");
+  if (B < 1 || !bg) CV_FAIL(h, CV_ERR_INVALID, "background_peaks must have at least one column");
+  if (B > 1024) CV_FAIL(h, CV_ERR_UNSUPPORTED, "niterations > 1024 is not supported");
+  if (!expectation) CV_FAIL(h, CV_ERR_INVALID, "expectation is NULL");
+  if (annoptr[0] != 0) CV_FAIL(h, CV_ERR_INVALID, "annoptr must start at 0");
+  for (int64_t k = 0; k < K; ++k)
+    if (annoptr[k + 1] < annoptr[k]) CV_FAIL(h, CV_ERR_INVALID, "annoptr is not monotone");
+  const int64_t nnzA = annoptr[K];
+  if (nnzA > 0 && !annoidx) CV_FAIL(h, CV_ERR_INVALID, "annoidx is NULL");
+  const int64_t P = h->P;
+  double t0 = wall_ms();
+  h->K = K; h->B = B; h->nnzA = nnzA; h->index_base = index_base;
+  h->h_annoptr.assign(annoptr, annoptr + K + 1);
+  CV_TRY(cv_ensure(h, h->annoptr, (size_t)(K + 1) * 8));
+  CV_TRY(cv_ensure(h, h->anno_raw, (size_t)nnzA * 4));
+  CV_TRY(cv_ensure(h, h->annoidx, (size_t)nnzA * 4));
+  CV_TRY(cv_ensure(h, h->bg_raw, (size_t)P * B * 4));
+  CV_TRY(cv_ensure(h, h->expect, (size_t)P * 8));
+  CV_CUDA(h, cudaMemcpyAsync(h->annoptr.p, annoptr, (size_t)(K + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  if (nnzA)
+    CV_CUDA(h, cudaMemcpyAsync(h->anno_raw.p, annoidx, (size_t)nnzA * 4, cudaMemcpyHostToDevice, h->stream));
+  CV_CUDA(h, cudaMemcpyAsync(h->bg_raw.p, bg, (size_t)P * B * 4, cudaMemcpyHostToDevice, h->stream));
+  CV_CUDA(h, cudaMemcpyAsync(h->expect.p, expectation, (size_t)P * 8, cudaMemcpyHostToDevice, h->stream));
+  // annotations by decreasing set size (longest-processing-time-first work order)
+  std::vector<int32_t> order((size_t)K);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    return (annoptr[a + 1] - annoptr[a]) > (annoptr[b + 1] - annoptr[b]);
+  });
+  CV_TRY(cv_ensure(h, h->order, (size_t)K * 4));
+  CV_CUDA(h, cudaMemcpyAsync(h->order.p, order.data(), (size_t)K * 4, cudaMemcpyHostToDevice, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->st.ms_h2d = wall_ms() - t0;
+  h->st.h2d_bytes = (int64_t)((K + 1) * 8 + nnzA * 4 + P * B * 4 + P * 8);
+  h->have_anno = true;
+  return CV_OK;
+}
+
+template <typename AccT>
+static int launch_contract(cv_handle* h, const ContractParams& prm, size_t smem) {
+  CV_CUDA(h, cudaFuncSetAttribute(k_contract<AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = prm.n_items < h->num_sms ? prm.n_items : h->num_sms;
+  CV_LAUNCH(h, k_contract<AccT>, (unsigned)grid, CONTRACT_THREADS, smem, prm);
+  return CV_OK;
+}
+
+extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, int keep_sums) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
+  if (!h->have_anno) CV_FAIL(h, CV_ERR_STATE, "annotations / background not uploaded");
+  if (!h->totals_committed)
+    CV_FAIL(h, CV_ERR_STATE, "per-peak totals handed out for a cross-shard reduction; call cv_peak_totals_commit first");
+  const int64_t P = h->P, N = h->N, K = h->K;
+  const int B = h->B, I = B + 1;
+  h->have_results = false;
+
+  // accumulator width: |sum| <= (largest set) * (largest count)
+  int64_t set_max = 0;
+  for (int64_t k = 0; k < K; ++k) set_max = std::max(set_max, h->h_annoptr[k + 1] - h->h_annoptr[k]);
+  const bool wide = (double)set_max * (double)h->max_val >= 2147483647.0;
+  const int acc_bytes = wide ? 8 : 4;
+  int W = 0;
+  CV_TRY(cv_choose_tile(h, B, acc_bytes, &W));
+
+  // ---- stage 0: counts layout (derived from the resident CSC) -----------------------------
+  CV_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  if (rebuild_counts_layout || !h->layout_valid || h->W != W) CV_TRY(cv_build_layout(h, W));
+  const int T = h->T;
+  CV_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+
+  // ---- stage 1: annotation / background preparation ---------------------------------------
+  CV_TRY(cv_ensure(h, h->flags, 64));
+  CV_CUDA(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
+  CV_TRY(cv_ensure(h, h->bgT, (size_t)P * B * 4));
+  {
+    dim3 grid((unsigned)((P + 31) / 32), (unsigned)((B + 31) / 32));
+    CV_LAUNCH(h, k_bg_prepare, grid, 256, 0, h->bg_raw.as<int32_t>(), (int)P, B, h->index_base,
+              h->bgT.as<int32_t>(), h->flags.as<uint32_t>());
+  }
+  CV_LAUNCH(h, k_check_zero_peaks, (unsigned)((P + 255) / 256), 256, 0,
+            h->peak_tot.as<unsigned long long>(), (int)P, h->flags.as<uint32_t>());
+  if (h->nnzA)
+    CV_LAUNCH(h, k_anno_prepare, (unsigned)((h->nnzA + 255) / 256), 256, 0, h->anno_raw.as<int32_t>(),
+              h->nnzA, (int)P, h->index_base, h->annoidx.as<int32_t>(), h->flags.as<uint32_t>());
+  CV_TRY(cv_ensure(h, h->etab, (size_t)K * I * 8));
+  CV_TRY(cv_ensure(h, h->overlap, (size_t)K * 8));
+  CV_TRY(cv_ensure(h, h->matches, (size_t)K * 8));
+  {
+    int grid = (int)std::min<int64_t>(K, (int64_t)h->num_sms * 2);
+    size_t mark_bytes = (size_t)grid * P * 4;
+    if (h->mark.cap < mark_bytes) {
+      CV_TRY(cv_ensure(h, h->mark, mark_bytes));
+      CV_CUDA(h, cudaMemsetAsync(h->mark.p, 0, h->mark.cap, h->stream));
+    }
+    size_t smem = (size_t)(STATS_THREADS / 32) * I * 8;
+    CV_CUDA(h, cudaFuncSetAttribute(k_anno_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CV_LAUNCH(h, k_anno_stats, grid, STATS_THREADS, smem, h->annoptr.as<int64_t>(),
+              h->annoidx.as<int32_t>(), h->bgT.as<int32_t>(), h->expect.as<double>(), (int)P, B,
+              (int)K, h->mark.as<int32_t>(), h->etab.as<double>(), h->overlap.as<double>(),
+              h->matches.as<double>());
+  }
+  CV_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+
+  // ---- stage 2: contraction + fused epilogue -----------------------------------------------
+  CV_TRY(cv_ensure(h, h->dev_rm, (size_t)K * N * 8));
+  CV_TRY(cv_ensure(h, h->z_rm, (size_t)K * N * 8));
+  CV_TRY(cv_ensure(h, h->varpart, (size_t)K * T * 4 * 8));
+  CV_TRY(cv_ensure(h, h->varfinal, (size_t)K * 4 * 8));
+  CV_TRY(cv_ensure(h, h->variab, (size_t)K * 8));
+  CV_TRY(cv_ensure(h, h->work_ctr, 64));
+  CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
+  if (keep_sums) {
+    CV_TRY(cv_ensure(h, h->obs, (size_t)K * N * 8));
+    CV_TRY(cv_ensure(h, h->samp, (size_t)K * B * N * 8));
+  }
+  h->kept_sums = keep_sums != 0;
+  ContractParams prm;
+  prm.P = (int)P; prm.N = (int)N; prm.K = (int)K; prm.B = B; prm.W = W; prm.T = T;
+  prm.n_items = (int64_t)T * K;
+  prm.annoptr = h->annoptr.as<int64_t>();
+  prm.annoidx = h->annoidx.as<int32_t>();
+  prm.bgT = h->bgT.as<int32_t>();
+  prm.rowptr = h->rowptr.as<uint32_t>();
+  prm.entries = h->entries.as<uint32_t>();
+  prm.etab = h->etab.as<double>();
+  prm.fps = h->fps.as<double>();
+  prm.order = h->order.as<int32_t>();
+  prm.work_ctr = h->work_ctr.as<uint32_t>();
+  prm.dev_rm = h->dev_rm.as<double>();
+  prm.z_rm = h->z_rm.as<double>();
+  prm.varpart = h->varpart.as<double>();
+  prm.obs = keep_sums ? h->obs.as<long long>() : nullptr;
+  prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
+  prm.upd_ctr = reinterpret_cast<unsigned long long*>(h->work_ctr.as<uint32_t>() + 2);
+  const size_t smem = (size_t)I * W * acc_bytes;
+  CV_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+  if (wide) CV_TRY(launch_contract<long long>(h, prm, smem));
+  else CV_TRY(launch_contract<int>(h, prm, smem));
+  CV_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
+
+  // ---- stage 3: variability merge + ABI layout ----------------------------------------------
+  CV_LAUNCH(h, k_var_merge, (unsigned)((K + 127) / 128), 128, 0, h->varpart.as<double>(), (int)K, T,
+            h->varfinal.as<double>(), h->variab.as<double>());
+  CV_TRY(cv_ensure(h, h->dev_cm, (size_t)K * N * 8));
+  CV_TRY(cv_ensure(h, h->z_cm, (size_t)K * N * 8));
+  {
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((K + 31) / 32));
+    CV_LAUNCH(h, k_transpose<double>, grid, 256, 0, h->dev_rm.as<double>(), h->dev_cm.as<double>(), K, N);
+    CV_LAUNCH(h, k_transpose<double>, grid, 256, 0, h->z_rm.as<double>(), h->z_cm.as<double>(), K, N);
+  }
+  CV_CUDA(h, cudaEventRecord(h->ev[5], h->stream));
+  uint32_t flags = 0;
+  unsigned long long upd = 0;
+  CV_CUDA(h, cudaMemcpyAsync(&flags, h->flags.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaMemcpyAsync(&upd, h->work_ctr.as<uint32_t>() + 2, 8, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (flags & 16u)
+    CV_FAIL(h, CV_ERR_INVALID, "All peaks must have at least one fragment in one sample");
+  if (flags & FLAG_BADIDX)
+    CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
+  float ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->st.ms_counts_layout = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->st.ms_anno_prep = ms;
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->st.ms_contract = ms;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->st.ms_finalize = ms;
+  h->st.contract_updates = (int64_t)upd;
+  // gather model: every visited entry is a 4-byte load, plus the
+  // compulsory one-time traffic (layout, annotation lists, background rows, outputs)
+  h->st.contract_bytes = (int64_t)upd * 4 + h->n_entries * 4 + (int64_t)T * P * 4 +
+                         h->nnzA * 4 * T + (int64_t)P * B * 4 + 2 * K * N * 8;
+  h->st.path = 0;
+  h->st.acc_bytes = acc_bytes;
+  h->have_results = true;
+  return CV_OK;
+}
+
+extern "C" int cv_deviations_download(cv_handle* h, double* out_dev, double* out_z,
+                                      double* out_matches, double* out_overlap,
+                                      double* out_variability, int64_t* out_observed,
+                                      int64_t* out_sampled) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no results: call cv_deviations_compute first");
+  const int64_t N = h->N, K = h->K;
+  const int B = h->B;
+  double t0 = wall_ms();
+  int64_t bytes = 0;
+  if (out_dev) { CV_CUDA(h, cudaMemcpyAsync(out_dev, h->dev_cm.p, (size_t)K * N * 8, cudaMemcpyDeviceToHost, h->stream)); bytes += K * N * 8; }
+  if (out_z) { CV_CUDA(h, cudaMemcpyAsync(out_z, h->z_cm.p, (size_t)K * N * 8, cudaMemcpyDeviceToHost, h->stream)); bytes += K * N * 8; }
+  if (out_matches) { CV_CUDA(h, cudaMemcpyAsync(out_matches, h->matches.p, (size_t)K * 8, cudaMemcpyDeviceToHost, h->stream)); bytes += K * 8; }
+  if (out_overlap) { CV_CUDA(h, cudaMemcpyAsync(out_overlap, h->overlap.p, (size_t)K * 8, cudaMemcpyDeviceToHost, h->stream)); bytes += K * 8; }
+  if (out_variability) { CV_CUDA(h, cudaMemcpyAsync(out_variability, h->variab.p, (size_t)K * 8, cudaMemcpyDeviceToHost, h->stream)); bytes += K * 8; }
+  if (out_observed || out_sampled) {
+    if (!h->kept_sums) CV_FAIL(h, CV_ERR_STATE, "integer sums were not kept (keep_sums = 0)");
+    if (out_observed) {
+      // device holds [K][N]; ABI wants K x N column-major
+      CV_TRY(cv_ensure(h, h->tmp1, (size_t)K * N * 8));
+      dim3 grid((unsigned)((N + 31) / 32), (unsigned)((K + 31) / 32));
+      CV_LAUNCH(h, k_transpose<long long>, grid, 256, 0, h->obs.as<long long>(), h->tmp1.as<long long>(), K, N);
+      CV_CUDA(h, cudaMemcpyAsync(out_observed, h->tmp1.p, (size_t)K * N * 8, cudaMemcpyDeviceToHost, h->stream));
+      bytes += K * N * 8;
+    }
+    if (out_sampled) {
+      CV_CUDA(h, cudaMemcpyAsync(out_sampled, h->samp.p, (size_t)K * B * N * 8, cudaMemcpyDeviceToHost, h->stream));
+      bytes += K * B * N * 8;
+    }
+  }
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->st.ms_d2h = wall_ms() - t0;
+  h->st.d2h_bytes = bytes;
+  return CV_OK;
+}
+
+extern "C" int cv_deviations(cv_handle* h, int64_t K, const int64_t* annoptr,
+                             const int32_t* annoidx, int index_base, const int32_t* bg, int B,
+                             const double* expectation, double* out_dev, double* out_z,
+                             double* out_matches, double* out_overlap, double* out_variability,
+                             int64_t* out_observed, int64_t* out_sampled) {
+  if (!h) return CV_ERR_INVALID;
+  CV_TRY(cv_deviations_upload(h, K, annoptr, annoidx, index_base, bg, B, expectation));
+  double h2d_ms = h->st.ms_h2d;
+  int64_t h2d_b = h->st.h2d_bytes;
+  CV_TRY(cv_deviations_compute(h, 0, (out_observed || out_sampled) ? 1 : 0));
+  CV_TRY(cv_deviations_download(h, out_dev, out_z, out_matches, out_overlap, out_variability,
+                                out_observed, out_sampled));
+  h->st.ms_h2d = h2d_ms;
+  h->st.h2d_bytes = h2d_b;
+  return CV_OK;
+}
+
+extern "C" int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t* n_elems) {
+  if (!h || !dptr) return CV_ERR_INVALID;
+  if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no results");
+  *dptr = h->varfinal.p;
+  if (n_elems) *n_elems = h->K * 4;
+  return CV_OK;
+}
+
+// host-side merge of per-shard (n, mean, M2, n_nonfinite) tables, Chan et al. parallel formula
+extern "C" int cv_merge_variability(const double* parts, int n_parts, int64_t K, int na_rm,
+                                    double* out_sd) {
+  if (!parts || !out_sd || n_parts < 1 || K < 0) return CV_ERR_INVALID;
+  const double nan = __builtin_nan("");
+  for (int64_t k = 0; k < K; ++k) {
+    double n = 0, mean = 0, m2 = 0, nf = 0;
+    for (int s = 0; s < n_parts; ++s) {
+      const double* q = parts + ((int64_t)s * K + k) * 4;
+      nf += q[3];
+      if (q[0] == 0) continue;
+      if (n == 0) { n = q[0]; mean = q[1]; m2 = q[2]; continue; }
+      double tot = n + q[0], d = q[1] - mean;
+      mean += d * (q[0] / tot);
+      m2 += q[2] + d * d * (n * q[0] / tot);
+      n = tot;
+    }
+    if (!na_rm && nf > 0) out_sd[k] = nan;          // arma::stddev over a row holding NaN
+    else out_sd[k] = n > 1 ? sqrt(m2 / (n - 1)) : nan;
+  }
+  return CV_OK;
+}

@@ -1,0 +1,153 @@
+// Internal declarations shared by the translation units of libchromvar_b200.so.
+// Nothing here crosses the C ABI (include/chromvar_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/chromvar_b200.h"
+
+#define CV_NUM_SMS_FALLBACK 148
+
+// ---- error plumbing -------------------------------------------------------------------
+#define CV_FAIL(h, code, ...)                                \
+  do {                                                       \
+    char _b[512];                                            \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                   \
+    (h)->err = _b;                                           \
+    return (code);                                           \
+  } while (0)
+
+#define CV_CUDA(h, expr)                                                               \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      cudaGetLastError();                                                              \
+      CV_FAIL(h, (_e == cudaErrorMemoryAllocation ? CV_ERR_OOM : CV_ERR_CUDA),         \
+              "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,  \
+              cudaGetErrorString(_e));                                                 \
+    }                                                                                  \
+  } while (0)
+
+#define CV_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != CV_OK) return _rc; \
+  } while (0)
+
+// kernel launch wrapper: counts launches (cv_stats.kernel_launches) and checks the launch
+#define CV_LAUNCH(h, kernel, grid, block, smem, ...)                         \
+  do {                                                                       \
+    kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);           \
+    (h)->launches++;                                                         \
+    CV_CUDA(h, cudaGetLastError());                                          \
+  } while (0)
+
+// ---- grow-only device buffer -------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct cv_handle {
+  int device = 0;
+  int num_sms = CV_NUM_SMS_FALLBACK;
+  int max_smem_optin = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- counts (raw input format, device resident) ----
+  int64_t P = 0, N = 0, nnz = 0;
+  bool have_counts = false;
+  bool totals_committed = false;   // per-peak totals are global (single shard or after commit)
+  DevBuf colptr;     // int64[N+1]
+  DevBuf rowidx;     // int32[nnz]
+  DevBuf val;        // uint32[nnz]   (validated integer counts)
+  DevBuf xraw;       // staging for the uploaded x / dense input
+  DevBuf peak_tot;   // int64[P+1], slot P = grand total (this shard, or global after commit)
+  DevBuf peak_loc;   // int64[P+1] local copy kept when totals get all-reduced
+  DevBuf cell_tot;   // int64[N]
+  DevBuf fps;        // double[N]  fragments per sample
+  DevBuf flags;      // uint32[8] device-side validation flags / counters
+  uint32_t max_val = 0;
+
+  // ---- cell-tiled row layout of the counts (derived) ----
+  bool layout_valid = false;
+  int W = 0, T = 0;  // cells per tile, number of tiles
+  int64_t n_entries = 0;
+  DevBuf tcnt;       // uint32[T*P]   per (tile,row) entry counts, reused as fill cursor
+  DevBuf rowptr;     // uint32[T*P+1]
+  DevBuf entries;    // uint32[n_entries] : cell_in_tile << 20 | value
+  DevBuf scan_tmp;
+
+  // ---- annotations / background / expectation (raw + derived) ----
+  bool have_anno = false;
+  int64_t K = 0, nnzA = 0;
+  int B = 0;
+  std::vector<int64_t> h_annoptr;
+  DevBuf annoptr;    // int64[K+1]
+  DevBuf anno_raw;   // int32[nnzA] as uploaded (index_base)
+  DevBuf annoidx;    // int32[nnzA] 0-based
+  DevBuf bg_raw;     // int32[P*B] as uploaded (col-major, index_base)
+  int index_base = 1;
+  DevBuf bgT;        // int32[P][B] 0-based
+  DevBuf expect;     // double[P]
+  DevBuf etab;       // double[K][B+1]
+  DevBuf overlap;    // double[K]
+  DevBuf matches;    // double[K]
+  DevBuf mark;       // int32[grid][P] scratch for the overlap count
+  DevBuf order;      // int32[K] annotations by decreasing set size
+  DevBuf work_ctr;   // uint32 dynamic work counters
+
+  // ---- results (device) ----
+  bool have_results = false;
+  DevBuf dev_rm, z_rm;     // double[K][N] row-major
+  DevBuf dev_cm, z_cm;     // double K x N col-major (ABI layout)
+  DevBuf varpart;          // double[K][T][4]
+  DevBuf varfinal;         // double[K][4]
+  DevBuf variab;           // double[K]
+  DevBuf obs, samp;        // int64 parity outputs
+  bool kept_sums = false;
+
+  // background sampler / compat-routine buffers (cv_background.cu, cv_compat.cu)
+  DevBuf bk[16];
+
+  // generic scratch
+  DevBuf tmp0, tmp1, tmp2;
+
+  cv_stage_stats st = {};
+};
+
+int cv_ensure(cv_handle* h, DevBuf& b, size_t bytes);
+void cv_release(DevBuf& b);
+int cv_sync_check(cv_handle* h);
+
+// cv_counts.cu
+int cv_build_layout(cv_handle* h, int W);
+// cv_background.cu: shared sampler back half (bin CDF rows + Philox draws)
+int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
+                         const double* d_binp_colmajor, const double* d_bin_xy, double w,
+                         int niter, int32_t* host_out, double* host_binprob, double* host_density);
+// cv_deviations.cu
+int cv_choose_tile(cv_handle* h, int B, int acc_bytes, int* W_out);
+
+// ---- small device helpers -----------------------------------------------------------------
+__device__ __forceinline__ double cv_na_real() {
+  return __longlong_as_double((long long)CV_NA_REAL_BITS);
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

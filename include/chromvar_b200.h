@@ -1,0 +1,172 @@
+/*
+ * chromvar_b200.h -- C ABI of libchromvar_b200.so, the B200-native deviation engine.
+ *
+ * This is the drop-in boundary for chromVAR's hot path
+ *   computeExpectations -> getBackgroundPeaks -> compute_deviations_core -> computeVariability.
+ * Plain C: pointers and sizes only, no R / Rcpp / torch types.  Every entry point cites the
+ * reference interface it replaces (paths relative to the chromVAR 1.5.0 tree).  The reference
+ * binds native code through `.Call` into registered routines (src/RcppExports.cpp:59-137,
+ * R/RcppExports.R:20-38); INTEGRATION.md shows the `.Call` glue a maintainer adds for each
+ * function below.
+ *
+ * Conventions
+ *   - Matrices are column-major (R layout).  z / deviations are K x N (annotation = row).
+ *   - Peak indices crossing the ABI carry an explicit `index_base` (R passes 1).
+ *   - Caller allocates every output; the library keeps no host pointer after return.
+ *   - Every call returns 0 (CV_OK) or an error code; cv_last_error() gives the message.  Nothing
+ *     throws or longjmps across the ABI.  There is no CPU fallback: without a usable sm_100
+ *     device cv_create fails.
+ *   - NA: entries the reference sets to NA (R/compute_deviations.R:458-461,517-520) are written
+ *     as R's NA_real_ bit pattern 0x7FF00000000007A2.
+ *   - One handle = one GPU.  Cells (columns of the counts matrix) shard across handles /
+ *     processes; the two cross-shard reductions are exposed as device buffers so the host can
+ *     run NCCL on them (cv_peak_totals_device, cv_variability_partials_device).
+ */
+#ifndef CHROMVAR_B200_H
+#define CHROMVAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cv_handle cv_handle;
+
+enum {
+  CV_OK = 0,
+  CV_ERR_INVALID = 1,     /* bad argument / input fails the reference's own checks */
+  CV_ERR_CUDA = 2,        /* CUDA runtime error (message holds cudaGetErrorString) */
+  CV_ERR_OOM = 3,         /* device or pinned-host allocation failed */
+  CV_ERR_STATE = 4,       /* call order: e.g. deviations before counts were set */
+  CV_ERR_UNSUPPORTED = 5  /* shape outside what the kernels cover (message says which) */
+};
+
+/* element types for the polymorphic inputs */
+enum { CV_I32 = 0, CV_I64 = 1, CV_F64 = 2, CV_U8 = 3, CV_F32 = 4 };
+
+/* R's NA_real_ payload */
+#define CV_NA_REAL_BITS 0x7FF00000000007A2ULL
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  seed: keys the Philox streams of the samplers (R shim derives it from
+ * R's RNG so set.seed() keeps run-to-run reproducibility; the reference uses Rcpp::RNGScope,
+ * src/RcppExports.cpp:88,100). */
+int cv_create(int device, uint64_t seed, cv_handle** out);
+void cv_destroy(cv_handle* h);
+const char* cv_last_error(const cv_handle* h); /* h == NULL: last error of a failed cv_create */
+int cv_version(void);
+int cv_set_seed(cv_handle* h, uint64_t seed);
+/* the CUDA stream all of this handle's kernels run on (a cudaStream_t), for event timing */
+void* cv_stream(cv_handle* h);
+
+/* ---- counts (assay "counts"; replaces the dgCMatrix / matrix the reference passes around) -- */
+/* CSC as in Matrix::dgCMatrix: colptr (N+1, @p, CV_I32 or CV_I64), rowidx (@i, 0-based int32),
+ * x (@x; CV_F64 as R stores it, or CV_I32 / CV_U8).  Values must be finite, >= 0 and
+ * integer-valued (counts_check, R/utils.R:3-12).  nnz < 2^32 per handle. */
+int cv_set_counts_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr, int colptr_type,
+                      const int32_t* rowidx, const void* x, int x_type);
+/* dense column-major P x N (base matrix / dgeMatrix input; bulk ATAC, config 4) */
+int cv_set_counts_dense(cv_handle* h, int64_t P, int64_t N, const void* x, int x_type);
+
+/* getFragmentsPerPeak / getFragmentsPerSample / getTotalFragments
+ * (R/helper_functions.R:48-58, 64-74, 79-89).  Any output may be NULL. */
+int cv_fragments(cv_handle* h, double* out_per_peak /*P*/, double* out_per_sample /*N*/,
+                 double* out_total /*1*/);
+/* Multi-GPU: device pointer to this shard's per-peak totals, int64[P+1] (slot P = grand total).
+ * The host all-reduces (sum) that buffer across shards (NCCL) and then calls
+ * cv_peak_totals_commit so expectations / background sampling use the global totals. */
+int cv_peak_totals_device(cv_handle* h, void** dptr, int64_t* n_elems);
+int cv_peak_totals_commit(cv_handle* h);
+
+/* computeExpectations -> compute_expectations_core (R/compute_deviations.R:415-448).
+ * norm: 0/1.  group: NULL or N labels in 0..n_groups-1 (factor codes - 1). out_e: P doubles.
+ * (norm / group variants are per-shard quantities; with sharded cells only the default
+ * variant is defined across shards.) */
+int cv_expectations(cv_handle* h, int norm, const int32_t* group, int n_groups, double* out_e);
+
+/* ---- getBackgroundPeaks -> get_background_peaks_core (R/background_peaks.R:116-156) -------- */
+/* bias: P doubles.  out_bg: P x niter column-major, 1-based peak indices (the reference returns
+ * the same matrix as doubles).  Optional debug outputs (NULL to skip):
+ *   out_trans P x 2 col-major (trans_norm_mat), out_membership P (1-based bin of each peak),
+ *   out_density bs^2, out_binprob bs^2 x bs^2 row-major: row i = destination-bin distribution
+ *   of a peak in bin i (what src/utils.cpp:83-99 induces). */
+int cv_background_peaks(cv_handle* h, const double* bias, int niter, double w, int bs,
+                        int32_t* out_bg, double* out_trans, int32_t* out_membership,
+                        double* out_density, double* out_binprob);
+
+/* ---- computeDeviations -> compute_deviations_core (R/compute_deviations.R:355-408), the whole
+ * bplapply fan-out over compute_deviations_single (:451-537) in one call -------------------- */
+/* annoptr: K+1 offsets into annoidx; annoidx: peak indices (index_base 0 or 1; duplicates keep
+ * their multiplicity like sparseMatrix does, :480-484).  bg: P x B col-major int32 peak indices
+ * (same index_base).  expectation: P doubles.
+ * Outputs: out_dev, out_z K x N col-major; out_matches, out_overlap K (fractionMatches,
+ * fractionBackgroundOverlap, :398-401); out_variability K or NULL (row SD of z over this
+ * handle's cells, finite entries only = row_sds(z, TRUE), src/utils.cpp:9-25);
+ * parity outputs or NULL: out_observed K x N col-major int64 (observed, :486),
+ * out_sampled [K][B][N] int64, N fastest (sampled, :501). */
+int cv_deviations(cv_handle* h, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
+                  int index_base, const int32_t* bg, int B, const double* expectation,
+                  double* out_dev, double* out_z, double* out_matches, double* out_overlap,
+                  double* out_variability, int64_t* out_observed, int64_t* out_sampled);
+
+/* The same call split in three so a caller (bench.py `value`, repeated-set callers such as
+ * R/variability_synergy.R:173-177) can keep inputs resident in HBM:
+ *   upload   : H2D of annotations / background / expectation (raw input formats only)
+ *   compute  : every kernel of the path on resident inputs; results stay on the device.
+ *              rebuild_counts_layout != 0 also redoes the counts layout pass (what a fresh
+ *              cv_set_counts_* triggers) so a timed step covers all derived work.
+ *   download : D2H of the results (any pointer may be NULL). */
+int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
+                         int index_base, const int32_t* bg, int B, const double* expectation);
+int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, int keep_sums);
+int cv_deviations_download(cv_handle* h, double* out_dev, double* out_z, double* out_matches,
+                           double* out_overlap, double* out_variability, int64_t* out_observed,
+                           int64_t* out_sampled);
+/* Multi-GPU computeVariability: device pointer to double[K][4] = (n_finite, mean, M2,
+ * n_nonfinite) of this shard's z rows; shards are merged with cv_merge_variability. */
+int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t* n_elems);
+/* merge n_parts partial tables (host memory, each K x 4) -> sd[K] (n-1 denominator) */
+int cv_merge_variability(const double* parts, int n_parts, int64_t K, int na_rm, double* out_sd);
+
+/* ---- the reference's five registered native routines (src/RcppExports.cpp:59-119) --------- */
+/* row_sds(x, na_rm)  src/utils.cpp:9-25.  x: K x N col-major. */
+int cv_row_sds(cv_handle* h, int64_t K, int64_t N, const double* x, int na_rm, double* out_sd);
+/* row_sds_perm(x, na_rm)  src/utils.cpp:28-33, batched: n_rep bootstrap replicates at once
+ * (R/compute_variability.R:57-60 calls it bootstrap_samples times).  out: n_rep x K row-major. */
+int cv_row_sds_perm(cv_handle* h, int64_t K, int64_t N, const double* x, int na_rm, int n_rep,
+                    double* out_sd);
+/* ProbSampleReplace(size, prob)  src/utils.cpp:38-77.  out: size 1-based indices. */
+int cv_prob_sample_replace(cv_handle* h, int64_t size, int64_t n, const double* prob,
+                           int32_t* out);
+/* bg_sample_helper(bin_membership, bin_p, bin_density, niterations)  src/utils.cpp:83-99.
+ * bin_membership: P 0-based bins; bin_p: nb x nb col-major; bin_density: nb.
+ * out: P x niter col-major, 1-based. */
+int cv_bg_sample_helper(cv_handle* h, int64_t P, const int32_t* bin_membership, int64_t nb,
+                        const double* bin_p, const double* bin_density, int niter, int32_t* out);
+/* euc_dist(x)  src/utils.cpp:107-117.  x: n x d col-major -> out n x n. */
+int cv_euc_dist(cv_handle* h, int64_t n, int64_t d, const double* x, double* out);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+typedef struct cv_stage_stats {
+  double ms_counts_layout;   /* row/col sums + cell-tiled row layout build (K1) */
+  double ms_anno_prep;       /* background transpose + expected-fraction table + overlap */
+  double ms_contract;        /* gather-contraction + fused epilogue (K5+K6+K7): dominant kernel */
+  double ms_finalize;        /* variability merge + K x N transposes */
+  double ms_h2d, ms_d2h;     /* host<->device copies of the last call (wall clock) */
+  double ms_background;      /* last cv_background_peaks, device time */
+  int64_t contract_updates;  /* (B+1) * sum_k sum_{p in set_k} nnz(counts row) actually visited */
+  int64_t contract_bytes;    /* algorithmic bytes of the gather model, DESIGN.md section 4 */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t kernel_launches;   /* kernels launched by this handle since creation */
+  int32_t path;              /* 0 = cell-tiled row-gather SpMM, 1 = dense tcgen05 */
+  int32_t cell_tile;         /* W */
+  int32_t n_cell_tiles;
+  int32_t acc_bytes;         /* accumulator width used (4 or 8) */
+} cv_stage_stats;
+int cv_stats(cv_handle* h, cv_stage_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMVAR_B200_H */
