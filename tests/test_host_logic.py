@@ -1,0 +1,70 @@
+"""Host-side logic of the R-API mirror that needs no GPU: input marshalling, validation order
+and messages (R/compute_deviations.R:362-379, R/utils.R:3-27,289-300), BH adjustment."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from chromvar_b200 import api
+from oracle import chromvar_oracle as orc
+
+
+def test_convert_to_ix_list_dense_and_sparse():
+    rng = np.random.default_rng(0)
+    M = rng.random((40, 6)) < 0.2
+    ptr, idx = api.convert_to_ix_list(M)
+    ref = orc.convert_to_ix_list(M)
+    assert [list(idx[ptr[k]:ptr[k + 1]]) for k in range(6)] == [list(r) for r in ref]
+    ptr2, idx2 = api.convert_to_ix_list(sp.csr_matrix(M))
+    assert np.array_equal(ptr, ptr2) and np.array_equal(idx, idx2)
+    # quirk kept: an explicitly stored FALSE counts as a match for sparse input (summary() triplets)
+    S = sp.csc_matrix((np.array([True, False, True]), (np.array([0, 3, 5]), np.array([0, 0, 1]))), shape=(8, 2))
+    ptr3, idx3 = api.convert_to_ix_list(S)
+    assert list(ptr3) == [0, 2, 3] and list(idx3) == [1, 4, 6]
+
+
+def test_annotation_validation_messages():
+    C = np.ones((5, 3))
+    bg = np.ones((5, 4), np.int32)
+    e = np.full(5, 0.2)
+    with pytest.raises(ValueError, match="Annotations are not valid"):
+        api.computeDeviations(C, [[1.5, 2]], bg, e)
+    with pytest.raises(ValueError, match="Annotations are not valid"):
+        api.computeDeviations(C, [[], []], bg, e)
+    with pytest.raises(ValueError, match="Annotations are not valid"):
+        api.computeDeviations(C, [[0, 1]], bg, e)
+    with pytest.raises(ValueError, match="Annotations are not valid"):
+        api.computeDeviations(C, [[1, 6]], bg, e)
+    with pytest.raises(ValueError, match="nrow"):
+        api.computeDeviations(C, [[1, 2]], np.ones((4, 4), np.int32), e)
+    with pytest.raises(ValueError, match="length\\(expectation\\)"):
+        api.computeDeviations(C, [[1, 2]], bg, np.full(4, 0.25))
+    with pytest.raises(TypeError, match="background_peaks"):
+        api.computeDeviations(C, [[1, 2]])        # matrix method has no default (:298-353)
+
+
+def test_counts_and_matches_check():
+    with pytest.raises(ValueError):
+        api.counts_check(api.SummarizedExperiment({"notcounts": np.ones((2, 2))}))
+    with pytest.raises(ValueError):
+        api.counts_check(api.SummarizedExperiment({"counts": np.array([[1.0, -1.0], [0, 1]])}))
+    with pytest.raises(ValueError):
+        api.counts_check(api.SummarizedExperiment({"counts": np.ones((3, 1))}))
+    with pytest.raises(ValueError):
+        api.matches_check(api.SummarizedExperiment({"foo": np.ones((2, 2))}))
+    se = api.SummarizedExperiment({"motifMatches": np.eye(2, dtype=bool)})
+    assert api.annotationMatches(se) is se.assays["motifMatches"]
+    with pytest.raises(ValueError):
+        api.chromVARDeviations({"z": np.ones((1, 1))})
+
+
+def test_group_argument_validation():
+    C = np.ones((4, 3))
+    with pytest.raises(ValueError, match="Group must be vector"):
+        api.computeExpectations(C, group=[1, 2])
+
+
+def test_bh_adjust_matches_oracle():
+    rng = np.random.default_rng(1)
+    p = rng.random(50)
+    p[[3, 9]] = np.nan
+    assert np.allclose(api._p_adjust_bh(p), orc.p_adjust_bh(p), equal_nan=True)
