@@ -193,6 +193,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     eng = _lib.Handle(local, seed=20173)
+    eng.set_option("path", args.path)
     d, name = make_workload(rank, args.cells, args.quick)
     C = d["counts"]
     P, N = C.shape
@@ -238,7 +239,7 @@ def run_ours(args):
     sampler.start()
     barrier()
     step_ms, contract_ms, stage_acc = [], [], np.zeros(4)
-    upd = bytes_alg = 0
+    upd = bytes_alg = path = 0
     for _ in range(args.steps):
         with torch.cuda.stream(ext):
             flush.zero_()                                # L2 flush between timed iterations
@@ -251,7 +252,7 @@ def run_ours(args):
         st = eng.stats()
         contract_ms.append(st["ms_contract"])
         stage_acc += [st["ms_counts_layout"], st["ms_anno_prep"], st["ms_contract"], st["ms_finalize"]]
-        upd, bytes_alg = st["contract_updates"], st["contract_bytes"]
+        upd, bytes_alg, path = st["contract_updates"], st["contract_bytes"], st["path"]
     barrier()
     clocks = sampler.stop()
     launches = eng.stats()["kernel_launches"] - launches0
@@ -294,14 +295,27 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (k_contract) ------------------------------------------------
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
     peaks, peaks_kind = peaks_json()
     c_ms = float(np.mean(contract_ms))
-    achieved = bytes_alg / (c_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-            "peak_kind": peaks_kind, "ms_per_launch": c_ms, "algorithmic_bytes_per_launch": int(bytes_alg),
-            "updates_per_launch": int(upd), "share_of_step": c_ms / (total_ms / args.steps)}
+    share = c_ms / (total_ms / args.steps)
+    if path == 1:
+        # dense tcgen05 path: algorithmic ops = 2 (B+1) K P N, int8 peak = 2 x the
+        # measured bf16 figure (sustained: the kernel runs inside a multi-step loop)
+        flops = 2.0 * (NITER + 1) * K * P * N
+        peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        achieved = flops / (c_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_dense_contract", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_kind": peaks_kind +
+                " (2 x bf16 sustained = int8 dense)", "peak_burst": 2.0 * peaks["bf16_tflops"],
+                "ms_per_launch": c_ms, "algorithmic_ops_per_launch": flops,
+                "padded_ops_per_launch": eng.stats()["contract_flops"], "share_of_step": share}
+    else:
+        achieved = bytes_alg / (c_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_kind": peaks_kind, "ms_per_launch": c_ms, "algorithmic_bytes_per_launch": int(bytes_alg),
+                "updates_per_launch": int(upd), "share_of_step": share}
 
     # ---- CPU baseline beside it (N=1 only): bounded sample of the same workload ---------------
     cpu = None
@@ -315,10 +329,13 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32 sums, f64 epilogue", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 x u8 -> s32 (tcgen05), f64 epilogue" if path == 1 else "int32 sums, f64 epilogue",
+        "data": "synthetic",
         "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
                    "niterations": NITER, "nnz_per_gpu": nnz, "nnz_annotations": int(d["annoptr"][-1]),
-                   "l2": "256 MB flush write between timed steps", "cell_tile": eng.stats()["cell_tile"]},
+                   "l2": "256 MB flush write between timed steps", "cell_tile": eng.stats()["cell_tile"],
+                   "path": "dense_tcgen05" if path == 1 else "row_gather_spmm"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e},
         "gpu_launches": int(launches),
@@ -343,6 +360,7 @@ def main():
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (default: config 2's 10000)")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
     args = ap.parse_args()
     if args.warmup < 3 and not args.quick and args.impl == "ours":
         log("[bench] warning: fewer than 3 warm-up steps")

@@ -22,7 +22,7 @@ _DTYPE_TAG = {np.dtype(np.int32): CV_I32, np.dtype(np.int64): CV_I64,
 
 # every symbol include/chromvar_b200.h declares (tests check the library exports them all)
 EXPORTS = [
-    "cv_create", "cv_destroy", "cv_last_error", "cv_version", "cv_set_seed", "cv_stream",
+    "cv_create", "cv_destroy", "cv_last_error", "cv_version", "cv_set_seed", "cv_set_option", "cv_stream",
     "cv_set_counts_csc", "cv_set_counts_dense", "cv_fragments", "cv_peak_totals_device",
     "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_deviations",
     "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_download",
@@ -36,6 +36,7 @@ class StageStats(C.Structure):
         ("ms_counts_layout", C.c_double), ("ms_anno_prep", C.c_double),
         ("ms_contract", C.c_double), ("ms_finalize", C.c_double),
         ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("ms_background", C.c_double),
+        ("contract_flops", C.c_double),
         ("contract_updates", C.c_int64), ("contract_bytes", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64),
         ("path", C.c_int32), ("cell_tile", C.c_int32), ("n_cell_tiles", C.c_int32),
@@ -75,6 +76,7 @@ def load(build_if_missing=True):
         "cv_version": (i32, []),
         "cv_set_seed": (i32, [vp, u64]),
         "cv_stream": (vp, [vp]),
+        "cv_set_option": (i32, [vp, C.c_char_p, i64]),
         "cv_set_counts_csc": (i32, [vp, i64, i64, vp, i32, vp, vp, i32]),
         "cv_set_counts_dense": (i32, [vp, i64, i64, vp, i32]),
         "cv_fragments": (i32, [vp, vp, vp, vp]),
@@ -330,6 +332,9 @@ class Handle:
 
     def set_seed(self, seed):
         self._check(self.lib.cv_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
+
+    def set_option(self, key, value):
+        self._check(self.lib.cv_set_option(self._h, key.encode(), int(value)))
 
     def stats(self):
         s = StageStats()

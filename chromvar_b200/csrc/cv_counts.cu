@@ -106,7 +106,7 @@ extern "C" void cv_destroy(cv_handle* h) {
                     &h->scan_tmp, &h->annoptr, &h->anno_raw, &h->annoidx, &h->bg_raw, &h->bgT, &h->expect,
                     &h->etab, &h->overlap, &h->matches, &h->mark, &h->order, &h->work_ctr,
                     &h->dev_rm, &h->z_rm, &h->dev_cm, &h->z_cm, &h->varpart, &h->varfinal,
-                    &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2};
+                    &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C};
   for (DevBuf* b : bufs) cv_release(*b);
   for (DevBuf& b : h->bk) cv_release(b);
   for (int i = 0; i < 8; ++i)
@@ -123,6 +123,16 @@ extern "C" int cv_set_seed(cv_handle* h, uint64_t seed) {
   if (!h) return CV_ERR_INVALID;
   h->seed = seed;
   return CV_OK;
+}
+
+extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
+  if (!h || !key) return CV_ERR_INVALID;
+  if (!strcmp(key, "path")) {
+    if (value < 0 || value > 2) CV_FAIL(h, CV_ERR_INVALID, "path must be 0 (auto), 1 (row-gather SpMM) or 2 (dense tcgen05)");
+    h->opt_path = (int)value;
+    return CV_OK;
+  }
+  CV_FAIL(h, CV_ERR_INVALID, "unknown option %s", key);
 }
 
 extern "C" void* cv_stream(cv_handle* h) { return h ? (void*)h->stream : nullptr; }

@@ -465,21 +465,31 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
   const int B = h->B, I = B + 1;
   h->have_results = false;
 
-  // accumulator width: |sum| <= (largest set) * (largest count)
+  // accumulator width of the row-gather path: |sum| <= (largest set) * (largest count)
   int64_t set_max = 0;
   for (int64_t k = 0; k < K; ++k) set_max = std::max(set_max, h->h_annoptr[k + 1] - h->h_annoptr[k]);
   const bool wide = (double)set_max * (double)h->max_val >= 2147483647.0;
   const int acc_bytes = wide ? 8 : 4;
-  int W = 0;
-  CV_TRY(cv_choose_tile(h, B, acc_bytes, &W));
 
-  // ---- stage 0: counts layout (derived from the resident CSC) -----------------------------
-  CV_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-  if (rebuild_counts_layout || !h->layout_valid || h->W != W) CV_TRY(cv_build_layout(h, W));
-  const int T = h->T;
-  CV_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+  // ---- path selection: dense tcgen05 GEMM vs. cell-tiled row-gather SpMM -----------------------
+  // sparse cost: (B+1) * nnzA * (nnz / P) entry updates at the measured rate of k_contract;
+  // dense cost: the padded u8 GEMM at a sustained tensor rate (cv_dense_cost_ms).
+  int use_dense = 0;
+  {
+    std::string why;
+    const int feasible = cv_dense_feasible(h, &why);
+    if (h->opt_path == 2) {
+      if (!feasible) CV_FAIL(h, CV_ERR_UNSUPPORTED, "dense path requested but not applicable: %s", why.c_str());
+      use_dense = 1;
+    } else if (h->opt_path == 0 && feasible) {
+      const double updates = (double)I * (double)h->nnzA * ((double)h->nnz / (double)P);
+      const double sparse_ms = updates / 2.7e8 + 0.3;
+      use_dense = cv_dense_cost_ms(h) < sparse_ms;
+    }
+  }
 
   // ---- stage 1: annotation / background preparation ---------------------------------------
+  CV_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
   CV_TRY(cv_ensure(h, h->flags, 64));
   CV_CUDA(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
   CV_TRY(cv_ensure(h, h->bgT, (size_t)P * B * 4));
@@ -512,10 +522,9 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
   }
   CV_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
 
-  // ---- stage 2: contraction + fused epilogue -----------------------------------------------
+  // ---- stage 2: operand layout + contraction + fused epilogue -----------------------------------
   CV_TRY(cv_ensure(h, h->dev_rm, (size_t)K * N * 8));
   CV_TRY(cv_ensure(h, h->z_rm, (size_t)K * N * 8));
-  CV_TRY(cv_ensure(h, h->varpart, (size_t)K * T * 4 * 8));
   CV_TRY(cv_ensure(h, h->varfinal, (size_t)K * 4 * 8));
   CV_TRY(cv_ensure(h, h->variab, (size_t)K * 8));
   CV_TRY(cv_ensure(h, h->work_ctr, 64));
@@ -525,29 +534,45 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
     CV_TRY(cv_ensure(h, h->samp, (size_t)K * B * N * 8));
   }
   h->kept_sums = keep_sums != 0;
-  ContractParams prm;
-  prm.P = (int)P; prm.N = (int)N; prm.K = (int)K; prm.B = B; prm.W = W; prm.T = T;
-  prm.n_items = (int64_t)T * K;
-  prm.annoptr = h->annoptr.as<int64_t>();
-  prm.annoidx = h->annoidx.as<int32_t>();
-  prm.bgT = h->bgT.as<int32_t>();
-  prm.rowptr = h->rowptr.as<uint32_t>();
-  prm.entries = h->entries.as<uint32_t>();
-  prm.etab = h->etab.as<double>();
-  prm.fps = h->fps.as<double>();
-  prm.order = h->order.as<int32_t>();
-  prm.work_ctr = h->work_ctr.as<uint32_t>();
-  prm.dev_rm = h->dev_rm.as<double>();
-  prm.z_rm = h->z_rm.as<double>();
-  prm.varpart = h->varpart.as<double>();
-  prm.obs = keep_sums ? h->obs.as<long long>() : nullptr;
-  prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
-  prm.upd_ctr = reinterpret_cast<unsigned long long*>(h->work_ctr.as<uint32_t>() + 2);
-  const size_t smem = (size_t)I * W * acc_bytes;
-  CV_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
-  if (wide) CV_TRY(launch_contract<long long>(h, prm, smem));
-  else CV_TRY(launch_contract<int>(h, prm, smem));
-  CV_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
+  int T = 0;
+  if (use_dense) {
+    int soft = 0;
+    int rc = cv_dense_contract(h, keep_sums, &T, &soft);     // records ev[3], ev[4] around the GEMM
+    if (rc != CV_OK) {
+      if (soft && h->opt_path != 2) use_dense = 0;           // multiplicity bound failed: exact fallback
+      else return rc;
+    }
+  }
+  if (!use_dense) {
+    int W = 0;
+    CV_TRY(cv_choose_tile(h, B, acc_bytes, &W));
+    if (rebuild_counts_layout || !h->layout_valid || h->W != W) CV_TRY(cv_build_layout(h, W));
+    T = h->T;
+    CV_TRY(cv_ensure(h, h->varpart, (size_t)K * T * 4 * 8));
+    ContractParams prm;
+    prm.P = (int)P; prm.N = (int)N; prm.K = (int)K; prm.B = B; prm.W = W; prm.T = T;
+    prm.n_items = (int64_t)T * K;
+    prm.annoptr = h->annoptr.as<int64_t>();
+    prm.annoidx = h->annoidx.as<int32_t>();
+    prm.bgT = h->bgT.as<int32_t>();
+    prm.rowptr = h->rowptr.as<uint32_t>();
+    prm.entries = h->entries.as<uint32_t>();
+    prm.etab = h->etab.as<double>();
+    prm.fps = h->fps.as<double>();
+    prm.order = h->order.as<int32_t>();
+    prm.work_ctr = h->work_ctr.as<uint32_t>();
+    prm.dev_rm = h->dev_rm.as<double>();
+    prm.z_rm = h->z_rm.as<double>();
+    prm.varpart = h->varpart.as<double>();
+    prm.obs = keep_sums ? h->obs.as<long long>() : nullptr;
+    prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
+    prm.upd_ctr = reinterpret_cast<unsigned long long*>(h->work_ctr.as<uint32_t>() + 2);
+    const size_t smem = (size_t)I * W * acc_bytes;
+    CV_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+    if (wide) CV_TRY(launch_contract<long long>(h, prm, smem));
+    else CV_TRY(launch_contract<int>(h, prm, smem));
+    CV_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
+  }
 
   // ---- stage 3: variability merge + ABI layout ----------------------------------------------
   CV_LAUNCH(h, k_var_merge, (unsigned)((K + 127) / 128), 128, 0, h->varpart.as<double>(), (int)K, T,
@@ -570,17 +595,27 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
   if (flags & FLAG_BADIDX)
     CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
   float ms;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->st.ms_counts_layout = ms;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->st.ms_counts_layout = ms;   // operand layout of the chosen path
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->st.ms_anno_prep = ms;
   cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->st.ms_contract = ms;
   cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->st.ms_finalize = ms;
   h->st.contract_updates = (int64_t)upd;
   // gather model: every visited entry is a 4-byte load, plus the
   // compulsory one-time traffic (layout, annotation lists, background rows, outputs)
-  h->st.contract_bytes = (int64_t)upd * 4 + h->n_entries * 4 + (int64_t)T * P * 4 +
-                         h->nnzA * 4 * T + (int64_t)P * B * 4 + 2 * K * N * 8;
-  h->st.path = 0;
-  h->st.acc_bytes = acc_bytes;
+  if (use_dense) {
+    h->st.contract_bytes = 0;
+    h->st.contract_flops = h->dn_flops;
+    h->st.path = 1;
+    h->st.acc_bytes = 4;
+    h->st.cell_tile = 128;
+    h->st.n_cell_tiles = T;
+  } else {
+    h->st.contract_bytes = (int64_t)upd * 4 + h->n_entries * 4 + (int64_t)T * P * 4 +
+                           h->nnzA * 4 * T + (int64_t)P * B * 4 + 2 * K * N * 8;
+    h->st.contract_flops = 0;
+    h->st.path = 0;
+    h->st.acc_bytes = acc_bytes;
+  }
   h->have_results = true;
   return CV_OK;
 }

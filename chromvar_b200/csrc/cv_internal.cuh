@@ -118,6 +118,12 @@ struct cv_handle {
   DevBuf obs, samp;        // int64 parity outputs
   bool kept_sums = false;
 
+  // dense tensor-core path (cv_dense.cu)
+  DevBuf dn_M;       // u8 [n_groups*256][Ppad] stacked annotation x iteration operand
+  DevBuf dn_C;       // u8 [n_cell_blocks*128][Ppad] densified counts (cells x peaks)
+  double dn_flops = 0;
+  int opt_path = 0;  // 0 auto, 1 force row-gather SpMM, 2 force dense tcgen05
+
   // background sampler / compat-routine buffers (cv_background.cu, cv_compat.cu)
   DevBuf bk[16];
 
@@ -137,6 +143,10 @@ int cv_build_layout(cv_handle* h, int W);
 int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
                          const double* d_binp_colmajor, const double* d_bin_xy, double w,
                          int niter, int32_t* host_out, double* host_binprob, double* host_density);
+// cv_dense.cu
+int cv_dense_feasible(cv_handle* h, std::string* reason);
+double cv_dense_cost_ms(cv_handle* h);
+int cv_dense_contract(cv_handle* h, int keep_sums, int* T_out, int* soft_fail);
 // cv_deviations.cu
 int cv_choose_tile(cv_handle* h, int B, int acc_bytes, int* W_out);
 

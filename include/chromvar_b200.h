@@ -57,6 +57,9 @@ void cv_destroy(cv_handle* h);
 const char* cv_last_error(const cv_handle* h); /* h == NULL: last error of a failed cv_create */
 int cv_version(void);
 int cv_set_seed(cv_handle* h, uint64_t seed);
+/* options: "path" = 0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05 (fails if the problem
+ * cannot be represented exactly in u8 operands) */
+int cv_set_option(cv_handle* h, const char* key, int64_t value);
 /* the CUDA stream all of this handle's kernels run on (a cudaStream_t), for event timing */
 void* cv_stream(cv_handle* h);
 
@@ -155,6 +158,7 @@ typedef struct cv_stage_stats {
   double ms_finalize;        /* variability merge + K x N transposes */
   double ms_h2d, ms_d2h;     /* host<->device copies of the last call (wall clock) */
   double ms_background;      /* last cv_background_peaks, device time */
+  double contract_flops;     /* dense path: 2 * rows * cells * peaks of the padded GEMM (0 on the sparse path) */
   int64_t contract_updates;  /* (B+1) * sum_k sum_{p in set_k} nnz(counts row) actually visited */
   int64_t contract_bytes;    /* algorithmic bytes of the gather model, DESIGN.md section 4 */
   int64_t h2d_bytes, d2h_bytes;

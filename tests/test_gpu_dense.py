@@ -1,0 +1,138 @@
+"""GPU parity tests of the dense tensor-core path (tcgen05 u8 x u8 -> s32 GEMM with the stacked
+annotation x iteration operand and the TMEM-resident fused epilogue), forced with
+cv_set_option("path", 2): same bars as the row-gather path -- integer sums bit-exact against the
+oracle (and against the row-gather kernel), deviations / z within 1e-5 relative, identical NA masks."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import chromvar_oracle as orc  # noqa: E402
+from test_gpu_parity import assert_close, check_against_oracle, sets_to_csr, _mini, _example  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def dense_engine(engine):
+    engine.set_option("path", 2)
+    yield engine
+    engine.set_option("path", 0)
+
+
+def _run(engine, C, sets, bg, e, sums=True):
+    Cc = sp.csc_matrix(C)
+    engine.set_counts_csc(Cc.shape[0], Cc.shape[1], Cc.indptr, Cc.indices, Cc.data)
+    ptr, idx = sets_to_csr(sets)
+    return engine.deviations(ptr, idx, bg, e, index_base=1, sums=sums)
+
+
+def test_dense_known_answer(dense_engine, golden_deviations_test):
+    g = golden_deviations_test
+    got = _run(dense_engine, g["counts"], [g["set0"], g["set1"], g["set2"]], g["bg"],
+               g["counts"].sum(axis=1) / g["counts"].sum())
+    assert dense_engine.stats()["path"] == 1
+    assert np.max(np.abs(got["dev"] - g["deviations"])) < 1e-12
+    assert np.max(np.abs(got["z"] - g["z"])) < 1e-12
+
+
+def test_dense_mini_against_oracle(dense_engine, golden_mini):
+    C, A = _mini(golden_mini)
+    sets = orc.convert_to_ix_list(A)
+    e = orc.compute_expectations_core(C)
+    bg = orc.get_background_peaks_core(C, golden_mini["bias"], rng=np.random.default_rng(3))
+    got = _run(dense_engine, C, sets, bg, e)
+    assert dense_engine.stats()["path"] == 1
+    ref = orc.compute_deviations_core(C, sets, bg, e, intermediate=True)
+    check_against_oracle(got, ref)
+    assert_close(got["variability"], orc.row_sds(ref["z"], True), "variability")
+
+
+def test_dense_example_counts_edge_cases(dense_engine, golden_example_counts):
+    """29k peaks x 50 cells: single-peak sets, duplicates, the whole peak set, NA mask, and more
+    annotations than one 5-annotation accumulator group (tile raster + partial last group)."""
+    from chromvar_b200._lib import is_na
+    C = _example(golden_example_counts)
+    C = C[np.nonzero(np.asarray(C.sum(axis=1)).ravel() > 0)[0], :].tocsc()
+    P = C.shape[0]
+    rng = np.random.default_rng(42)
+    sizes = [1, 1, 2, 3, 7, 40, 300, 2000, 9000, P, 55, 1200, 17]
+    sets = [np.sort(rng.choice(P, s, replace=False)) + 1 for s in sizes]
+    sets.append(np.array([5, 5, 5, 9, 12]))
+    sets.append(rng.integers(1, P + 1, 500))
+    bg = orc.get_background_peaks_core(C, rng.uniform(0.3, 0.8, P), niterations=50, rng=np.random.default_rng(8))
+    e = orc.compute_expectations_core(C)
+    got = _run(dense_engine, C, sets, bg, e)
+    assert dense_engine.stats()["path"] == 1
+    ref = orc.compute_deviations_core(C, [np.asarray(s) for s in sets], bg, e, intermediate=True)
+    check_against_oracle(got, ref)
+    fps = np.asarray(C.sum(axis=0)).ravel()
+    fail = np.array([e[np.asarray(s) - 1].sum() * fps < 1 for s in sets])
+    assert fail.any() and np.array_equal(is_na(got["z"]), fail)
+
+
+def test_dense_equals_row_gather_at_size(engine):
+    """20000 x 2000 synthetic: both kernels give identical integer sums; dev / z agree to 1e-9;
+    an empty annotation in the middle; more cells than one 128-cell block."""
+    from chromvar_b200 import synthetic
+    d = synthetic.make_config("small")
+    C = d["counts"]
+    P, N = C.shape
+    rng = np.random.default_rng(2)
+    bg = synthetic.random_background(P, 50, rng)
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    sets = [d["annoidx"][d["annoptr"][k]:d["annoptr"][k + 1]] for k in range(12)]
+    sets.insert(6, np.zeros(0, np.int32))                     # an empty annotation in the middle
+    ptr, idx = sets_to_csr(sets)
+    engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    engine.set_option("path", 1)
+    a = engine.deviations(ptr, idx, bg, e, sums=True)
+    assert engine.stats()["path"] == 0
+    engine.set_option("path", 2)
+    try:
+        b = engine.deviations(ptr, idx, bg, e, sums=True)
+        assert engine.stats()["path"] == 1
+    finally:
+        engine.set_option("path", 0)
+    assert np.array_equal(a["observed"], b["observed"])
+    assert np.array_equal(a["sampled"], b["sampled"])
+    assert np.array_equal(np.isnan(a["z"]), np.isnan(b["z"]))
+    ok = ~np.isnan(a["z"])
+    assert np.max(np.abs(a["z"][ok] - b["z"][ok]) / np.maximum(np.abs(a["z"][ok]), 1e-3)) < 1e-9
+    assert np.max(np.abs(a["dev"][ok] - b["dev"][ok]) / np.maximum(np.abs(a["dev"][ok]), 1e-3)) < 1e-9
+    assert np.allclose(a["variability"], b["variability"], rtol=1e-9, equal_nan=True)
+    assert np.array_equal(a["matches"], b["matches"]) and np.allclose(a["overlap"], b["overlap"], equal_nan=True)
+
+
+@pytest.mark.parametrize("B", [2, 15, 31, 50, 64, 127, 255])
+def test_dense_niterations(dense_engine, golden_mini, B):
+    C, A = _mini(golden_mini)
+    sets = orc.convert_to_ix_list(A)
+    e = orc.compute_expectations_core(C)
+    bg = np.random.default_rng(B).integers(1, 1001, (1000, B)).astype(np.int32)
+    got = _run(dense_engine, C, sets, bg, e)
+    ref = orc.compute_deviations_core(C, sets, bg, e, intermediate=True)
+    check_against_oracle(got, ref)
+
+
+def test_dense_refuses_what_it_cannot_represent(dense_engine):
+    from chromvar_b200 import _lib
+    rng = np.random.default_rng(0)
+    D = rng.integers(0, 1000, (300, 20)).astype(np.float64)       # counts above 255
+    D[D.sum(axis=1) == 0, 0] = 1
+    bg = rng.integers(1, 301, (300, 10)).astype(np.int32)
+    dense_engine.set_counts_dense(D)
+    ptr, idx = sets_to_csr([np.arange(1, 100)])
+    with pytest.raises(_lib.ChromVARError) as ei:
+        dense_engine.deviations(ptr, idx, bg, D.sum(axis=1) / D.sum())
+    assert ei.value.code == _lib.CV_ERR_UNSUPPORTED
+    # auto mode falls back to the exact row-gather kernel
+    dense_engine.set_option("path", 0)
+    got = dense_engine.deviations(ptr, idx, bg, D.sum(axis=1) / D.sum(), sums=True)
+    ref = orc.compute_deviations_core(sp.csc_matrix(D), [np.arange(1, 100)], bg, D.sum(axis=1) / D.sum(), intermediate=True)
+    check_against_oracle(got, ref)
+    assert dense_engine.stats()["path"] == 0
