@@ -120,98 +120,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- operand construction -------------------------------------------------------------------------
-// Cd[c][q] (u8, row stride Ppad) from the validated CSC.  32-bit atomics on the containing word so
-// that duplicate (row, col) pairs in the input still sum; max count <= 255 is checked by the host.
-__device__ __forceinline__ int dn_find_col(const int64_t* __restrict__ colptr, int lo, int hi, int64_t e) {
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (__ldg(colptr + mid) <= e) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
-__global__ void __launch_bounds__(256)
-k_dense_counts(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
-               const uint32_t* __restrict__ val, int64_t nnz, int N, int64_t Ppad,
-               uint32_t* __restrict__ Cd_words) {
-  const unsigned full = 0xffffffffu;
-  int lane = threadIdx.x & 31;
-  int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  for (int64_t base = warp_id * 32; base < nnz; base += warps_total * 32) {
-    int64_t e = base + lane;
-    bool active = e < nnz;
-    int64_t e_last = base + 31 < nnz ? base + 31 : nnz - 1;
-    int c = 0;
-    if (lane == 0) c = dn_find_col(colptr, 0, N - 1, base);
-    if (lane == 31) c = dn_find_col(colptr, 0, N - 1, e_last);
-    int c_lo = __shfl_sync(full, c, 0), c_hi = __shfl_sync(full, c, 31);
-    c = (c_lo == c_hi || !active) ? c_lo : dn_find_col(colptr, c_lo, c_hi, e);
-    if (active) {
-      uint32_t v = val[e];
-      if (v) {
-        int64_t byte = (int64_t)c * Ppad + rowidx[e];
-        atomicAdd(Cd_words + (byte >> 2), v << (8 * (int)(byte & 3)));
-      }
-    }
-  }
-}
-
-// M[(g, a, j)][q] += 1 for every (annotation k = g*G + a, peak p of its list, iteration j) with
-// q = p (j = 0) or bg[p][j-1].  One CTA per annotation (strided), a warp per peak, lanes over j.
-__global__ void __launch_bounds__(256)
-k_dense_annot(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx,
-              const int32_t* __restrict__ bgT, int K, int B, int G, int64_t Ppad,
-              uint32_t* __restrict__ M_words) {
-  const int I = B + 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int k = blockIdx.x; k < K; k += gridDim.x) {
-    const int64_t beg = annoptr[k], end = annoptr[k + 1];
-    const int64_t row0 = (int64_t)(k / G) * DN_BLOCK_N + (int64_t)(k % G) * I;
-    for (int64_t idx = beg + warp; idx < end; idx += nwarps) {
-      const int p = __ldg(annoidx + idx);
-      for (int j = lane; j < I; j += 32) {
-        const int q = (j == 0) ? p : __ldg(bgT + (int64_t)p * B + (j - 1));
-        const int64_t byte = (row0 + j) * Ppad + q;
-        atomicAdd(M_words + (byte >> 2), 1u << (8 * (int)(byte & 3)));
-      }
-    }
-  }
-}
-
-// multiplicity bound: cnt[j][q] = #{p : bg[p][j] = q} over ALL peaks >= any entry of M for j >= 1
-__global__ void k_bg_mult_count(const int32_t* __restrict__ bgT, int64_t PB, int P, int B,
-                                uint32_t* __restrict__ cnt) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= PB) return;
-  int j = (int)(i % B);
-  atomicAdd(cnt + (int64_t)j * P + bgT[i], 1u);
-}
-__global__ void k_u32_max(const uint32_t* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
-  uint32_t m = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    m = max(m, x[i]);
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
-// largest multiplicity of one peak inside one annotation list (1 unless the caller passes duplicates)
-__global__ void __launch_bounds__(256)
-k_anno_maxdup(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx, int K, int P,
-              int32_t* __restrict__ mark /*[gridDim.x][P] zero*/, uint32_t* __restrict__ out) {
-  int32_t* mk = mark + (int64_t)blockIdx.x * P;
-  for (int k = blockIdx.x; k < K; k += gridDim.x) {
-    int64_t beg = annoptr[k], end = annoptr[k + 1];
-    uint32_t m = 0;
-    for (int64_t idx = beg + threadIdx.x; idx < end; idx += blockDim.x)
-      m = max(m, (uint32_t)atomicAdd(mk + annoidx[idx], 1) + 1u);
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-    __syncthreads();
-    for (int64_t idx = beg + threadIdx.x; idx < end; idx += blockDim.x) mk[annoidx[idx]] = 0;
-    __syncthreads();
-  }
-}
-
 // ---- the GEMM + fused epilogue -----------------------------------------------------------------------
 struct DenseParams {
   int N, K, B, G;            // cells, annotations, iterations, annotations per 256-row group
@@ -518,57 +426,8 @@ int cv_dense_contract(cv_handle* h, int keep_sums, int* T_out, int* soft_fail) {
   const int ncb = (int)((N + DN_BLOCK_M - 1) / DN_BLOCK_M);
   const int64_t rowsM = (int64_t)n_groups * DN_BLOCK_N, rowsC = (int64_t)ncb * DN_BLOCK_M;
 
-  // ---- exactness bound for the u8 annotation operand --------------------------------------------
-  CV_TRY(cv_ensure(h, h->tmp1, (size_t)P * B * 4));
-  CV_TRY(cv_ensure(h, h->flags, 64));
-  CV_CUDA(h, cudaMemsetAsync(h->tmp1.p, 0, (size_t)P * B * 4, h->stream));
-  CV_CUDA(h, cudaMemsetAsync(h->flags.as<uint32_t>() + 4, 0, 8, h->stream));
-  CV_LAUNCH(h, k_bg_mult_count, (unsigned)((P * B + 255) / 256), 256, 0, h->bgT.as<int32_t>(), P * B, (int)P, B,
-            h->tmp1.as<uint32_t>());
-  CV_LAUNCH(h, k_u32_max, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, h->flags.as<uint32_t>() + 4);
-  {
-    int grid = (int)std::min<int64_t>(K, (int64_t)h->num_sms * 2);
-    CV_LAUNCH(h, k_anno_maxdup, grid, 256, 0, h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), (int)K, (int)P,
-              h->mark.as<int32_t>(), h->flags.as<uint32_t>() + 5);
-  }
-  uint32_t mx[2] = {0, 0};
-  CV_CUDA(h, cudaMemcpyAsync(mx, h->flags.as<uint32_t>() + 4, 8, cudaMemcpyDeviceToHost, h->stream));
-  CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  const uint64_t maxmult = (uint64_t)std::max(mx[0], 1u) * std::max(mx[1], 1u);
-  if (maxmult > 255) {
-    *soft_fail = 1;
-    CV_FAIL(h, CV_ERR_UNSUPPORTED, "annotation multiplicity bound %llu exceeds the u8 operand", (unsigned long long)maxmult);
-  }
-  // s32 accumulator bound: S <= maxmult * (fragments of the cell)  -- checked against 2^31
-  {
-    // max fps is cheap to get on the host side from the per-cell totals
-    std::vector<unsigned long long> ct((size_t)N);
-    CV_CUDA(h, cudaMemcpyAsync(ct.data(), h->cell_tot.p, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
-    CV_CUDA(h, cudaStreamSynchronize(h->stream));
-    unsigned long long m = 0;
-    for (auto v : ct) m = std::max(m, v);
-    if ((double)m * (double)maxmult >= 2147483647.0) {
-      *soft_fail = 1;
-      CV_FAIL(h, CV_ERR_UNSUPPORTED, "s32 accumulator bound exceeded");
-    }
-  }
-
-  // ---- operands -------------------------------------------------------------------------------------
-  CV_TRY(cv_ensure(h, h->dn_M, (size_t)rowsM * Ppad));
-  CV_TRY(cv_ensure(h, h->dn_C, (size_t)rowsC * Ppad));
-  CV_CUDA(h, cudaMemsetAsync(h->dn_M.p, 0, (size_t)rowsM * Ppad, h->stream));
-  CV_CUDA(h, cudaMemsetAsync(h->dn_C.p, 0, (size_t)rowsC * Ppad, h->stream));
-  if (h->nnz > 0) {
-    int64_t g = (h->nnz + 1023) / 1024;
-    g = std::min<int64_t>(g, (int64_t)h->num_sms * 16);
-    CV_LAUNCH(h, k_dense_counts, (unsigned)g, 256, 0, h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(),
-              h->val.as<uint32_t>(), h->nnz, (int)N, Ppad, h->dn_C.as<uint32_t>());
-  }
-  {
-    int grid = (int)std::min<int64_t>(K, (int64_t)h->num_sms * 8);
-    CV_LAUNCH(h, k_dense_annot, grid, 256, 0, h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(),
-              h->bgT.as<int32_t>(), (int)K, B, G, Ppad, h->dn_M.as<uint32_t>());
-  }
+  // ---- operands, per-annotation tables, exactness bounds (cv_dense_build.cu) -------------------
+  CV_TRY(cv_dense_build_operands(h, G, Ppad, rowsM, rowsC, soft_fail));
 
   // ---- GEMM + fused epilogue --------------------------------------------------------------------------
   CUtensorMap map_c, map_m;

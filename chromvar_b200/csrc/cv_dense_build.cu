@@ -1,0 +1,287 @@
+// Operand construction for the dense tensor-core path (cv_dense.cu), built in shared memory and
+// written out coalesced so that neither operand needs a global memset or global atomics:
+//
+//   k_dense_rows   one CTA per annotation k: the B+1 stacked rows M[(k, j), :] (u8 multiplicities),
+//                  together with everything else that is per (annotation, iteration) and cell
+//                  independent: the expected-fraction table E[k][j] (tf_vec %*% expectation,
+//                  sample_mat %*% expectation; R/compute_deviations.R:488,502), the background
+//                  overlap (:506, :477-478) and fractionMatches (:533).  Row j = 0 (the set's own
+//                  multiplicities) stays in shared memory while rows j >= 1 are built, so the
+//                  overlap sum_q M[(k,j),q] * M[(k,0),q] costs one shared-memory byte read per draw.
+//   k_dense_cells  one CTA per cell: the densified counts row Cd[c, :] (u8) from the CSC column.
+//   k_bg_mult_*    exactness bound for the u8 operand: max_{j,q} #{p : bg[p, j] = q}.
+//
+// Rows longer than the shared-memory budget (P > ~110k peaks) are built in chunks of the peak axis.
+#include <algorithm>
+#include <vector>
+
+#include "cv_internal.cuh"
+
+#define DB_THREADS 512
+#define DB_BLOCK_N 256
+
+enum { DB_FLAG_BADIDX = 8u };
+
+__device__ __forceinline__ void db_zero(uint32_t* row, int nwords) {
+  uint4* r4 = reinterpret_cast<uint4*>(row);
+  for (int i = threadIdx.x; i < (nwords >> 2); i += DB_THREADS) r4[i] = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void db_store(const uint32_t* row, uint32_t* __restrict__ dst, int nwords) {
+  const uint4* r4 = reinterpret_cast<const uint4*>(row);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int i = threadIdx.x; i < (nwords >> 2); i += DB_THREADS) d4[i] = r4[i];
+}
+
+// bg: P x B column-major as uploaded (index_base); annoidx: 0-based, validated.
+__global__ void __launch_bounds__(DB_THREADS, 1)
+k_dense_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx,
+             const int32_t* __restrict__ bg, int base, const double* __restrict__ e,
+             const int32_t* __restrict__ order, int K, int P, int B, int G, int64_t Ppad, int chunk,
+             uint8_t* __restrict__ M, double* __restrict__ etab, double* __restrict__ overlap,
+             double* __restrict__ matches, uint32_t* __restrict__ work_ctr, uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) uint32_t db_smem[];
+  uint32_t* row0 = db_smem;                       // [chunk / 4] words: the set's own multiplicities
+  uint32_t* rowj = db_smem + (chunk >> 2);        // [chunk / 4] words: the row being built
+  __shared__ double s_red[DB_THREADS / 32];
+  __shared__ unsigned long long s_ov[DB_THREADS / 32];
+  __shared__ int s_item;
+  const int I = B + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint8_t* row0b = reinterpret_cast<const uint8_t*>(row0);
+  for (;;) {
+    if (threadIdx.x == 0) s_item = (int)atomicAdd(work_ctr, 1u);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= K) break;
+    const int k = order[item];
+    const int64_t beg = annoptr[k], end = annoptr[k + 1];
+    const int64_t mrow0 = (int64_t)(k / G) * DB_BLOCK_N + (int64_t)(k % G) * I;
+    unsigned long long ov_total = 0;               // thread 0 only
+    for (int64_t q0 = 0; q0 < Ppad; q0 += chunk) {
+      const int cw = (int)min((int64_t)chunk, Ppad - q0) >> 2;     // words in this chunk
+      const int qhi = (int)min((int64_t)P, q0 + ((int64_t)cw << 2));
+      // ---- row j = 0: multiplicity of each peak in the annotation's list ----
+      db_zero(row0, cw);
+      __syncthreads();
+      double se = 0.0;
+      for (int64_t idx = beg + threadIdx.x; idx < end; idx += DB_THREADS) {
+        const int p = __ldg(annoidx + idx);
+        if (p >= q0 && p < qhi) {
+          const int off = p - (int)q0;
+          atomicAdd(row0 + (off >> 2), 1u << (8 * (off & 3)));
+          se += __ldg(e + p);
+        }
+      }
+      __syncthreads();
+      db_store(row0, reinterpret_cast<uint32_t*>(M + mrow0 * Ppad + q0), cw);
+      se = warp_sum<double>(se);
+      if (lane == 0) s_red[warp] = se;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < DB_THREADS / 32; ++w) s += s_red[w];
+        double* dst = etab + (int64_t)k * I;
+        dst[0] = (q0 == 0) ? s : dst[0] + s;
+      }
+      // ---- rows j = 1..B: background iteration j ----
+      for (int j = 1; j <= B; ++j) {
+        db_zero(rowj, cw);
+        __syncthreads();                           // also orders the s_red reads above
+        const int32_t* __restrict__ bgcol = bg + (int64_t)(j - 1) * P;
+        double sj = 0.0;
+        unsigned long long ov = 0;
+        for (int64_t idx = beg + threadIdx.x; idx < end; idx += DB_THREADS) {
+          const int p = __ldg(annoidx + idx);
+          int q = __ldg(bgcol + p) - base;
+          if (q < 0 || q >= P) { atomicOr(flags, DB_FLAG_BADIDX); q = 0; }
+          if (q >= q0 && q < qhi) {
+            const int off = q - (int)q0;
+            atomicAdd(rowj + (off >> 2), 1u << (8 * (off & 3)));
+            sj += __ldg(e + q);
+            ov += (unsigned long long)row0b[off];
+          }
+        }
+        __syncthreads();
+        db_store(rowj, reinterpret_cast<uint32_t*>(M + (mrow0 + j) * Ppad + q0), cw);
+        sj = warp_sum<double>(sj);
+        ov = warp_sum<unsigned long long>(ov);
+        if (lane == 0) { s_red[warp] = sj; s_ov[warp] = ov; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double s = 0.0;
+          unsigned long long o = 0;
+          for (int w = 0; w < DB_THREADS / 32; ++w) { s += s_red[w]; o += s_ov[w]; }
+          double* dst = etab + (int64_t)k * I + j;
+          *dst = (q0 == 0) ? s : *dst + s;
+          ov_total += o;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double cnt = (double)(end - beg);
+      matches[k] = cnt / (double)P;
+      overlap[k] = (end > beg) ? ((double)ov_total / (double)B) / cnt : cv_na_real();
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int db_find_col_dummy() { return 0; }
+
+// Cd[c][:] for one cell per CTA iteration.  val: validated counts (<= 255 checked by the host).
+__global__ void __launch_bounds__(DB_THREADS, 1)
+k_dense_cells(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
+              const uint32_t* __restrict__ val, int N, int n_rows_padded, int64_t Ppad, int chunk,
+              uint8_t* __restrict__ Cd, uint32_t* __restrict__ work_ctr) {
+  extern __shared__ __align__(16) uint32_t db_smem[];
+  __shared__ int s_item;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = (int)atomicAdd(work_ctr, 1u);
+    __syncthreads();
+    const int c = s_item;
+    if (c >= n_rows_padded) break;
+    const int64_t beg = c < N ? colptr[c] : 0, end = c < N ? colptr[c + 1] : 0;
+    for (int64_t q0 = 0; q0 < Ppad; q0 += chunk) {
+      const int cw = (int)min((int64_t)chunk, Ppad - q0) >> 2;
+      const int64_t qhi = q0 + ((int64_t)cw << 2);
+      db_zero(db_smem, cw);
+      __syncthreads();
+      for (int64_t x = beg + threadIdx.x; x < end; x += DB_THREADS) {
+        const int q = __ldg(rowidx + x);
+        if (q >= q0 && q < qhi) {
+          const int off = q - (int)q0;
+          atomicAdd(db_smem + (off >> 2), __ldg(val + x) << (8 * (off & 3)));   // duplicates still sum
+        }
+      }
+      __syncthreads();
+      db_store(db_smem, reinterpret_cast<uint32_t*>(Cd + (int64_t)c * Ppad + q0), cw);
+      __syncthreads();
+    }
+  }
+}
+
+// cnt[j][q] = #{p : bg[p, j] = q}; bg column-major, so reads are coalesced
+__global__ void k_bg_mult_count_cm(const int32_t* __restrict__ bg, int base, int64_t PB, int P,
+                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= PB) return;
+  int q = bg[i] - base;
+  if (q < 0 || q >= P) { atomicOr(flags, DB_FLAG_BADIDX); return; }
+  atomicAdd(cnt + (i / P) * P + q, 1u);
+}
+__global__ void k_u32_max_db(const uint32_t* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, x[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+// largest byte of the j = 0 rows = largest multiplicity of one peak inside one annotation list.
+// A byte that wrapped (a peak listed > 255 times) shows up as a byte sum != list length and is
+// reported as an impossible multiplicity.
+__global__ void __launch_bounds__(256)
+k_row0_max(const uint8_t* __restrict__ M, const int64_t* __restrict__ annoptr, int K, int G, int I,
+           int64_t Ppad, uint32_t* __restrict__ out) {
+  __shared__ unsigned long long s_sum[8];
+  const int k = blockIdx.x;
+  if (k >= K) return;
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(M + ((int64_t)(k / G) * DB_BLOCK_N + (int64_t)(k % G) * I) * Ppad);
+  uint32_t m = 0;
+  unsigned long long sum = 0;
+  for (int64_t i = threadIdx.x; i < (Ppad >> 2); i += blockDim.x) {
+    uint32_t w = row[i];
+    m = max(m, max(max(w & 0xffu, (w >> 8) & 0xffu), max((w >> 16) & 0xffu, w >> 24)));
+    sum += (w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  sum = warp_sum<unsigned long long>(sum);
+  if ((threadIdx.x & 31) == 0) {
+    if (m) atomicMax(out, m);
+    s_sum[threadIdx.x >> 5] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += s_sum[w];
+    if (t != (unsigned long long)(annoptr[k + 1] - annoptr[k])) atomicMax(out, 0xFFFFu);
+  }
+}
+
+// rows of a 256-row group that no (annotation, iteration) owns must read as zero
+__global__ void __launch_bounds__(256)
+k_zero_pad_rows(uint8_t* __restrict__ M, int K, int G, int I, int64_t Ppad) {
+  const int g = blockIdx.x;
+  const int nk = min(G, K - g * G);
+  const int first = nk * I;
+  uint4* base = reinterpret_cast<uint4*>(M + ((int64_t)g * DB_BLOCK_N + first) * Ppad);
+  const int64_t n16 = ((int64_t)(DB_BLOCK_N - first) * Ppad) >> 4;
+  for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) base[i] = make_uint4(0, 0, 0, 0);
+}
+
+// Host: bound check + both operands + the per-annotation tables.  soft_fail = 1 when the u8 / s32
+// bounds cannot be guaranteed (the caller then falls back to the exact row-gather kernel).
+int cv_dense_build_operands(cv_handle* h, int G, int64_t Ppad, int64_t rowsM, int64_t rowsC,
+                            int* soft_fail) {
+  *soft_fail = 0;
+  const int64_t P = h->P, N = h->N, K = h->K;
+  const int B = h->B, I = B + 1;
+  uint32_t* flags = h->flags.as<uint32_t>();
+
+  // ---- multiplicity bound over all peaks (cheap, before anything big is allocated) ------------
+  // list duplicates: a peak repeated d times inside one list multiplies every entry by up to d;
+  // bounded here by the longest list's worst case only when duplicates exist (checked after the
+  // rows are built through k_row0_max).
+  CV_TRY(cv_ensure(h, h->tmp1, (size_t)P * B * 4));
+  CV_CUDA(h, cudaMemsetAsync(h->tmp1.p, 0, (size_t)P * B * 4, h->stream));
+  CV_CUDA(h, cudaMemsetAsync(flags + 4, 0, 8, h->stream));
+  CV_LAUNCH(h, k_bg_mult_count_cm, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(),
+            h->index_base, P * B, (int)P, h->tmp1.as<uint32_t>(), flags);
+  CV_LAUNCH(h, k_u32_max_db, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, flags + 4);
+
+  // ---- operands ------------------------------------------------------------------------------------
+  CV_TRY(cv_ensure(h, h->dn_M, (size_t)rowsM * Ppad));
+  CV_TRY(cv_ensure(h, h->dn_C, (size_t)rowsC * Ppad));
+  const int budget = h->max_smem_optin - 2048;
+  // rows kernel keeps two row chunks, cells kernel one
+  int chunk2 = (int)std::min<int64_t>(Ppad, ((budget / 2) / 128) * 128);
+  int chunk1 = (int)std::min<int64_t>(Ppad, (budget / 128) * 128);
+  CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
+  // rows of a group that no (annotation, iteration) owns must be zero
+  {
+    const int n_groups = (int)(rowsM / DB_BLOCK_N);
+    if (G * I < DB_BLOCK_N || K % G)
+      CV_LAUNCH(h, k_zero_pad_rows, n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, Ppad);
+  }
+  CV_CUDA(h, cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * chunk2));
+  CV_LAUNCH(h, k_dense_rows, (unsigned)std::min<int64_t>(K, h->num_sms), DB_THREADS, (size_t)2 * chunk2,
+            h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
+            h->expect.as<double>(), h->order.as<int32_t>(), (int)K, (int)P, B, G, Ppad, chunk2,
+            h->dn_M.as<uint8_t>(), h->etab.as<double>(), h->overlap.as<double>(), h->matches.as<double>(),
+            h->work_ctr.as<uint32_t>(), flags);
+  CV_LAUNCH(h, k_row0_max, (unsigned)K, 256, 0, h->dn_M.as<uint8_t>(), h->annoptr.as<int64_t>(), (int)K, G, I, Ppad, flags + 5);
+  CV_CUDA(h, cudaFuncSetAttribute(k_dense_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk1));
+  CV_LAUNCH(h, k_dense_cells, (unsigned)std::min<int64_t>(rowsC, (int64_t)h->num_sms), DB_THREADS, (size_t)chunk1,
+            h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), (int)N, (int)rowsC, Ppad,
+            chunk1, h->dn_C.as<uint8_t>(), h->work_ctr.as<uint32_t>() + 1);
+
+  // ---- bounds: u8 entries of M, s32 accumulators ---------------------------------------------------
+  uint32_t mx[2] = {0, 0};
+  CV_CUDA(h, cudaMemcpyAsync(mx, flags + 4, 8, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<unsigned long long> ct((size_t)N);
+  CV_CUDA(h, cudaMemcpyAsync(ct.data(), h->cell_tot.p, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  const uint64_t maxmult = (uint64_t)std::max(mx[0], 1u) * std::max(mx[1], 1u);
+  if (maxmult > 255) {
+    *soft_fail = 1;
+    CV_FAIL(h, CV_ERR_UNSUPPORTED, "annotation multiplicity bound %llu exceeds the u8 operand",
+            (unsigned long long)maxmult);
+  }
+  unsigned long long m = 0;
+  for (auto v : ct) m = std::max(m, v);
+  if ((double)m * (double)maxmult >= 2147483647.0) {
+    *soft_fail = 1;
+    CV_FAIL(h, CV_ERR_UNSUPPORTED, "s32 accumulator bound exceeded");
+  }
+  return CV_OK;
+}

@@ -488,16 +488,10 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
     }
   }
 
-  // ---- stage 1: annotation / background preparation ---------------------------------------
+  // ---- stage 1: validation and per-annotation tables ---------------------------------------------
   CV_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
   CV_TRY(cv_ensure(h, h->flags, 64));
   CV_CUDA(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
-  CV_TRY(cv_ensure(h, h->bgT, (size_t)P * B * 4));
-  {
-    dim3 grid((unsigned)((P + 31) / 32), (unsigned)((B + 31) / 32));
-    CV_LAUNCH(h, k_bg_prepare, grid, 256, 0, h->bg_raw.as<int32_t>(), (int)P, B, h->index_base,
-              h->bgT.as<int32_t>(), h->flags.as<uint32_t>());
-  }
   CV_LAUNCH(h, k_check_zero_peaks, (unsigned)((P + 255) / 256), 256, 0,
             h->peak_tot.as<unsigned long long>(), (int)P, h->flags.as<uint32_t>());
   if (h->nnzA)
@@ -506,20 +500,7 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
   CV_TRY(cv_ensure(h, h->etab, (size_t)K * I * 8));
   CV_TRY(cv_ensure(h, h->overlap, (size_t)K * 8));
   CV_TRY(cv_ensure(h, h->matches, (size_t)K * 8));
-  {
-    int grid = (int)std::min<int64_t>(K, (int64_t)h->num_sms * 2);
-    size_t mark_bytes = (size_t)grid * P * 4;
-    if (h->mark.cap < mark_bytes) {
-      CV_TRY(cv_ensure(h, h->mark, mark_bytes));
-      CV_CUDA(h, cudaMemsetAsync(h->mark.p, 0, h->mark.cap, h->stream));
-    }
-    size_t smem = (size_t)(STATS_THREADS / 32) * I * 8;
-    CV_CUDA(h, cudaFuncSetAttribute(k_anno_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CV_LAUNCH(h, k_anno_stats, grid, STATS_THREADS, smem, h->annoptr.as<int64_t>(),
-              h->annoidx.as<int32_t>(), h->bgT.as<int32_t>(), h->expect.as<double>(), (int)P, B,
-              (int)K, h->mark.as<int32_t>(), h->etab.as<double>(), h->overlap.as<double>(),
-              h->matches.as<double>());
-  }
+  CV_TRY(cv_ensure(h, h->work_ctr, 64));
   CV_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
 
   // ---- stage 2: operand layout + contraction + fused epilogue -----------------------------------
@@ -527,8 +508,6 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
   CV_TRY(cv_ensure(h, h->z_rm, (size_t)K * N * 8));
   CV_TRY(cv_ensure(h, h->varfinal, (size_t)K * 4 * 8));
   CV_TRY(cv_ensure(h, h->variab, (size_t)K * 8));
-  CV_TRY(cv_ensure(h, h->work_ctr, 64));
-  CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
   if (keep_sums) {
     CV_TRY(cv_ensure(h, h->obs, (size_t)K * N * 8));
     CV_TRY(cv_ensure(h, h->samp, (size_t)K * B * N * 8));
@@ -544,6 +523,28 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
     }
   }
   if (!use_dense) {
+    // background matrix -> [P][B] 0-based, expected-fraction table, overlap, matches
+    CV_TRY(cv_ensure(h, h->bgT, (size_t)P * B * 4));
+    {
+      dim3 grid((unsigned)((P + 31) / 32), (unsigned)((B + 31) / 32));
+      CV_LAUNCH(h, k_bg_prepare, grid, 256, 0, h->bg_raw.as<int32_t>(), (int)P, B, h->index_base,
+                h->bgT.as<int32_t>(), h->flags.as<uint32_t>());
+    }
+    {
+      int grid = (int)std::min<int64_t>(K, (int64_t)h->num_sms * 2);
+      size_t mark_bytes = (size_t)grid * P * 4;
+      if (h->mark.cap < mark_bytes) {
+        CV_TRY(cv_ensure(h, h->mark, mark_bytes));
+        CV_CUDA(h, cudaMemsetAsync(h->mark.p, 0, h->mark.cap, h->stream));
+      }
+      size_t smem = (size_t)(STATS_THREADS / 32) * I * 8;
+      CV_CUDA(h, cudaFuncSetAttribute(k_anno_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CV_LAUNCH(h, k_anno_stats, grid, STATS_THREADS, smem, h->annoptr.as<int64_t>(),
+                h->annoidx.as<int32_t>(), h->bgT.as<int32_t>(), h->expect.as<double>(), (int)P, B,
+                (int)K, h->mark.as<int32_t>(), h->etab.as<double>(), h->overlap.as<double>(),
+                h->matches.as<double>());
+    }
+    CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
     int W = 0;
     CV_TRY(cv_choose_tile(h, B, acc_bytes, &W));
     if (rebuild_counts_layout || !h->layout_valid || h->W != W) CV_TRY(cv_build_layout(h, W));
@@ -595,7 +596,8 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
   if (flags & FLAG_BADIDX)
     CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
   float ms;
-  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->st.ms_counts_layout = ms;   // operand layout of the chosen path
+  // ev[2] -> ev[3]: operand layout of the chosen path together with the per-annotation tables
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->st.ms_counts_layout = ms;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->st.ms_anno_prep = ms;
   cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->st.ms_contract = ms;
   cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->st.ms_finalize = ms;

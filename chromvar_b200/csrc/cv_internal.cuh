@@ -147,6 +147,8 @@ int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_
 int cv_dense_feasible(cv_handle* h, std::string* reason);
 double cv_dense_cost_ms(cv_handle* h);
 int cv_dense_contract(cv_handle* h, int keep_sums, int* T_out, int* soft_fail);
+// cv_dense_build.cu
+int cv_dense_build_operands(cv_handle* h, int G, int64_t Ppad, int64_t rowsM, int64_t rowsC, int* soft_fail);
 // cv_deviations.cu
 int cv_choose_tile(cv_handle* h, int B, int acc_bytes, int* W_out);
 
