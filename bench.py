@@ -47,6 +47,16 @@ def peaks_json():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def ncu_traffic(kernel, workload):
+    """dram bytes (read + write) per launch of `kernel` on `workload` from the committed ncu --set
+    full capture (profiles/traffic.json, written by hand from the .ncu-rep), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -194,6 +204,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     eng = _lib.Handle(local, seed=20173)
     eng.set_option("path", args.path)
+    eng.set_option("dense_cta_pair", args.pair)
     d, name = make_workload(rank, args.cells, args.quick)
     C = d["counts"]
     P, N = C.shape
@@ -254,6 +265,7 @@ def run_ours(args):
         contract_ms.append(st["ms_contract"])
         stage_acc += [st["ms_counts_layout"], st["ms_anno_prep"], st["ms_contract"], st["ms_finalize"]]
         upd, bytes_alg, path = st["contract_updates"], st["contract_bytes"], st["path"]
+        tile_cells, gemm_launches, padded_flops = st["cell_tile"], st["n_cell_tiles"] * max(st["planes"], 1), st["contract_flops"]
     barrier()
     clocks = sampler.stop()
     launches = eng.stats()["kernel_launches"] - launches0
@@ -270,23 +282,26 @@ def run_ours(args):
                matches=np.empty(K), overlap=np.empty(K), variability=np.empty(K))
 
     def e2e_step():
-        eng.set_counts_csc(P, N, h_colptr, h_rowidx, h_x)              # H2D counts + K1
-        if ws > 1:
-            cvd.allreduce_peak_totals(eng)
-        eng.deviations_upload(h_ptr, h_idx, h_bg, h_e, index_base=1)   # H2D annotations, bg, expectation
-        eng.deviations_compute(rebuild_counts_layout=False, keep_sums=False)
-        eng.deviations_download(out=out)                                # D2H dev, z (+ K-vectors)
+        # compute_deviations_core as the R shim calls it: ONE ABI call on host buffers (counts CSC,
+        # annotations, background, expectation in; deviations / z out).  The library overlaps the
+        # chunked H2D of the counts and the chunked D2H of the results with the kernels.
+        eng.deviations_csc(P, N, h_colptr, h_rowidx, h_x, h_ptr, h_idx, h_bg, h_e, index_base=1, out=out)
         if ws > 1:
             cvd.gather_variability(eng)
 
+    if ws > 1:
+        eng.set_option("check_zero_peaks", 0)     # a shard may hold no fragment of a peak; e is global
+
+    e2e_step()
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 5))
+    n_e2e = max(1, min(args.steps, 10))
     for _ in range(n_e2e):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_stats = eng.stats()
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -306,11 +321,14 @@ def run_ours(args):
         flops = 2.0 * (NITER + 1) * K * P * N
         peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         achieved = flops / (c_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_dense_contract", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_kind": peaks_kind +
-                " (2 x bf16 sustained = int8 dense)", "peak_burst": 2.0 * peaks["bf16_tflops"],
-                "ms_per_launch": c_ms, "algorithmic_ops_per_launch": flops,
-                "padded_ops_per_launch": eng.stats()["contract_flops"], "share_of_step": share}
+        kname = "k_dense_contract_pair" if tile_cells == 256 else "k_dense_contract"
+        roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(kname, name),
+                "peak_kind": peaks_kind + " (2 x bf16 sustained = int8 dense)",
+                "peak_burst": 2.0 * peaks["bf16_tflops"], "peak_nominal": 4500.0,
+                "ms_per_launch": c_ms / max(gemm_launches, 1), "launches_per_step": int(gemm_launches),
+                "algorithmic_ops_per_launch": flops / max(gemm_launches, 1),
+                "padded_ops_per_step": padded_flops, "share_of_step": share}
     else:
         achieved = bytes_alg / (c_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"],
@@ -335,10 +353,15 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
                    "niterations": NITER, "nnz_per_gpu": nnz, "nnz_annotations": int(d["annoptr"][-1]),
-                   "l2": "256 MB flush write between timed steps", "cell_tile": eng.stats()["cell_tile"],
-                   "path": "dense_tcgen05" if path == 1 else "row_gather_spmm"},
+                   "l2": "256 MB flush write between timed steps", "cell_tile": int(tile_cells),
+                   "path": ("dense_tcgen05_cta_pair" if tile_cells == 256 else "dense_tcgen05") if path == 1
+                   else "row_gather_spmm"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e},
+                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
+                "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
+                "cell_chunks": int(e2e_stats["n_cell_tiles"]),
+                "device_ms": {k: round(float(e2e_stats[k]), 3) for k in
+                              ("ms_counts_layout", "ms_anno_prep", "ms_contract", "ms_finalize")}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -362,6 +385,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
+    ap.add_argument("--pair", type=int, default=1, help="dense path: 1 CTA-pair kernel (cta_group::2), 0 single-CTA kernel")
     args = ap.parse_args()
     if args.warmup < 3 and not args.quick and args.impl == "ours":
         log("[bench] warning: fewer than 3 warm-up steps")

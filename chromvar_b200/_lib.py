@@ -24,7 +24,7 @@ _DTYPE_TAG = {np.dtype(np.int32): CV_I32, np.dtype(np.int64): CV_I64,
 EXPORTS = [
     "cv_create", "cv_destroy", "cv_last_error", "cv_version", "cv_set_seed", "cv_set_option", "cv_stream",
     "cv_set_counts_csc", "cv_set_counts_dense", "cv_fragments", "cv_peak_totals_device",
-    "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_deviations",
+    "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_deviations", "cv_deviations_csc",
     "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
     "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats",
@@ -40,7 +40,7 @@ class StageStats(C.Structure):
         ("contract_updates", C.c_int64), ("contract_bytes", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64),
         ("path", C.c_int32), ("cell_tile", C.c_int32), ("n_cell_tiles", C.c_int32),
-        ("acc_bytes", C.c_int32),
+        ("acc_bytes", C.c_int32), ("planes", C.c_int32), ("reserved", C.c_int32),
     ]
 
     def as_dict(self):
@@ -85,6 +85,8 @@ def load(build_if_missing=True):
         "cv_expectations": (i32, [vp, i32, vp, i32, vp]),
         "cv_background_peaks": (i32, [vp, vp, i32, dbl, i32, vp, vp, vp, vp, vp]),
         "cv_deviations": (i32, [vp, i64, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "cv_deviations_csc": (i32, [vp, i64, i64, vp, i32, vp, vp, i32, i64, vp, vp, i32, vp, i32, vp,
+                                    vp, vp, vp, vp, vp]),
         "cv_deviations_upload": (i32, [vp, i64, vp, vp, i32, vp, i32, vp]),
         "cv_deviations_compute": (i32, [vp, i32, i32]),
         "cv_deviations_download": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -286,6 +288,41 @@ class Handle:
                                            _ptr(out["matches"]), _ptr(out["overlap"]),
                                            _ptr(out["variability"]), _ptr(obs), _ptr(samp)))
         self.K, self.B = K, B
+        return out
+
+    def deviations_csc(self, P, N, colptr, rowidx, x, annoptr, annoidx, bg, expectation=None, index_base=1,
+                       out=None):
+        """cv_deviations_csc: compute_deviations_core as one call on host data (counts, annotations,
+        background, expectation in; deviations / z out), copies overlapped with the kernels."""
+        colptr = np.ascontiguousarray(colptr)
+        if colptr.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+            colptr = colptr.astype(np.int64)
+        rowidx = _carr(rowidx, np.int32)
+        x = np.ascontiguousarray(x)
+        if x.dtype not in _DTYPE_TAG or x.dtype == np.dtype(np.int64):
+            x = x.astype(np.float64)
+        annoptr = _carr(annoptr, np.int64)
+        annoidx = _carr(annoidx, np.int32)
+        bg = np.asarray(bg)
+        if bg.dtype != np.dtype(np.int32) or not bg.flags.f_contiguous:
+            bg = np.asfortranarray(bg.astype(np.int32, copy=False))
+        if expectation is not None:
+            expectation = _carr(expectation, np.float64)
+            if expectation.shape[0] != P:
+                raise ChromVARError(CV_ERR_INVALID, "length(expectation) must equal nrow(counts)")
+        if bg.shape[0] != P:
+            raise ChromVARError(CV_ERR_INVALID, "nrow(background_peaks) must equal nrow(counts)")
+        K, B = annoptr.shape[0] - 1, bg.shape[1]
+        if out is None:
+            out = dict(dev=np.empty((K, N), np.float64, order="F"), z=np.empty((K, N), np.float64, order="F"),
+                       matches=np.empty(K, np.float64), overlap=np.empty(K, np.float64),
+                       variability=np.empty(K, np.float64))
+        self._check(self.lib.cv_deviations_csc(
+            self._h, P, N, _ptr(colptr), _DTYPE_TAG[colptr.dtype], _ptr(rowidx), _ptr(x), _DTYPE_TAG[x.dtype],
+            K, _ptr(annoptr), _ptr(annoidx), index_base, _ptr(bg), B, _ptr(expectation),
+            _ptr(out["dev"]), _ptr(out["z"]), _ptr(out["matches"]), _ptr(out["overlap"]),
+            _ptr(out["variability"])))
+        self.P, self.N, self.K, self.B = int(P), int(N), K, B
         return out
 
     def variability_partials_device(self):

@@ -92,6 +92,12 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
     delete h;
     return CV_ERR_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "cudaStreamCreate failed";
+    delete h;
+    return CV_ERR_CUDA;
+  }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   *out = h;
   return CV_OK;
@@ -106,11 +112,14 @@ extern "C" void cv_destroy(cv_handle* h) {
                     &h->scan_tmp, &h->annoptr, &h->anno_raw, &h->annoidx, &h->bg_raw, &h->bgT, &h->expect,
                     &h->etab, &h->overlap, &h->matches, &h->mark, &h->order, &h->work_ctr,
                     &h->dev_rm, &h->z_rm, &h->dev_cm, &h->z_cm, &h->varpart, &h->varfinal,
-                    &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C};
+                    &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C, &h->dn_S};
   for (DevBuf* b : bufs) cv_release(*b);
   for (DevBuf& b : h->bk) cv_release(b);
   for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->s_up) cudaStreamDestroy(h->s_up);
+  if (h->s_dn) cudaStreamDestroy(h->s_dn);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -132,7 +141,45 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
     h->opt_path = (int)value;
     return CV_OK;
   }
+  if (!strcmp(key, "dense_cta_pair")) { h->opt_pair = value != 0; return CV_OK; }
+  if (!strcmp(key, "cell_chunk")) {
+    if (value < 0) CV_FAIL(h, CV_ERR_INVALID, "cell_chunk must be >= 0");
+    h->opt_chunk = value;
+    return CV_OK;
+  }
+  if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
   CV_FAIL(h, CV_ERR_INVALID, "unknown option %s", key);
+}
+
+// ---- timed spans ----------------------------------------------------------------------------------------
+static cudaEvent_t span_event(cv_handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+void cv_spans_reset(cv_handle* h) {
+  h->ev_used = 0;
+  h->spans.clear();
+}
+void cv_span_begin(cv_handle* h, int cat) {
+  cv_handle::Span sp;
+  sp.a = span_event(h);
+  sp.b = span_event(h);
+  sp.cat = cat;
+  cudaEventRecord(sp.a, h->stream);
+  h->spans.push_back(sp);
+}
+void cv_span_end(cv_handle* h) { cudaEventRecord(h->spans.back().b, h->stream); }
+void cv_spans_collect(cv_handle* h, double* ms_by_cat) {
+  for (int i = 0; i < CV_SPAN_N; ++i) ms_by_cat[i] = 0.0;
+  for (const auto& sp : h->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ms_by_cat[sp.cat] += ms;
+    else cudaGetLastError();
+  }
 }
 
 extern "C" void* cv_stream(cv_handle* h) { return h ? (void*)h->stream : nullptr; }
@@ -219,7 +266,7 @@ __device__ __forceinline__ uint32_t load_count<uint8_t>(const uint8_t* __restric
 template <typename XT>
 __global__ void __launch_bounds__(256)
 k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
-              const XT* __restrict__ x, int64_t nnz, int P, int N,
+              const XT* __restrict__ x, int64_t e_begin, int64_t nnz /* end of the range */, int P, int N,
               uint32_t* __restrict__ val, unsigned long long* __restrict__ peak_tot,
               unsigned long long* __restrict__ cell_tot, uint32_t* __restrict__ flags) {
   const unsigned full = 0xffffffffu;
@@ -227,7 +274,7 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   uint32_t bad = 0, vmax = 0;
   int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  for (int64_t base = warp_id * 32; base < nnz; base += warps_total * 32) {
+  for (int64_t base = e_begin + warp_id * 32; base < nnz; base += warps_total * 32) {
     int64_t e = base + lane;
     bool active = e < nnz;
     int c = find_col_warp(colptr, N, active ? e : nnz - 1, nnz, active);
@@ -281,10 +328,17 @@ k_totals_finish(unsigned long long* __restrict__ peak_tot, int P) {
   }
 }
 
+// fragments per sample as doubles + the largest cell total (bounds the s32 accumulators)
 __global__ void k_u64_to_f64(const unsigned long long* __restrict__ in, double* __restrict__ out,
-                             int64_t n) {
+                             int64_t n, unsigned long long* __restrict__ vmax) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (double)in[i];
+  unsigned long long v = i < n ? in[i] : 0ull;
+  if (i < n) out[i] = (double)v;
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(vmax, v);
 }
 
 // dense column-major -> CSC (rows within a column land in arbitrary order; nothing downstream
@@ -563,8 +617,13 @@ static double wall_ms() {
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-// runs K1 on the device-resident CSC (colptr int64, rowidx, xraw of x_type)
-static int counts_sums(cv_handle* h, int x_type) {
+// K1 on the device-resident CSC (colptr int64, rowidx, xraw of x_type), in pieces so that the
+// streamed call can run it per uploaded cell chunk:
+//   cv_counts_begin         buffers + zeroed totals / flags
+//   cv_counts_range         nonzeros [e0, e1) = cells [c0, c1): validation, val, totals, fps
+//   cv_counts_finish_async  grand total
+//   cv_counts_verdict       host-side reading of the flag words (after a stream sync)
+int cv_counts_begin(cv_handle* h) {
   int64_t P = h->P, N = h->N, nnz = h->nnz;
   CV_TRY(cv_ensure(h, h->val, (size_t)nnz * 4));
   CV_TRY(cv_ensure(h, h->peak_tot, (size_t)(P + 1) * 8));
@@ -573,52 +632,76 @@ static int counts_sums(cv_handle* h, int x_type) {
   CV_TRY(cv_ensure(h, h->flags, 64));
   CV_CUDA(h, cudaMemsetAsync(h->peak_tot.p, 0, (size_t)(P + 1) * 8, h->stream));
   CV_CUDA(h, cudaMemsetAsync(h->cell_tot.p, 0, (size_t)N * 8, h->stream));
-  CV_CUDA(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
-  unsigned grid = grid_for(h, nnz, 256 * 4);
+  CV_CUDA(h, cudaMemsetAsync(h->flags.p, 0, 32, h->stream));
+  h->have_counts = false;
+  return CV_OK;
+}
+
+int cv_counts_range(cv_handle* h, int x_type, int64_t e0, int64_t e1, int64_t c0, int64_t c1) {
+  int64_t P = h->P, N = h->N;
+  unsigned grid = grid_for(h, e1 - e0, 256 * 4);
   auto pt = h->peak_tot.as<unsigned long long>();
   auto ct = h->cell_tot.as<unsigned long long>();
-  if (nnz > 0) {
+  if (e1 > e0) {
     switch (x_type) {
       case CV_F64:
         CV_LAUNCH(h, k_counts_sums<double>, grid, 256, 0, h->colptr.as<int64_t>(),
-                  h->rowidx.as<int32_t>(), h->xraw.as<double>(), nnz, (int)P, (int)N,
+                  h->rowidx.as<int32_t>(), h->xraw.as<double>(), e0, e1, (int)P, (int)N,
                   h->val.as<uint32_t>(), pt, ct, h->flags.as<uint32_t>());
         break;
       case CV_F32:
         CV_LAUNCH(h, k_counts_sums<float>, grid, 256, 0, h->colptr.as<int64_t>(),
-                  h->rowidx.as<int32_t>(), h->xraw.as<float>(), nnz, (int)P, (int)N,
+                  h->rowidx.as<int32_t>(), h->xraw.as<float>(), e0, e1, (int)P, (int)N,
                   h->val.as<uint32_t>(), pt, ct, h->flags.as<uint32_t>());
         break;
       case CV_I32:
         CV_LAUNCH(h, k_counts_sums<int32_t>, grid, 256, 0, h->colptr.as<int64_t>(),
-                  h->rowidx.as<int32_t>(), h->xraw.as<int32_t>(), nnz, (int)P, (int)N,
+                  h->rowidx.as<int32_t>(), h->xraw.as<int32_t>(), e0, e1, (int)P, (int)N,
                   h->val.as<uint32_t>(), pt, ct, h->flags.as<uint32_t>());
         break;
       case CV_U8:
         CV_LAUNCH(h, k_counts_sums<uint8_t>, grid, 256, 0, h->colptr.as<int64_t>(),
-                  h->rowidx.as<int32_t>(), h->xraw.as<uint8_t>(), nnz, (int)P, (int)N,
+                  h->rowidx.as<int32_t>(), h->xraw.as<uint8_t>(), e0, e1, (int)P, (int)N,
                   h->val.as<uint32_t>(), pt, ct, h->flags.as<uint32_t>());
         break;
       default:
         CV_FAIL(h, CV_ERR_INVALID, "unsupported value type %d", x_type);
     }
   }
-  CV_LAUNCH(h, k_totals_finish, 1, 1024, 0, pt, (int)P);
-  CV_LAUNCH(h, k_u64_to_f64, (unsigned)((N + 255) / 256), 256, 0, ct, h->fps.as<double>(), N);
-  uint32_t flags[2] = {0, 0};
-  CV_CUDA(h, cudaMemcpyAsync(flags, h->flags.p, 8, cudaMemcpyDeviceToHost, h->stream));
-  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (c1 > c0)
+    CV_LAUNCH(h, k_u64_to_f64, (unsigned)((c1 - c0 + 255) / 256), 256, 0, ct + c0, h->fps.as<double>() + c0,
+              c1 - c0, reinterpret_cast<unsigned long long*>(h->flags.as<uint32_t>() + 2));
+  return CV_OK;
+}
+
+int cv_counts_finish_async(cv_handle* h) {
+  CV_LAUNCH(h, k_totals_finish, 1, 1024, 0, h->peak_tot.as<unsigned long long>(), (int)h->P);
+  return CV_OK;
+}
+
+int cv_counts_verdict(cv_handle* h, const uint32_t* flags) {
   if (flags[0] & FLAG_BADROW) CV_FAIL(h, CV_ERR_INVALID, "counts: row index outside [0, P)");
   if (flags[0] & FLAG_HUGE) CV_FAIL(h, CV_ERR_UNSUPPORTED, "counts: value >= 2^32");
   if (flags[0] & FLAG_BADVAL)
     CV_FAIL(h, CV_ERR_INVALID,
             "counts must be finite, non-negative and integer-valued (counts_check)");
   h->max_val = flags[1];
+  h->max_cell_tot = (uint64_t)flags[2] | ((uint64_t)flags[3] << 32);
   h->have_counts = true;
   h->layout_valid = false;
   h->totals_committed = true;  // single shard until the host says otherwise
   h->have_results = false;
   return CV_OK;
+}
+
+static int counts_sums(cv_handle* h, int x_type) {
+  CV_TRY(cv_counts_begin(h));
+  CV_TRY(cv_counts_range(h, x_type, 0, h->nnz, 0, h->N));
+  CV_TRY(cv_counts_finish_async(h));
+  uint32_t flags[4] = {0, 0, 0, 0};
+  CV_CUDA(h, cudaMemcpyAsync(flags, h->flags.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return cv_counts_verdict(h, flags);
 }
 
 extern "C" int cv_set_counts_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr,

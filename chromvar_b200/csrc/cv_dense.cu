@@ -18,6 +18,12 @@
 // the fused fp64 epilogue (expected, raw deviations, mean / sd over iterations, bias-corrected
 // deviation, z, NA mask, variability partials; :488-520) never writes an intermediate to HBM.
 //
+// Two kernels share the epilogue: k_dense_contract (one CTA per 128-cell x 256-row tile) and
+// k_dense_contract_pair (tcgen05 cta_group::2: a CTA pair per 256-cell x 256-row tile; default).
+// Counts above 255 run as u8 digit planes (one GEMM per plane, int64 sums combined in HBM scratch
+// and finished by k_dense_finalize_sums); cells are processed in chunks so the densified operand
+// never exceeds a fixed budget and host copies can overlap the GEMMs.
+//
 // Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0  TMA producer          warp 1  MMA issuer        warp 2  TMEM allocator
 //   warps 4-7  epilogue (TMEM lane quadrant = warp % 4)
@@ -40,6 +46,10 @@
 #define DN_B_BYTES (DN_BLOCK_N * DN_BLOCK_K)
 #define DN_STAGE_BYTES (DN_A_BYTES + DN_B_BYTES)
 #define DN_SMEM_BYTES (DN_STAGES * DN_STAGE_BYTES + 1024 /*align*/ + 4096 /*winv*/ + 256 /*barriers*/)
+// CTA-pair kernel: each CTA stages its 128 cells and half of the 256 stacked rows
+#define DN_STAGES2 6
+#define DN_STAGE2_BYTES (2 * DN_A_BYTES)
+#define DN_SMEM2_BYTES (DN_STAGES2 * DN_STAGE2_BYTES + 1024 + 4096 + 256)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -120,20 +130,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cluster / CTA-pair PTX wrappers --------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) inside CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA of a pair: data lands in this CTA's shared memory, the transaction bytes
+// are counted on the leader CTA's mbarrier (bar_cluster_addr is a shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst,
+                                                 int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(x), "r"(y)
+      : "memory");
+}
+// arrive (once the pair's MMAs issued so far have retired) on the barrier at this shared-memory
+// offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 x 32: 128 rows from each CTA] * B[32 x 256: 128 columns from each CTA]
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u),
+        "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
 // ---- the GEMM + fused epilogue -----------------------------------------------------------------------
+enum { DN_EPI_FUSED = 0, DN_EPI_SUMS = 1 };
+
 struct DenseParams {
-  int N, K, B, G;            // cells, annotations, iterations, annotations per 256-row group
-  int n_cell_blocks, n_groups, n_kblocks;
-  int64_t n_tiles;
+  int N, K, B, G;            // cells (whole shard), annotations, iterations, annotations per 256-row group
+  int cb0;                   // global index of this launch's first 128-cell block
+  int c_end;                 // cells >= c_end are padding of this launch (no output)
+  int n_cell_blocks;         // 128-cell blocks in this launch (chunk of the shard)
+  int ncb_total;             // 128-cell blocks of the whole shard (stride of varpart)
+  int n_groups, n_kblocks;
+  int64_t n_tiles;           // work items: (cell block | cell block pair) x group
   int band;                  // groups per raster band
   const int64_t* annoptr;
   const double* etab;        // [K][B+1]
   const double* fps;         // [N]
   double* dev_rm;            // [K][N]
   double* z_rm;
-  double* varpart;           // [K][n_cell_blocks][4]
+  double* varpart;           // [K][ncb_total][4]
   long long* obs;            // [K][N] or null
   long long* samp;           // [K][B][N] or null
+  // DN_EPI_SUMS: exact integer sums of one u8 digit plane, added into sums[(k*(B+1)+j)*sums_ld + (c - sums_c0)]
+  long long* sums;
+  int sums_ld, sums_c0, sums_shift, sums_acc;
 };
 
 struct DWelford { double n, mean, m2; };
@@ -147,19 +214,159 @@ __device__ __forceinline__ DWelford dw_merge(const DWelford& a, const DWelford& 
   r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
   return r;
 }
+// deterministic, lane-symmetric tree: every lane ends with the same bits
+__device__ __forceinline__ void dw_warp_reduce(DWelford& wf, double& nonfinite, int lane) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    DWelford b;
+    b.n = __shfl_xor_sync(full, wf.n, o);
+    b.mean = __shfl_xor_sync(full, wf.mean, o);
+    b.m2 = __shfl_xor_sync(full, wf.m2, o);
+    wf = (lane & o) ? dw_merge(b, wf) : dw_merge(wf, b);
+    nonfinite += __shfl_xor_sync(full, nonfinite, o);
+  }
+}
 
-__device__ __forceinline__ void dn_decode_tile(const DenseParams& p, int64_t tile, int& cb, int& g) {
-  // raster: bands of `band` groups; inside a band cell blocks are the slow index so that the
-  // ~148 concurrently running tiles cover about band groups x 148/band cell blocks (L2 reuse)
-  const int64_t per_band = (int64_t)p.band * p.n_cell_blocks;
+// per (annotation, cell) running state over the B+1 stacked sums (R/compute_deviations.R:488-520)
+struct DnCell { double obs_v, pivot, sum, sumsq; };
+__device__ __forceinline__ void dn_cell_add(DnCell& a, int j, double sv, double winv_j, double rf) {
+  if (j == 0) {
+    a.obs_v = sv;
+    a.sum = 0.0;
+    a.sumsq = 0.0;
+  } else {
+    // (sampled - sampled_expected) / sampled_expected with sampled_expected = E_j * fps (:502-504),
+    // accumulated relative to the first iteration's value (exact zeros when all agree)
+    const double d = sv * winv_j * rf - 1.0;
+    if (j == 1) a.pivot = d;
+    const double dd = d - a.pivot;
+    a.sum += dd;
+    a.sumsq += dd * dd;
+  }
+}
+__device__ __forceinline__ void dn_cell_finish(const DnCell& a, double E0, double fpsv, int B, bool empty,
+                                               double& devv, double& zv) {
+  const double expected = E0 * fpsv;                                  // :488
+  const double obs_dev = (a.obs_v - expected) / expected;             // :489
+  const double Bd = (double)B;
+  const double mshift = a.sum / Bd;
+  const double mean = a.pivot + mshift;                               // :511
+  const double var = (a.sumsq - a.sum * mshift) / (Bd - 1.0);
+  const double sd = sqrt(var > 0.0 ? var : (var == var ? 0.0 : var)); // :512
+  devv = obs_dev - mean;                                              // :514
+  zv = devv / sd;                                                     // :515
+  if (empty || expected < 1.0) devv = zv = cv_na_real();              // :458-461, :509, :517-520
+}
+
+// raster: bands of `band` groups; inside a band the cell units are the slow index so that the
+// concurrently running tiles cover about band groups x (#CTAs / band) cell units (L2 reuse)
+__device__ __forceinline__ void dn_decode_tile(int band, int n_groups, int n_units, int64_t tile, int& unit, int& g) {
+  const int64_t per_band = (int64_t)band * n_units;
   const int bnd = (int)(tile / per_band);
   const int64_t r = tile - (int64_t)bnd * per_band;
-  const int g0 = bnd * p.band;
-  const int gw = min(p.band, p.n_groups - g0);
-  cb = (int)(r / gw);
+  const int g0 = bnd * band;
+  const int gw = min(band, n_groups - g0);
+  unit = (int)(r / gw);
   g = g0 + (int)(r % gw);
 }
 
+// 1 / E[k][j] of the group's annotations -> shared memory (epilogue warps only: bar 1, 128 threads)
+__device__ __forceinline__ void dn_epi_stage_tables(const DenseParams& prm, int g, double* s_winv, int et) {
+  const int I = prm.B + 1;
+  const int k0 = g * prm.G;
+  const int nk = min(prm.G, prm.K - k0);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int i = et; i < nk * I; i += 128) s_winv[i] = 1.0 / prm.etab[(int64_t)k0 * I + i];
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// One epilogue thread = one cell (one TMEM lane): streams the 256 accumulator columns of its lane.
+// FUSED: deviations / z / variability partials straight from TMEM.  SUMS: the integer sums of this
+// digit plane are added (shifted) into the int64 scratch and finished by k_dense_finalize_sums.
+template <int MODE>
+__device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_local, int g, uint32_t taddr,
+                                               const double* s_winv, double* s_wred, int q4, int lane) {
+  const int I = prm.B + 1;
+  const int k0 = g * prm.G;
+  const int nk = min(prm.G, prm.K - k0);
+  const int c = (prm.cb0 + cb_local) * DN_BLOCK_M + q4 * 32 + lane;
+  const bool live = c < prm.c_end;
+  const double fpsv = live ? prm.fps[c] : 1.0;
+  const double rf = 1.0 / fpsv;
+  int a = 0, j = 0;
+  DnCell cell = {0.0, 0.0, 0.0, 0.0};
+  const int ncols = nk * I;
+  for (int col0 = 0; col0 < ncols; col0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)col0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      if (col0 + u < ncols) {
+        const int k = k0 + a;
+        if (MODE == DN_EPI_SUMS) {
+          if (live) {
+            long long* dst = prm.sums + ((int64_t)k * I + j) * prm.sums_ld + (c - prm.sums_c0);
+            const long long v = (long long)(int)r[u] << prm.sums_shift;
+            *dst = prm.sums_acc ? *dst + v : v;
+          }
+          if (++j == I) { j = 0; ++a; }
+        } else {
+          const double sv = (double)(int)r[u];
+          dn_cell_add(cell, j, sv, s_winv[a * I + j], rf);
+          if (live) {
+            if (j == 0) { if (prm.obs) prm.obs[(int64_t)k * prm.N + c] = (long long)(int)r[u]; }
+            else if (prm.samp) prm.samp[((int64_t)k * prm.B + (j - 1)) * prm.N + c] = (long long)(int)r[u];
+          }
+          if (++j == I) {
+            const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
+            double devv, zv;
+            dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
+            DWelford wf = {0.0, 0.0, 0.0};
+            double nonfinite = 0.0;
+            if (live) {
+              prm.dev_rm[(int64_t)k * prm.N + c] = devv;
+              prm.z_rm[(int64_t)k * prm.N + c] = zv;
+              if (isfinite(zv)) { wf.n = 1.0; wf.mean = zv; } else nonfinite = 1.0;
+            }
+            // variability partial of (k, cell block): warp tree, then the 4 epilogue warps
+            dw_warp_reduce(wf, nonfinite, lane);
+            if (lane == 0) {
+              double* w = s_wred + (a * 4 + q4) * 4;
+              w[0] = wf.n; w[1] = wf.mean; w[2] = wf.m2; w[3] = nonfinite;
+            }
+            j = 0;
+            ++a;
+          }
+        }
+      }
+    }
+  }
+}
+
+// merge the 4 epilogue warps' variability partials of every annotation of the group
+__device__ __forceinline__ void dn_epi_merge(const DenseParams& prm, int cb_local, int g, const double* s_wred,
+                                             int et) {
+  const int k0 = g * prm.G;
+  const int nk = min(prm.G, prm.K - k0);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (et < nk) {
+    DWelford tot = {0.0, 0.0, 0.0};
+    double nf = 0.0;
+    for (int w4 = 0; w4 < 4; ++w4) {
+      const double* w = s_wred + (et * 4 + w4) * 4;
+      DWelford b = {w[0], w[1], w[2]};
+      tot = dw_merge(tot, b);
+      nf += w[3];
+    }
+    double* vp = prm.varpart + ((int64_t)(k0 + et) * prm.ncb_total + prm.cb0 + cb_local) * 4;
+    vp[0] = tot.n; vp[1] = tot.mean; vp[2] = tot.m2; vp[3] = nf;
+  }
+}
+
+// ---- single-CTA kernel: tile = 128 cells x 256 stacked rows ----------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(DN_THREADS, 1)
 k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_m,
                  const DenseParams prm) {
@@ -169,7 +376,7 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
   unsigned char* smem_a = smem;                                   // [STAGES][16 KB]
   unsigned char* smem_b = smem + DN_STAGES * DN_A_BYTES;          // [STAGES][32 KB]
   double* s_winv = reinterpret_cast<double*>(smem + DN_STAGES * DN_STAGE_BYTES);            // [256]
-  double* s_wred = s_winv + 256;                                                            // [4][4][...]
+  double* s_wred = s_winv + 256;                                                            // [G][4][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DN_STAGES * DN_STAGE_BYTES + 4096);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + DN_STAGES;       // [STAGES]
@@ -178,7 +385,6 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DN_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int I = prm.B + 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
@@ -206,7 +412,7 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
       uint32_t ph = 0;
       for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
         int cb, g;
-        dn_decode_tile(prm, tile, cb, g);
+        dn_decode_tile(prm.band, prm.n_groups, prm.n_cell_blocks, tile, cb, g);
         for (int kb = 0; kb < prm.n_kblocks; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1u);
           mbar_expect_tx(full_bar + s, DN_STAGE_BYTES);
@@ -247,110 +453,20 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
     // ===== epilogue: one thread = one cell (TMEM lane) =====
     const int q4 = warp & 3;                   // TMEM lane quadrant this warp may read
     const int et = threadIdx.x - 128;          // 0..127
-    const unsigned full = 0xffffffffu;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++it) {
       int cb, g;
-      dn_decode_tile(prm, tile, cb, g);
+      dn_decode_tile(prm.band, prm.n_groups, prm.n_cell_blocks, tile, cb, g);
       const int as = (int)(it & 1);
-      const int k0 = g * prm.G;
-      const int nk = min(prm.G, prm.K - k0);
-      // 1 / E[k][j] for the annotations of this group
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < nk * I; i += 128) s_winv[i] = 1.0 / prm.etab[(int64_t)k0 * I + i];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int c = cb * DN_BLOCK_M + q4 * 32 + lane;
-      const bool live = c < prm.N;
-      const double fpsv = live ? prm.fps[c] : 1.0;
-      const double rf = 1.0 / fpsv;
-
+      if (MODE == DN_EPI_FUSED) dn_epi_stage_tables(prm, g, s_winv, et);
       mbar_wait(tfull_bar + as, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * DN_BLOCK_N);
-
-      // stream the 256 columns; (a, j) walks (annotation in group, iteration)
-      int a = 0, j = 0;
-      double obs_v = 0.0, pivot = 0.0, sum = 0.0, sumsq = 0.0;
-      const int ncols = nk * I;
-      for (int col0 = 0; col0 < ncols; col0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)col0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          if (col0 + u < ncols) {
-            const double sv = (double)(int)r[u];
-            const int k = k0 + a;
-            if (j == 0) {
-              obs_v = sv;
-              sum = 0.0; sumsq = 0.0;
-              if (prm.obs && live) prm.obs[(int64_t)k * prm.N + c] = (long long)(int)r[u];
-            } else {
-              // (sampled - sampled_expected) / sampled_expected with sampled_expected = E_j * fps
-              // accumulated relative to the first iteration's value (exact zeros when all agree)
-              const double d = sv * s_winv[a * I + j] * rf - 1.0;
-              if (j == 1) pivot = d;
-              const double dd = d - pivot;
-              sum += dd;
-              sumsq += dd * dd;
-              if (prm.samp && live) prm.samp[((int64_t)k * prm.B + (j - 1)) * prm.N + c] = (long long)(int)r[u];
-            }
-            if (++j == I) {
-              // ---- finish annotation k for this cell (R/compute_deviations.R:488-520) ----
-              const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
-              const double E0 = prm.etab[(int64_t)k * I];
-              const double expected = E0 * fpsv;
-              const double obs_dev = (obs_v - expected) / expected;
-              const double Bd = (double)prm.B;
-              const double mshift = sum / Bd;
-              const double mean = pivot + mshift;
-              const double var = (sumsq - sum * mshift) / (Bd - 1.0);
-              const double sd = sqrt(var > 0.0 ? var : (var == var ? 0.0 : var));
-              double devv = obs_dev - mean, zv = devv / sd;
-              if (empty || expected < 1.0) devv = zv = cv_na_real();
-              DWelford wf = {0.0, 0.0, 0.0};
-              double nonfinite = 0.0;
-              if (live) {
-                prm.dev_rm[(int64_t)k * prm.N + c] = devv;
-                prm.z_rm[(int64_t)k * prm.N + c] = zv;
-                if (isfinite(zv)) { wf.n = 1.0; wf.mean = zv; } else nonfinite = 1.0;
-              }
-              // variability partial of (k, cell block): warp tree, then the 4 epilogue warps
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                DWelford b;
-                b.n = __shfl_xor_sync(full, wf.n, o);
-                b.mean = __shfl_xor_sync(full, wf.mean, o);
-                b.m2 = __shfl_xor_sync(full, wf.m2, o);
-                wf = (lane & o) ? dw_merge(b, wf) : dw_merge(wf, b);
-                nonfinite += __shfl_xor_sync(full, nonfinite, o);
-              }
-              if (lane == 0) {
-                double* w = s_wred + (a * 4 + q4) * 4;
-                w[0] = wf.n; w[1] = wf.mean; w[2] = wf.m2; w[3] = nonfinite;
-              }
-              j = 0;
-              ++a;
-            }
-          }
-        }
-      }
+      dn_epi_consume<MODE>(prm, cb, g, taddr, s_winv, s_wred, q4, lane);
       // every TMEM column of this stage has been read: hand the accumulator back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar + as);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et < nk) {
-        DWelford tot = {0.0, 0.0, 0.0};
-        double nf = 0.0;
-        for (int w4 = 0; w4 < 4; ++w4) {
-          const double* w = s_wred + (et * 4 + w4) * 4;
-          DWelford b = {w[0], w[1], w[2]};
-          tot = dw_merge(tot, b);
-          nf += w[3];
-        }
-        double* vp = prm.varpart + ((int64_t)(k0 + et) * prm.n_cell_blocks + cb) * 4;
-        vp[0] = tot.n; vp[1] = tot.mean; vp[2] = tot.m2; vp[3] = nf;
-      }
+      if (MODE == DN_EPI_FUSED) dn_epi_merge(prm, cb, g, s_wred, et);
     }
   }
   tc_fence_before();
@@ -358,6 +474,179 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- CTA-pair kernel: tile = 256 cells x 256 stacked rows on two SMs (tcgen05 cta_group::2) -------------
+// Each CTA of the pair stages its own 128 cells (A) and one half of the 256 stacked rows (B), so
+// the L2 -> SM operand stream per SM drops by a third against the single-CTA tile and the ring is
+// 6 stages of 32 KB.  The leader CTA (cluster rank 0) issues every MMA; its commits are multicast
+// to the barriers of both CTAs.  Both CTAs run the same epilogue on their own TMEM lanes.
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
+k_dense_contract_pair(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_m,
+                      const DenseParams prm) {
+  extern __shared__ unsigned char dn_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dn_smem_raw) + 1023) &
+                                                         ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;                                   // [STAGES2][16 KB] own cells
+  unsigned char* smem_b = smem + DN_STAGES2 * DN_A_BYTES;         // [STAGES2][16 KB] own half of the rows
+  double* s_winv = reinterpret_cast<double*>(smem + DN_STAGES2 * DN_STAGE2_BYTES);          // [256]
+  double* s_wred = s_winv + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DN_STAGES2 * DN_STAGE2_BYTES + 4096);
+  uint64_t* full_bar = bars;                     // [STAGES2]  (the leader's are the ones waited on)
+  uint64_t* empty_bar = bars + DN_STAGES2;       // [STAGES2]
+  uint64_t* tfull_bar = bars + 2 * DN_STAGES2;   // [2]
+  uint64_t* tempty_bar = bars + 2 * DN_STAGES2 + 2;   // [2]  (leader's: 256 arrivals, both CTAs' epilogues)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DN_STAGES2 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_units = (prm.n_cell_blocks + 1) >> 1;               // 256-cell units of this launch
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_m) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < DN_STAGES2; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own cells + own half of the stacked rows =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = pair_id; tile < prm.n_tiles; tile += n_pairs) {
+        int unit, g;
+        dn_decode_tile(prm.band, prm.n_groups, n_units, tile, unit, g);
+        const int yc = (2 * unit + (int)rank) * DN_BLOCK_M;
+        const int ym = g * DN_BLOCK_N + (int)rank * (DN_BLOCK_N / 2);
+        for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+          mbar_wait(empty_bar + s, ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(full_bar + s, 2 * DN_STAGE2_BYTES);
+          const uint32_t fb = mapa_u32(smem_u32(full_bar + s), 0);
+          tma_load_2d_pair(&map_c, fb, smem_a + s * DN_A_BYTES, kb * DN_BLOCK_K, yc);
+          tma_load_2d_pair(&map_m, fb, smem_b + s * DN_A_BYTES, kb * DN_BLOCK_K, ym);
+          if (++s == DN_STAGES2) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_u8(2 * DN_BLOCK_M, DN_BLOCK_N);
+      int s = 0;
+      uint32_t ph = 0;
+      int64_t it = 0;
+      for (int64_t tile = pair_id; tile < prm.n_tiles; tile += n_pairs, ++it) {
+        const int as = (int)(it & 1);
+        mbar_wait(tempty_bar + as, (uint32_t)((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * DN_BLOCK_N);
+        for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + s * DN_A_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + s * DN_A_BYTES));
+#pragma unroll
+          for (int k = 0; k < DN_BLOCK_K / DN_UMMA_K; ++k)
+            umma_i8_pair(tmem_d, da + (uint64_t)(k * DN_UMMA_K / 16), db + (uint64_t)(k * DN_UMMA_K / 16), idesc,
+                         (kb | k) ? 1u : 0u);
+          tc_commit_pair(empty_bar + s, 3);    // frees the stage in both CTAs when these MMAs retire
+          if (++s == DN_STAGES2) { s = 0; ph ^= 1u; }
+        }
+        tc_commit_pair(tfull_bar + as, 3);     // accumulator tile complete: both epilogues may start
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): one thread = one cell (TMEM lane of this CTA) =====
+    const int q4 = warp & 3;
+    const int et = threadIdx.x - 128;
+    int64_t it = 0;
+    for (int64_t tile = pair_id; tile < prm.n_tiles; tile += n_pairs, ++it) {
+      int unit, g;
+      dn_decode_tile(prm.band, prm.n_groups, n_units, tile, unit, g);
+      const int cb = 2 * unit + (int)rank;
+      const int as = (int)(it & 1);
+      if (MODE == DN_EPI_FUSED) dn_epi_stage_tables(prm, g, s_winv, et);
+      mbar_wait(tfull_bar + as, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * DN_BLOCK_N);
+      dn_epi_consume<MODE>(prm, cb, g, taddr, s_winv, s_wred, q4, lane);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar + as), 0));
+      if (MODE == DN_EPI_FUSED && cb < prm.n_cell_blocks) dn_epi_merge(prm, cb, g, s_wred, et);
+      else if (MODE == DN_EPI_FUSED) asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  // no CTA may leave (or free TMEM) while its peer can still read its shared memory / signal it
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- digit-plane finish: int64 sums -> deviations / z / variability partials -------------------------------
+// grid (cell blocks of the chunk, K); 128 threads = the cells of one block.  Same arithmetic as the
+// fused epilogue (dn_cell_add / dn_cell_finish), so results are bit-identical to the one-plane path.
+__global__ void __launch_bounds__(128)
+k_dense_finalize_sums(const DenseParams prm) {
+  __shared__ double s_w[4][4];
+  const int I = prm.B + 1;
+  const int k = blockIdx.y, cb_local = blockIdx.x;
+  const int lane = threadIdx.x & 31, w4 = threadIdx.x >> 5;
+  const int c = (prm.cb0 + cb_local) * DN_BLOCK_M + threadIdx.x;
+  const bool live = c < prm.c_end;
+  const double fpsv = live ? prm.fps[c] : 1.0;
+  const double rf = 1.0 / fpsv;
+  const double* et = prm.etab + (int64_t)k * I;
+  DnCell cell = {0.0, 0.0, 0.0, 0.0};
+  for (int j = 0; j < I; ++j) {
+    const long long s = live ? prm.sums[((int64_t)k * I + j) * prm.sums_ld + (c - prm.sums_c0)] : 0ll;
+    dn_cell_add(cell, j, (double)s, 1.0 / et[j], rf);
+    if (live) {
+      if (j == 0) { if (prm.obs) prm.obs[(int64_t)k * prm.N + c] = s; }
+      else if (prm.samp) prm.samp[((int64_t)k * prm.B + (j - 1)) * prm.N + c] = s;
+    }
+  }
+  const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
+  double devv, zv;
+  dn_cell_finish(cell, et[0], fpsv, prm.B, empty, devv, zv);
+  DWelford wf = {0.0, 0.0, 0.0};
+  double nonfinite = 0.0;
+  if (live) {
+    prm.dev_rm[(int64_t)k * prm.N + c] = devv;
+    prm.z_rm[(int64_t)k * prm.N + c] = zv;
+    if (isfinite(zv)) { wf.n = 1.0; wf.mean = zv; } else nonfinite = 1.0;
+  }
+  dw_warp_reduce(wf, nonfinite, lane);
+  if (lane == 0) { s_w[w4][0] = wf.n; s_w[w4][1] = wf.mean; s_w[w4][2] = wf.m2; s_w[w4][3] = nonfinite; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DWelford tot = {0.0, 0.0, 0.0};
+    double nf = 0.0;
+    for (int w = 0; w < 4; ++w) {
+      DWelford b = {s_w[w][0], s_w[w][1], s_w[w][2]};
+      tot = dw_merge(tot, b);
+      nf += s_w[w][3];
+    }
+    double* vp = prm.varpart + ((int64_t)k * prm.ncb_total + prm.cb0 + cb_local) * 4;
+    vp[0] = tot.n; vp[1] = tot.mean; vp[2] = tot.m2; vp[3] = nf;
   }
 }
 
@@ -386,58 +675,106 @@ static int make_map_u8(cv_handle* h, CUtensorMap* map, void* base, uint64_t rows
   return CV_OK;
 }
 
-// can the dense path represent this problem exactly?  (reason filled when it cannot)
-int cv_dense_feasible(cv_handle* h, std::string* reason) {
+static inline int64_t round_up(int64_t v, int64_t m) { return ((v + m - 1) / m) * m; }
+
+// Can the dense path represent this problem exactly, and in which shape?  max_val = largest count
+// (0: not known yet -- streaming call -- assume one u8 plane and verify afterwards).
+// want_chunk: cells per GEMM launch requested by the caller (0 = as many as memory allows).
+int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan* pl, std::string* why) {
   const int I = h->B + 1;
-  if (I > DN_BLOCK_N) { *reason = "niterations + 1 > 256"; return 0; }
-  if (h->max_val > 255) { *reason = "counts above 255 (u8 operand)"; return 0; }
-  const int G = std::min(DN_BLOCK_N / I, DN_MAX_G);
-  const int64_t Ppad = ((h->P + DN_BLOCK_K - 1) / DN_BLOCK_K) * DN_BLOCK_K;
-  const int64_t n_groups = (h->K + G - 1) / G;
-  const int64_t ncb = (h->N + DN_BLOCK_M - 1) / DN_BLOCK_M;
-  const double bytes = (double)Ppad * ((double)n_groups * DN_BLOCK_N + (double)ncb * DN_BLOCK_M);
+  if (I > DN_BLOCK_N) { *why = "niterations + 1 > 256"; return 0; }
+  pl->I = I;
+  pl->G = std::min(DN_BLOCK_N / I, DN_MAX_G);
+  pl->Ppad = round_up(h->P, DN_BLOCK_K);
+  pl->n_groups = (int)((h->K + pl->G - 1) / pl->G);
+  pl->rowsM = (int64_t)pl->n_groups * DN_BLOCK_N;
+  pl->planes = 1;
+  for (uint32_t v = max_val >> 8; v; v >>= 8) pl->planes++;
+  pl->pair = h->opt_pair ? 1 : 0;
+  pl->m_bytes = pl->rowsM * pl->Ppad;
+  // per cell: one u8 row of the operand (+ the int64 sums scratch when digit planes are combined)
+  const double per_cell = (double)pl->Ppad + (pl->planes > 1 ? (double)h->K * I * 8.0 : 0.0);
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  const double avail = (double)free_b + (double)h->dn_M.cap + (double)h->dn_C.cap;
-  if (bytes > 0.85 * avail) { *reason = "dense operands do not fit in device memory"; return 0; }
+  const double avail = 0.85 * ((double)free_b + (double)h->dn_M.cap + (double)h->dn_C.cap + (double)h->dn_S.cap);
+  double budget = avail - (double)pl->m_bytes;
+  if (budget > 24e9) budget = 24e9;                       // operand chunk beyond this buys nothing
+  int64_t chunk = (int64_t)(budget / per_cell / 256.0) * 256;
+  if (chunk < 256) { *why = "dense operands do not fit in device memory"; return 0; }
+  const int64_t n256 = round_up(h->N, 256);
+  if (want_chunk > 0) chunk = std::min<int64_t>(chunk, round_up(want_chunk, 256));
+  if (h->opt_chunk > 0) chunk = std::min<int64_t>(chunk, round_up(h->opt_chunk, 256));
+  pl->chunk_cells = std::min(chunk, n256);
+  pl->c_bytes = pl->chunk_cells * pl->Ppad;
+  pl->sums_bytes = pl->planes > 1 ? pl->chunk_cells * (int64_t)h->K * I * 8 : 0;
   return 1;
 }
 
-double cv_dense_cost_ms(cv_handle* h) {
-  const int I = h->B + 1;
-  const int G = std::min(DN_BLOCK_N / I, DN_MAX_G);
-  const double Ppad = (double)(((h->P + DN_BLOCK_K - 1) / DN_BLOCK_K) * DN_BLOCK_K);
-  const double rows = (double)((h->K + G - 1) / G) * DN_BLOCK_N;
-  const double cells = (double)((h->N + DN_BLOCK_M - 1) / DN_BLOCK_M) * DN_BLOCK_M;
-  return 2.0 * Ppad * rows * cells / 2.0e15 * 1e3 + 0.3;     // ~2 POP/s sustained + fixed cost
+double cv_dense_cost_ms(cv_handle* h, const DensePlan& pl) {
+  const double cells = (double)round_up(h->N, DN_BLOCK_M);
+  const double gemm = 2.0 * (double)pl.Ppad * (double)pl.rowsM * cells / 2.5e15 * 1e3 * pl.planes;
+  const double build = (double)pl.m_bytes / 1.0e12 * 1e3;           // operand build ~1 TB/s
+  return gemm + build + 0.3;
 }
 
-// Builds the operands, runs the GEMM + fused epilogue.  On return dev_rm / z_rm / varpart (with
-// *T_out cell blocks per annotation) / obs / samp are filled exactly like k_contract fills them.
-// Returns CV_ERR_UNSUPPORTED (with *soft_fail = 1) when the exact-multiplicity check fails so the
-// caller can fall back to the sparse kernel.
-int cv_dense_contract(cv_handle* h, int keep_sums, int* T_out, int* soft_fail) {
-  *soft_fail = 0;
-  const int64_t P = h->P, N = h->N, K = h->K;
-  const int B = h->B, I = B + 1;
-  const int G = std::min(DN_BLOCK_N / I, DN_MAX_G);
-  const int64_t Ppad = ((P + DN_BLOCK_K - 1) / DN_BLOCK_K) * DN_BLOCK_K;
-  const int n_groups = (int)((K + G - 1) / G);
-  const int ncb = (int)((N + DN_BLOCK_M - 1) / DN_BLOCK_M);
-  const int64_t rowsM = (int64_t)n_groups * DN_BLOCK_N, rowsC = (int64_t)ncb * DN_BLOCK_M;
+template <int MODE>
+static int launch_gemm(cv_handle* h, const DensePlan& pl, const CUtensorMap& map_c, const CUtensorMap& map_m,
+                       const DenseParams& prm_in) {
+  DenseParams prm = prm_in;
+  if (pl.pair) {
+    const int n_units = (prm.n_cell_blocks + 1) / 2;
+    prm.n_tiles = (int64_t)n_units * prm.n_groups;
+    CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    DN_SMEM2_BYTES));
+    int pairs = h->num_sms / 2;
+    if (prm.n_tiles < pairs) pairs = (int)prm.n_tiles;
+    k_dense_contract_pair<MODE><<<2 * pairs, DN_THREADS, DN_SMEM2_BYTES, h->stream>>>(map_c, map_m, prm);
+  } else {
+    prm.n_tiles = (int64_t)prm.n_cell_blocks * prm.n_groups;
+    CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    DN_SMEM_BYTES));
+    const int grid = (int)std::min<int64_t>(prm.n_tiles, h->num_sms);
+    k_dense_contract<MODE><<<grid, DN_THREADS, DN_SMEM_BYTES, h->stream>>>(map_c, map_m, prm);
+  }
+  h->launches++;
+  CV_CUDA(h, cudaGetLastError());
+  return CV_OK;
+}
 
-  // ---- operands, per-annotation tables, exactness bounds (cv_dense_build.cu) -------------------
-  CV_TRY(cv_dense_build_operands(h, G, Ppad, rowsM, rowsC, soft_fail));
+// Operand M, per-annotation tables and the exactness counters: everything that does not depend on
+// the cells.  Asynchronous on the handle's stream.
+int cv_dense_prepare(cv_handle* h, const DensePlan& pl) {
+  CV_TRY(cv_ensure(h, h->dn_M, (size_t)pl.m_bytes));
+  CV_TRY(cv_ensure(h, h->dn_C, (size_t)pl.c_bytes));
+  if (pl.sums_bytes) CV_TRY(cv_ensure(h, h->dn_S, (size_t)pl.sums_bytes));
+  const int ncb_total = (int)((h->N + DN_BLOCK_M - 1) / DN_BLOCK_M);
+  CV_TRY(cv_ensure(h, h->varpart, (size_t)h->K * ncb_total * 4 * 8));
+  cv_span_begin(h, CV_SPAN_LAYOUT);
+  CV_TRY(cv_dense_build_rows(h, pl));
+  cv_span_end(h);
+  h->dn_flops = 0;
+  return CV_OK;
+}
 
-  // ---- GEMM + fused epilogue --------------------------------------------------------------------------
+// Cells [c0, c1) of this shard: densify (one u8 digit plane at a time), GEMM with fused epilogue
+// (or raw sums + finish when the counts need more than one plane).  Asynchronous.
+int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, int keep_sums) {
+  const int64_t N = h->N, K = h->K;
+  const int B = h->B;
+  if (c0 % 256 || c1 <= c0 || c1 - c0 > pl.chunk_cells)
+    CV_FAIL(h, CV_ERR_INVALID, "dense chunk [%lld, %lld) is not aligned / too large", (long long)c0, (long long)c1);
+  const int64_t rows = round_up(c1 - c0, 256);
   CUtensorMap map_c, map_m;
-  CV_TRY(make_map_u8(h, &map_c, h->dn_C.p, (uint64_t)rowsC, (uint64_t)Ppad, DN_BLOCK_M));
-  CV_TRY(make_map_u8(h, &map_m, h->dn_M.p, (uint64_t)rowsM, (uint64_t)Ppad, DN_BLOCK_N));
-  CV_TRY(cv_ensure(h, h->varpart, (size_t)K * ncb * 4 * 8));
+  CV_TRY(make_map_u8(h, &map_c, h->dn_C.p, (uint64_t)rows, (uint64_t)pl.Ppad, DN_BLOCK_M));
+  CV_TRY(make_map_u8(h, &map_m, h->dn_M.p, (uint64_t)pl.rowsM, (uint64_t)pl.Ppad, pl.pair ? DN_BLOCK_N / 2 : DN_BLOCK_N));
   DenseParams prm;
-  prm.N = (int)N; prm.K = (int)K; prm.B = B; prm.G = G;
-  prm.n_cell_blocks = ncb; prm.n_groups = n_groups; prm.n_kblocks = (int)(Ppad / DN_BLOCK_K);
-  prm.n_tiles = (int64_t)ncb * n_groups;
+  memset(&prm, 0, sizeof(prm));
+  prm.N = (int)N; prm.K = (int)K; prm.B = B; prm.G = pl.G;
+  prm.cb0 = (int)(c0 / DN_BLOCK_M);
+  prm.c_end = (int)std::min<int64_t>(c1, N);
+  prm.n_cell_blocks = (int)((std::min<int64_t>(c1, N) - c0 + DN_BLOCK_M - 1) / DN_BLOCK_M);
+  prm.ncb_total = (int)((N + DN_BLOCK_M - 1) / DN_BLOCK_M);
+  prm.n_groups = pl.n_groups; prm.n_kblocks = (int)(pl.Ppad / DN_BLOCK_K);
   prm.band = 12;
   prm.annoptr = h->annoptr.as<int64_t>();
   prm.etab = h->etab.as<double>();
@@ -447,14 +784,56 @@ int cv_dense_contract(cv_handle* h, int keep_sums, int* T_out, int* soft_fail) {
   prm.varpart = h->varpart.as<double>();
   prm.obs = keep_sums ? h->obs.as<long long>() : nullptr;
   prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
-  CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_SMEM_BYTES));
-  const int grid = (int)std::min<int64_t>(prm.n_tiles, h->num_sms);
-  CV_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
-  CV_LAUNCH(h, k_dense_contract, grid, DN_THREADS, DN_SMEM_BYTES, map_c, map_m, prm);
-  CV_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
-  *T_out = ncb;
-  h->st.contract_updates = 0;
-  h->st.contract_bytes = 0;
-  h->dn_flops = 2.0 * (double)rowsM * (double)rowsC * (double)Ppad;
+  prm.sums = h->dn_S.as<long long>();
+  prm.sums_ld = (int)pl.chunk_cells;
+  prm.sums_c0 = (int)c0;
+  for (int plane = 0; plane < pl.planes; ++plane) {
+    cv_span_begin(h, CV_SPAN_LAYOUT);
+    CV_TRY(cv_dense_build_cells(h, pl, c0, rows, 8 * plane));
+    cv_span_end(h);
+    cv_span_begin(h, CV_SPAN_CONTRACT);
+    if (pl.planes == 1) {
+      CV_TRY(launch_gemm<DN_EPI_FUSED>(h, pl, map_c, map_m, prm));
+    } else {
+      prm.sums_shift = 8 * plane;
+      prm.sums_acc = plane > 0;
+      CV_TRY(launch_gemm<DN_EPI_SUMS>(h, pl, map_c, map_m, prm));
+    }
+    cv_span_end(h);
+    h->dn_flops += 2.0 * (double)pl.rowsM * (double)rows * (double)pl.Ppad;
+  }
+  if (pl.planes > 1) {
+    cv_span_begin(h, CV_SPAN_CONTRACT);
+    dim3 grid((unsigned)prm.n_cell_blocks, (unsigned)K);
+    CV_LAUNCH(h, k_dense_finalize_sums, grid, 128, 0, prm);
+    cv_span_end(h);
+  }
+  return CV_OK;
+}
+
+// Exactness bounds of the u8 operands / s32 accumulators, from the device-side counters
+// (hflags = the handle's 16 flag words copied to the host after a stream sync).  with_counts = 0
+// checks only what is known before the counts have arrived (streamed call).
+int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, int with_counts, int* soft_fail) {
+  *soft_fail = 0;
+  const uint32_t* df = hflags + CV_DFLAGS;
+  const uint64_t maxmult = (uint64_t)std::max(df[1], 1u) * std::max(df[2], 1u);
+  if (df[2] >= 0xFFFFu || maxmult > 255) {
+    *soft_fail = 1;
+    CV_FAIL(h, CV_ERR_UNSUPPORTED, "annotation multiplicity bound %llu exceeds the u8 operand",
+            (unsigned long long)maxmult);
+  }
+  if (!with_counts) return CV_OK;
+  // every digit plane's sum is bounded by (cell total) x multiplicity
+  if ((double)h->max_cell_tot * (double)maxmult >= 2147483647.0) {
+    *soft_fail = 1;
+    CV_FAIL(h, CV_ERR_UNSUPPORTED, "s32 accumulator bound exceeded");
+  }
+  uint32_t planes = 1;
+  for (uint32_t v = h->max_val >> 8; v; v >>= 8) planes++;
+  if ((int)planes > pl.planes) {
+    *soft_fail = 1;
+    CV_FAIL(h, CV_ERR_UNSUPPORTED, "counts need %u u8 planes, the call assumed %d", planes, pl.planes);
+  }
   return CV_OK;
 }

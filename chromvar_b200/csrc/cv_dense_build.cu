@@ -19,6 +19,7 @@
 
 #define DB_THREADS 512
 #define DB_BLOCK_N 256
+#define DB_UNROLL 4
 
 enum { DB_FLAG_BADIDX = 8u };
 
@@ -64,12 +65,20 @@ k_dense_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ an
       db_zero(row0, cw);
       __syncthreads();
       double se = 0.0;
-      for (int64_t idx = beg + threadIdx.x; idx < end; idx += DB_THREADS) {
-        const int p = __ldg(annoidx + idx);
-        if (p >= q0 && p < qhi) {
-          const int off = p - (int)q0;
-          atomicAdd(row0 + (off >> 2), 1u << (8 * (off & 3)));
-          se += __ldg(e + p);
+      for (int64_t idx = beg + threadIdx.x; idx < end; idx += DB_UNROLL * DB_THREADS) {
+        int p[DB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DB_UNROLL; ++u) {
+          const int64_t i = idx + (int64_t)u * DB_THREADS;
+          p[u] = i < end ? __ldg(annoidx + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < DB_UNROLL; ++u) {
+          if (p[u] >= q0 && p[u] < qhi) {
+            const int off = p[u] - (int)q0;
+            atomicAdd(row0 + (off >> 2), 1u << (8 * (off & 3)));
+            se += __ldg(e + p[u]);
+          }
         }
       }
       __syncthreads();
@@ -90,15 +99,34 @@ k_dense_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ an
         const int32_t* __restrict__ bgcol = bg + (int64_t)(j - 1) * P;
         double sj = 0.0;
         unsigned long long ov = 0;
-        for (int64_t idx = beg + threadIdx.x; idx < end; idx += DB_THREADS) {
-          const int p = __ldg(annoidx + idx);
-          int q = __ldg(bgcol + p) - base;
-          if (q < 0 || q >= P) { atomicOr(flags, DB_FLAG_BADIDX); q = 0; }
-          if (q >= q0 && q < qhi) {
-            const int off = q - (int)q0;
-            atomicAdd(rowj + (off >> 2), 1u << (8 * (off & 3)));
-            sj += __ldg(e + q);
-            ov += (unsigned long long)row0b[off];
+        for (int64_t idx = beg + threadIdx.x; idx < end; idx += DB_UNROLL * DB_THREADS) {
+          // three dependent gathers per item (list -> background column -> expectation): keep
+          // DB_UNROLL independent chains in flight per thread
+          int q[DB_UNROLL];
+#pragma unroll
+          for (int u = 0; u < DB_UNROLL; ++u) {
+            const int64_t i = idx + (int64_t)u * DB_THREADS;
+            q[u] = i < end ? __ldg(annoidx + i) : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < DB_UNROLL; ++u) {
+            if (q[u] >= 0) {
+              int v = __ldg(bgcol + q[u]) - base;
+              if (v < 0 || v >= P) { atomicOr(flags, DB_FLAG_BADIDX); v = 0; }
+              q[u] = (v >= q0 && v < qhi) ? v : -1;
+            }
+          }
+          double ev[DB_UNROLL];
+#pragma unroll
+          for (int u = 0; u < DB_UNROLL; ++u) ev[u] = q[u] >= 0 ? __ldg(e + q[u]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < DB_UNROLL; ++u) {
+            if (q[u] >= 0) {
+              const int off = q[u] - (int)q0;
+              atomicAdd(rowj + (off >> 2), 1u << (8 * (off & 3)));
+              sj += ev[u];
+              ov += (unsigned long long)row0b[off];
+            }
           }
         }
         __syncthreads();
@@ -127,20 +155,20 @@ k_dense_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ an
   }
 }
 
-__device__ __forceinline__ int db_find_col_dummy() { return 0; }
-
 // Cd[c][:] for one cell per CTA iteration.  val: validated counts (<= 255 checked by the host).
+// Row r of Cd = cell c0 + r (zero row when that is past the last cell); shift selects the u8 digit plane.
 __global__ void __launch_bounds__(DB_THREADS, 1)
 k_dense_cells(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
-              const uint32_t* __restrict__ val, int N, int n_rows_padded, int64_t Ppad, int chunk,
+              const uint32_t* __restrict__ val, int N, int c0, int n_rows_padded, int shift, int64_t Ppad, int chunk,
               uint8_t* __restrict__ Cd, uint32_t* __restrict__ work_ctr) {
   extern __shared__ __align__(16) uint32_t db_smem[];
   __shared__ int s_item;
   for (;;) {
     if (threadIdx.x == 0) s_item = (int)atomicAdd(work_ctr, 1u);
     __syncthreads();
-    const int c = s_item;
-    if (c >= n_rows_padded) break;
+    const int r = s_item;
+    if (r >= n_rows_padded) break;
+    const int c = c0 + r;
     const int64_t beg = c < N ? colptr[c] : 0, end = c < N ? colptr[c + 1] : 0;
     for (int64_t q0 = 0; q0 < Ppad; q0 += chunk) {
       const int cw = (int)min((int64_t)chunk, Ppad - q0) >> 2;
@@ -151,11 +179,12 @@ k_dense_cells(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
         const int q = __ldg(rowidx + x);
         if (q >= q0 && q < qhi) {
           const int off = q - (int)q0;
-          atomicAdd(db_smem + (off >> 2), __ldg(val + x) << (8 * (off & 3)));   // duplicates still sum
+          // (duplicate row indices inside a column still sum, like Matrix does)
+          atomicAdd(db_smem + (off >> 2), ((__ldg(val + x) >> shift) & 0xFFu) << (8 * (off & 3)));
         }
       }
       __syncthreads();
-      db_store(db_smem, reinterpret_cast<uint32_t*>(Cd + (int64_t)c * Ppad + q0), cw);
+      db_store(db_smem, reinterpret_cast<uint32_t*>(Cd + (int64_t)r * Ppad + q0), cw);
       __syncthreads();
     }
   }
@@ -219,69 +248,44 @@ k_zero_pad_rows(uint8_t* __restrict__ M, int K, int G, int I, int64_t Ppad) {
   for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) base[i] = make_uint4(0, 0, 0, 0);
 }
 
-// Host: bound check + both operands + the per-annotation tables.  soft_fail = 1 when the u8 / s32
-// bounds cannot be guaranteed (the caller then falls back to the exact row-gather kernel).
-int cv_dense_build_operands(cv_handle* h, int G, int64_t Ppad, int64_t rowsM, int64_t rowsC,
-                            int* soft_fail) {
-  *soft_fail = 0;
-  const int64_t P = h->P, N = h->N, K = h->K;
-  const int B = h->B, I = B + 1;
-  uint32_t* flags = h->flags.as<uint32_t>();
-
-  // ---- multiplicity bound over all peaks (cheap, before anything big is allocated) ------------
-  // list duplicates: a peak repeated d times inside one list multiplies every entry by up to d;
-  // bounded here by the longest list's worst case only when duplicates exist (checked after the
-  // rows are built through k_row0_max).
+// Host: operand M + per-annotation tables + the multiplicity counters (dflags[1]: largest
+// #{p : bg[p, j] = q}; dflags[2]: largest multiplicity inside one list, 0xFFFF when a byte wrapped).
+// Asynchronous; cv_dense_check reads the counters after the caller's stream sync.
+int cv_dense_build_rows(cv_handle* h, const DensePlan& pl) {
+  const int64_t P = h->P, K = h->K;
+  const int B = h->B, I = B + 1, G = pl.G;
+  const int64_t Ppad = pl.Ppad;
+  uint32_t* dflags = h->flags.as<uint32_t>() + CV_DFLAGS;
   CV_TRY(cv_ensure(h, h->tmp1, (size_t)P * B * 4));
   CV_CUDA(h, cudaMemsetAsync(h->tmp1.p, 0, (size_t)P * B * 4, h->stream));
-  CV_CUDA(h, cudaMemsetAsync(flags + 4, 0, 8, h->stream));
   CV_LAUNCH(h, k_bg_mult_count_cm, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(),
-            h->index_base, P * B, (int)P, h->tmp1.as<uint32_t>(), flags);
-  CV_LAUNCH(h, k_u32_max_db, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, flags + 4);
-
-  // ---- operands ------------------------------------------------------------------------------------
-  CV_TRY(cv_ensure(h, h->dn_M, (size_t)rowsM * Ppad));
-  CV_TRY(cv_ensure(h, h->dn_C, (size_t)rowsC * Ppad));
+            h->index_base, P * B, (int)P, h->tmp1.as<uint32_t>(), dflags);
+  CV_LAUNCH(h, k_u32_max_db, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, dflags + 1);
   const int budget = h->max_smem_optin - 2048;
-  // rows kernel keeps two row chunks, cells kernel one
-  int chunk2 = (int)std::min<int64_t>(Ppad, ((budget / 2) / 128) * 128);
-  int chunk1 = (int)std::min<int64_t>(Ppad, (budget / 128) * 128);
+  const int chunk2 = (int)std::min<int64_t>(Ppad, ((budget / 2) / 128) * 128);   // two row chunks resident
   CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
   // rows of a group that no (annotation, iteration) owns must be zero
-  {
-    const int n_groups = (int)(rowsM / DB_BLOCK_N);
-    if (G * I < DB_BLOCK_N || K % G)
-      CV_LAUNCH(h, k_zero_pad_rows, n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, Ppad);
-  }
+  if (G * I < DB_BLOCK_N || K % G)
+    CV_LAUNCH(h, k_zero_pad_rows, pl.n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, Ppad);
   CV_CUDA(h, cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * chunk2));
   CV_LAUNCH(h, k_dense_rows, (unsigned)std::min<int64_t>(K, h->num_sms), DB_THREADS, (size_t)2 * chunk2,
             h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
             h->expect.as<double>(), h->order.as<int32_t>(), (int)K, (int)P, B, G, Ppad, chunk2,
             h->dn_M.as<uint8_t>(), h->etab.as<double>(), h->overlap.as<double>(), h->matches.as<double>(),
-            h->work_ctr.as<uint32_t>(), flags);
-  CV_LAUNCH(h, k_row0_max, (unsigned)K, 256, 0, h->dn_M.as<uint8_t>(), h->annoptr.as<int64_t>(), (int)K, G, I, Ppad, flags + 5);
-  CV_CUDA(h, cudaFuncSetAttribute(k_dense_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk1));
-  CV_LAUNCH(h, k_dense_cells, (unsigned)std::min<int64_t>(rowsC, (int64_t)h->num_sms), DB_THREADS, (size_t)chunk1,
-            h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), (int)N, (int)rowsC, Ppad,
-            chunk1, h->dn_C.as<uint8_t>(), h->work_ctr.as<uint32_t>() + 1);
+            h->work_ctr.as<uint32_t>(), dflags);
+  CV_LAUNCH(h, k_row0_max, (unsigned)K, 256, 0, h->dn_M.as<uint8_t>(), h->annoptr.as<int64_t>(), (int)K, G, I, Ppad,
+            dflags + 2);
+  return CV_OK;
+}
 
-  // ---- bounds: u8 entries of M, s32 accumulators ---------------------------------------------------
-  uint32_t mx[2] = {0, 0};
-  CV_CUDA(h, cudaMemcpyAsync(mx, flags + 4, 8, cudaMemcpyDeviceToHost, h->stream));
-  std::vector<unsigned long long> ct((size_t)N);
-  CV_CUDA(h, cudaMemcpyAsync(ct.data(), h->cell_tot.p, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
-  CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  const uint64_t maxmult = (uint64_t)std::max(mx[0], 1u) * std::max(mx[1], 1u);
-  if (maxmult > 255) {
-    *soft_fail = 1;
-    CV_FAIL(h, CV_ERR_UNSUPPORTED, "annotation multiplicity bound %llu exceeds the u8 operand",
-            (unsigned long long)maxmult);
-  }
-  unsigned long long m = 0;
-  for (auto v : ct) m = std::max(m, v);
-  if ((double)m * (double)maxmult >= 2147483647.0) {
-    *soft_fail = 1;
-    CV_FAIL(h, CV_ERR_UNSUPPORTED, "s32 accumulator bound exceeded");
-  }
+// Cd rows [0, rows) <- cells [c0, c0 + rows), digit plane `shift` / 8.  Asynchronous.
+int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift) {
+  const int budget = h->max_smem_optin - 2048;
+  const int chunk1 = (int)std::min<int64_t>(pl.Ppad, (budget / 128) * 128);
+  CV_CUDA(h, cudaMemsetAsync(h->work_ctr.as<uint32_t>() + 1, 0, 4, h->stream));
+  CV_CUDA(h, cudaFuncSetAttribute(k_dense_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk1));
+  CV_LAUNCH(h, k_dense_cells, (unsigned)std::min<int64_t>(rows, (int64_t)h->num_sms), DB_THREADS, (size_t)chunk1,
+            h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), (int)h->N, (int)c0, (int)rows,
+            shift, pl.Ppad, chunk1, h->dn_C.as<uint8_t>(), h->work_ctr.as<uint32_t>() + 1);
   return CV_OK;
 }

@@ -19,7 +19,7 @@
 #define CONTRACT_THREADS 512
 #define STATS_THREADS 512
 
-enum { FLAG_BADIDX = 8u };
+enum { FLAG_BADIDX = 8u, FLAG_ZEROPEAK = 16u };
 
 static double wall_ms() {
   struct timespec ts;
@@ -365,15 +365,16 @@ __global__ void k_var_merge(const double* __restrict__ varpart, int K, int T,
   variab[k] = tot.n > 1.0 ? sqrt(tot.m2 / (tot.n - 1.0)) : __longlong_as_double(0x7ff8000000000000LL);
 }
 
-// in: [R][C] row-major -> out: [C][R] row-major (= R x C column-major)
+// in: R rows x C columns, row stride ld_in -> out: C rows x R columns, row stride R
+// (a block of columns of a [R][N] row-major matrix -> the same columns of the R x N column-major one)
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_transpose(const T* __restrict__ in, T* __restrict__ out, int64_t R, int64_t C) {
+k_transpose(const T* __restrict__ in, T* __restrict__ out, int64_t R, int64_t C, int64_t ld_in) {
   __shared__ T tile[32][33];
   int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8)
-    if (r0 + r < R && c0 + tx < C) tile[r][tx] = in[(r0 + r) * C + c0 + tx];
+    if (r0 + r < R && c0 + tx < C) tile[r][tx] = in[(r0 + r) * ld_in + c0 + tx];
   __syncthreads();
   for (int c = ty; c < 32; c += 8)
     if (c0 + c < C && r0 + tx < R) out[(c0 + c) * R + r0 + tx] = tile[tx][c];
@@ -398,27 +399,24 @@ int cv_choose_tile(cv_handle* h, int B, int acc_bytes, int* W_out) {
   return CV_OK;
 }
 
-extern "C" int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* annoptr,
-                                    const int32_t* annoidx, int index_base, const int32_t* bg,
-                                    int B, const double* expectation) {
-  if (!h) return CV_ERR_INVALID;
-  cudaSetDevice(h->device);
+// host-side validation + H2D of annotations / background / expectation.  `sync` = 0 leaves the
+// copies in flight on `stream_for_copies` (the streamed call orders its kernels behind an event).
+static int upload_annotations(cv_handle* h, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
+                              int index_base, const int32_t* bg, int B, const double* expectation,
+                              cudaStream_t st) {
   h->have_anno = false;
   h->have_results = false;
-  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
   if (K < 1 || !annoptr) CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid");
   if (K > 0x7fffffff) CV_FAIL(h, CV_ERR_UNSUPPORTED, "K must be < 2^31");
   if (index_base != 0 && index_base != 1) CV_FAIL(h, CV_ERR_INVALID, "index_base must be 0 or 1");
   if (B < 1 || !bg) CV_FAIL(h, CV_ERR_INVALID, "background_peaks must have at least one column");
   if (B > 1024) CV_FAIL(h, CV_ERR_UNSUPPORTED, "niterations > 1024 is not supported");
-  if (!expectation) CV_FAIL(h, CV_ERR_INVALID, "expectation is NULL");
   if (annoptr[0] != 0) CV_FAIL(h, CV_ERR_INVALID, "annoptr must start at 0");
   for (int64_t k = 0; k < K; ++k)
     if (annoptr[k + 1] < annoptr[k]) CV_FAIL(h, CV_ERR_INVALID, "annoptr is not monotone");
   const int64_t nnzA = annoptr[K];
   if (nnzA > 0 && !annoidx) CV_FAIL(h, CV_ERR_INVALID, "annoidx is NULL");
   const int64_t P = h->P;
-  double t0 = wall_ms();
   h->K = K; h->B = B; h->nnzA = nnzA; h->index_base = index_base;
   h->h_annoptr.assign(annoptr, annoptr + K + 1);
   CV_TRY(cv_ensure(h, h->annoptr, (size_t)(K + 1) * 8));
@@ -426,22 +424,35 @@ extern "C" int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* anno
   CV_TRY(cv_ensure(h, h->annoidx, (size_t)nnzA * 4));
   CV_TRY(cv_ensure(h, h->bg_raw, (size_t)P * B * 4));
   CV_TRY(cv_ensure(h, h->expect, (size_t)P * 8));
-  CV_CUDA(h, cudaMemcpyAsync(h->annoptr.p, annoptr, (size_t)(K + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  CV_CUDA(h, cudaMemcpyAsync(h->annoptr.p, annoptr, (size_t)(K + 1) * 8, cudaMemcpyHostToDevice, st));
   if (nnzA)
-    CV_CUDA(h, cudaMemcpyAsync(h->anno_raw.p, annoidx, (size_t)nnzA * 4, cudaMemcpyHostToDevice, h->stream));
-  CV_CUDA(h, cudaMemcpyAsync(h->bg_raw.p, bg, (size_t)P * B * 4, cudaMemcpyHostToDevice, h->stream));
-  CV_CUDA(h, cudaMemcpyAsync(h->expect.p, expectation, (size_t)P * 8, cudaMemcpyHostToDevice, h->stream));
+    CV_CUDA(h, cudaMemcpyAsync(h->anno_raw.p, annoidx, (size_t)nnzA * 4, cudaMemcpyHostToDevice, st));
+  CV_CUDA(h, cudaMemcpyAsync(h->bg_raw.p, bg, (size_t)P * B * 4, cudaMemcpyHostToDevice, st));
+  if (expectation)
+    CV_CUDA(h, cudaMemcpyAsync(h->expect.p, expectation, (size_t)P * 8, cudaMemcpyHostToDevice, st));
   // annotations by decreasing set size (longest-processing-time-first work order)
-  std::vector<int32_t> order((size_t)K);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+  h->h_order.resize((size_t)K);
+  std::iota(h->h_order.begin(), h->h_order.end(), 0);
+  std::stable_sort(h->h_order.begin(), h->h_order.end(), [&](int32_t a, int32_t b) {
     return (annoptr[a + 1] - annoptr[a]) > (annoptr[b + 1] - annoptr[b]);
   });
   CV_TRY(cv_ensure(h, h->order, (size_t)K * 4));
-  CV_CUDA(h, cudaMemcpyAsync(h->order.p, order.data(), (size_t)K * 4, cudaMemcpyHostToDevice, h->stream));
+  CV_CUDA(h, cudaMemcpyAsync(h->order.p, h->h_order.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+  h->st.h2d_bytes = (int64_t)((K + 1) * 8 + nnzA * 4 + P * B * 4 + (expectation ? P * 8 : 0));
+  return CV_OK;
+}
+
+extern "C" int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* annoptr,
+                                    const int32_t* annoidx, int index_base, const int32_t* bg,
+                                    int B, const double* expectation) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
+  if (!expectation) CV_FAIL(h, CV_ERR_INVALID, "expectation is NULL");
+  double t0 = wall_ms();
+  CV_TRY(upload_annotations(h, K, annoptr, annoidx, index_base, bg, B, expectation, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   h->st.ms_h2d = wall_ms() - t0;
-  h->st.h2d_bytes = (int64_t)((K + 1) * 8 + nnzA * 4 + P * B * 4 + P * 8);
   h->have_anno = true;
   return CV_OK;
 }
@@ -454,58 +465,121 @@ static int launch_contract(cv_handle* h, const ContractParams& prm, size_t smem)
   return CV_OK;
 }
 
-extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, int keep_sums) {
-  if (!h) return CV_ERR_INVALID;
-  cudaSetDevice(h->device);
-  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
-  if (!h->have_anno) CV_FAIL(h, CV_ERR_STATE, "annotations / background not uploaded");
-  if (!h->totals_committed)
-    CV_FAIL(h, CV_ERR_STATE, "per-peak totals handed out for a cross-shard reduction; call cv_peak_totals_commit first");
+// What a call streams between host and device while the kernels run (all optional).
+struct DevIO {
+  // counts arriving chunk by chunk (cv_deviations_csc): host CSC arrays, colptr as int64
+  bool stream_counts = false;
+  const int64_t* h_colptr = nullptr;
+  const int32_t* h_rowidx = nullptr;
+  const char* h_x = nullptr;
+  int x_type = 0;
+  size_t xb = 0;
+  // results leaving chunk by chunk (K x N column-major: a cell chunk is a contiguous slab)
+  double* out_dev = nullptr;
+  double* out_z = nullptr;
+  bool results_streamed = false;     // set by deviations_run when out_dev / out_z were written
+  int soft_fail = 0;                 // set when the dense path turned out not to be exact
+};
+
+static int enqueue_counts_upload(cv_handle* h, const DevIO& io, int64_t c0, int64_t c1, cudaEvent_t done) {
+  const int64_t e0 = io.h_colptr[c0], e1 = io.h_colptr[c1];
+  if (e1 > e0) {
+    CV_CUDA(h, cudaMemcpyAsync(h->rowidx.as<int32_t>() + e0, io.h_rowidx + e0, (size_t)(e1 - e0) * 4,
+                               cudaMemcpyHostToDevice, h->s_up));
+    CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0 * io.xb, io.h_x + (size_t)e0 * io.xb,
+                               (size_t)(e1 - e0) * io.xb, cudaMemcpyHostToDevice, h->s_up));
+  }
+  CV_CUDA(h, cudaEventRecord(done, h->s_up));
+  return CV_OK;
+}
+
+static int enqueue_result_download(cv_handle* h, const DevIO& io, int64_t c0, int64_t c1, cudaEvent_t ready) {
+  const int64_t K = h->K;
+  CV_CUDA(h, cudaStreamWaitEvent(h->s_dn, ready, 0));
+  if (io.out_dev)
+    CV_CUDA(h, cudaMemcpyAsync(io.out_dev + c0 * K, h->dev_cm.as<double>() + c0 * K, (size_t)(c1 - c0) * K * 8,
+                               cudaMemcpyDeviceToHost, h->s_dn));
+  if (io.out_z)
+    CV_CUDA(h, cudaMemcpyAsync(io.out_z + c0 * K, h->z_cm.as<double>() + c0 * K, (size_t)(c1 - c0) * K * 8,
+                               cudaMemcpyDeviceToHost, h->s_dn));
+  return CV_OK;
+}
+
+// [K][c0:c1) row-major -> the same cells of the K x N column-major ABI matrices
+static int enqueue_transposes(cv_handle* h, int64_t c0, int64_t c1) {
+  const int64_t K = h->K, N = h->N;
+  dim3 grid((unsigned)((c1 - c0 + 31) / 32), (unsigned)((K + 31) / 32));
+  CV_LAUNCH(h, k_transpose<double>, grid, 256, 0, h->dev_rm.as<double>() + c0, h->dev_cm.as<double>() + c0 * K, K,
+            c1 - c0, N);
+  CV_LAUNCH(h, k_transpose<double>, grid, 256, 0, h->z_rm.as<double>() + c0, h->z_cm.as<double>() + c0 * K, K,
+            c1 - c0, N);
+  return CV_OK;
+}
+
+static cudaEvent_t pool_event(cv_handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+// ---- path selection: dense tcgen05 GEMM vs. cell-tiled row-gather SpMM -----------------------
+// sparse cost: (B+1) * nnzA * (nnz / P) entry updates at the measured rate of k_contract;
+// dense cost: the padded u8 GEMM (x digit planes) at a sustained tensor rate.
+static int choose_path(cv_handle* h, uint32_t max_val, int64_t want_chunk, bool must_be_dense, DensePlan* pl,
+                       int* use_dense) {
+  *use_dense = 0;
+  std::string why;
+  const int feasible = cv_dense_plan(h, max_val, want_chunk, pl, &why);
+  if (h->opt_path == 2 || must_be_dense) {
+    if (!feasible) CV_FAIL(h, CV_ERR_UNSUPPORTED, "dense path requested but not applicable: %s", why.c_str());
+    *use_dense = 1;
+  } else if (h->opt_path == 0 && feasible) {
+    const double updates = (double)(h->B + 1) * (double)h->nnzA * ((double)h->nnz / (double)h->P);
+    const double sparse_ms = updates / 2.7e8 + 0.3;
+    *use_dense = cv_dense_cost_ms(h, *pl) < sparse_ms;
+  }
+  return CV_OK;
+}
+
+// Every kernel of the path on resident (or arriving) inputs.
+static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums, DevIO* io) {
   const int64_t P = h->P, N = h->N, K = h->K;
   const int B = h->B, I = B + 1;
+  const bool streaming = io && io->stream_counts;
   h->have_results = false;
+  cv_spans_reset(h);
 
   // accumulator width of the row-gather path: |sum| <= (largest set) * (largest count)
   int64_t set_max = 0;
   for (int64_t k = 0; k < K; ++k) set_max = std::max(set_max, h->h_annoptr[k + 1] - h->h_annoptr[k]);
-  const bool wide = (double)set_max * (double)h->max_val >= 2147483647.0;
-  const int acc_bytes = wide ? 8 : 4;
 
-  // ---- path selection: dense tcgen05 GEMM vs. cell-tiled row-gather SpMM -----------------------
-  // sparse cost: (B+1) * nnzA * (nnz / P) entry updates at the measured rate of k_contract;
-  // dense cost: the padded u8 GEMM at a sustained tensor rate (cv_dense_cost_ms).
   int use_dense = 0;
+  DensePlan pl;
   {
-    std::string why;
-    const int feasible = cv_dense_feasible(h, &why);
-    if (h->opt_path == 2) {
-      if (!feasible) CV_FAIL(h, CV_ERR_UNSUPPORTED, "dense path requested but not applicable: %s", why.c_str());
-      use_dense = 1;
-    } else if (h->opt_path == 0 && feasible) {
-      const double updates = (double)I * (double)h->nnzA * ((double)h->nnz / (double)P);
-      const double sparse_ms = updates / 2.7e8 + 0.3;
-      use_dense = cv_dense_cost_ms(h) < sparse_ms;
-    }
+    // host copies overlap the GEMMs: about four chunks, none smaller than a few waves of tiles
+    const int64_t want_chunk = (io && (io->out_dev || io->out_z || streaming)) ? std::max<int64_t>((N + 3) / 4, 1024) : 0;
+    CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
   }
 
   // ---- stage 1: validation and per-annotation tables ---------------------------------------------
-  CV_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
-  CV_TRY(cv_ensure(h, h->flags, 64));
-  CV_CUDA(h, cudaMemsetAsync(h->flags.p, 0, 64, h->stream));
-  CV_LAUNCH(h, k_check_zero_peaks, (unsigned)((P + 255) / 256), 256, 0,
-            h->peak_tot.as<unsigned long long>(), (int)P, h->flags.as<uint32_t>());
+  uint32_t* dflags = h->flags.as<uint32_t>() + CV_DFLAGS;
+  cv_span_begin(h, CV_SPAN_ANNO);
+  CV_CUDA(h, cudaMemsetAsync(dflags, 0, 32, h->stream));
   if (h->nnzA)
     CV_LAUNCH(h, k_anno_prepare, (unsigned)((h->nnzA + 255) / 256), 256, 0, h->anno_raw.as<int32_t>(),
-              h->nnzA, (int)P, h->index_base, h->annoidx.as<int32_t>(), h->flags.as<uint32_t>());
+              h->nnzA, (int)P, h->index_base, h->annoidx.as<int32_t>(), dflags);
+  cv_span_end(h);
   CV_TRY(cv_ensure(h, h->etab, (size_t)K * I * 8));
   CV_TRY(cv_ensure(h, h->overlap, (size_t)K * 8));
   CV_TRY(cv_ensure(h, h->matches, (size_t)K * 8));
   CV_TRY(cv_ensure(h, h->work_ctr, 64));
-  CV_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
-
-  // ---- stage 2: operand layout + contraction + fused epilogue -----------------------------------
   CV_TRY(cv_ensure(h, h->dev_rm, (size_t)K * N * 8));
   CV_TRY(cv_ensure(h, h->z_rm, (size_t)K * N * 8));
+  CV_TRY(cv_ensure(h, h->dev_cm, (size_t)K * N * 8));
+  CV_TRY(cv_ensure(h, h->z_cm, (size_t)K * N * 8));
   CV_TRY(cv_ensure(h, h->varfinal, (size_t)K * 4 * 8));
   CV_TRY(cv_ensure(h, h->variab, (size_t)K * 8));
   if (keep_sums) {
@@ -513,22 +587,69 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
     CV_TRY(cv_ensure(h, h->samp, (size_t)K * B * N * 8));
   }
   h->kept_sums = keep_sums != 0;
+  CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
+
+  // ---- stage 2: operand layout + contraction + fused epilogue -----------------------------------
   int T = 0;
+  bool wide = false;
   if (use_dense) {
+    const int64_t chunk = pl.chunk_cells;
+    const int n_chunks = (int)((N + chunk - 1) / chunk);
+    std::vector<cudaEvent_t> ev_up((size_t)n_chunks), ev_done((size_t)n_chunks);
+    for (int i = 0; i < n_chunks; ++i) { ev_up[i] = pool_event(h); ev_done[i] = pool_event(h); }
+    auto lo = [&](int i) { return (int64_t)i * chunk; };
+    auto hi = [&](int i) { return std::min<int64_t>(N, (int64_t)(i + 1) * chunk); };
+    CV_TRY(cv_dense_prepare(h, pl));                          // operand M + tables: cell independent
+    if (streaming) CV_TRY(enqueue_counts_upload(h, *io, lo(0), hi(0), ev_up[0]));
+    // multiplicity bounds of the u8 operand before any GEMM runs (one short host sync; the first
+    // counts chunk is already in flight)
+    uint32_t hf[16];
+    CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
+    CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (hf[CV_DFLAGS] & FLAG_BADIDX)
+      CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
     int soft = 0;
-    int rc = cv_dense_contract(h, keep_sums, &T, &soft);     // records ev[3], ev[4] around the GEMM
+    int rc = cv_dense_check(h, pl, hf, streaming ? 0 : 1, &soft);
     if (rc != CV_OK) {
-      if (soft && h->opt_path != 2) use_dense = 0;           // multiplicity bound failed: exact fallback
-      else return rc;
+      if (soft && h->opt_path != 2 && !streaming) use_dense = 0;     // exact fallback below
+      else { if (io) io->soft_fail = soft; return rc; }
+    }
+    if (use_dense) {
+      const bool dl = io && (io->out_dev || io->out_z);
+      for (int i = 0; i < n_chunks; ++i) {
+        if (streaming) {
+          CV_CUDA(h, cudaStreamWaitEvent(h->stream, ev_up[i], 0));
+          cv_span_begin(h, CV_SPAN_K1);
+          CV_TRY(cv_counts_range(h, io->x_type, io->h_colptr[lo(i)], io->h_colptr[hi(i)], lo(i), hi(i)));
+          cv_span_end(h);
+        }
+        CV_TRY(cv_dense_chunk(h, pl, lo(i), hi(i), keep_sums));
+        cv_span_begin(h, CV_SPAN_FINALIZE);
+        CV_TRY(enqueue_transposes(h, lo(i), hi(i)));
+        cv_span_end(h);
+        CV_CUDA(h, cudaEventRecord(ev_done[i], h->stream));
+        // host copies: next chunk in, previous chunk out (one behind, so that a blocking copy of
+        // pageable memory still leaves a queued chunk for the GPU)
+        if (streaming && i + 1 < n_chunks) CV_TRY(enqueue_counts_upload(h, *io, lo(i + 1), hi(i + 1), ev_up[i + 1]));
+        if (dl && i > 0) CV_TRY(enqueue_result_download(h, *io, lo(i - 1), hi(i - 1), ev_done[i - 1]));
+      }
+      if (dl) {
+        CV_TRY(enqueue_result_download(h, *io, lo(n_chunks - 1), hi(n_chunks - 1), ev_done[n_chunks - 1]));
+        io->results_streamed = true;
+      }
+      T = (int)((N + 127) / 128);
     }
   }
   if (!use_dense) {
+    wide = (double)set_max * (double)h->max_val >= 2147483647.0;
+    const int acc_bytes = wide ? 8 : 4;
     // background matrix -> [P][B] 0-based, expected-fraction table, overlap, matches
+    cv_span_begin(h, CV_SPAN_ANNO);
     CV_TRY(cv_ensure(h, h->bgT, (size_t)P * B * 4));
     {
       dim3 grid((unsigned)((P + 31) / 32), (unsigned)((B + 31) / 32));
       CV_LAUNCH(h, k_bg_prepare, grid, 256, 0, h->bg_raw.as<int32_t>(), (int)P, B, h->index_base,
-                h->bgT.as<int32_t>(), h->flags.as<uint32_t>());
+                h->bgT.as<int32_t>(), dflags);
     }
     {
       int grid = (int)std::min<int64_t>(K, (int64_t)h->num_sms * 2);
@@ -544,10 +665,13 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
                 (int)K, h->mark.as<int32_t>(), h->etab.as<double>(), h->overlap.as<double>(),
                 h->matches.as<double>());
     }
+    cv_span_end(h);
     CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
     int W = 0;
     CV_TRY(cv_choose_tile(h, B, acc_bytes, &W));
+    cv_span_begin(h, CV_SPAN_LAYOUT);
     if (rebuild_counts_layout || !h->layout_valid || h->W != W) CV_TRY(cv_build_layout(h, W));
+    cv_span_end(h);
     T = h->T;
     CV_TRY(cv_ensure(h, h->varpart, (size_t)K * T * 4 * 8));
     ContractParams prm;
@@ -569,65 +693,82 @@ extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, in
     prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
     prm.upd_ctr = reinterpret_cast<unsigned long long*>(h->work_ctr.as<uint32_t>() + 2);
     const size_t smem = (size_t)I * W * acc_bytes;
-    CV_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+    cv_span_begin(h, CV_SPAN_CONTRACT);
     if (wide) CV_TRY(launch_contract<long long>(h, prm, smem));
     else CV_TRY(launch_contract<int>(h, prm, smem));
-    CV_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
+    cv_span_end(h);
+    cv_span_begin(h, CV_SPAN_FINALIZE);
+    CV_TRY(enqueue_transposes(h, 0, N));
+    cv_span_end(h);
   }
 
-  // ---- stage 3: variability merge + ABI layout ----------------------------------------------
+  // ---- stage 3: totals, zero-peak check, variability merge -----------------------------------------
+  cv_span_begin(h, CV_SPAN_FINALIZE);
+  if (streaming) CV_TRY(cv_counts_finish_async(h));
+  if (h->opt_check_zero)
+    CV_LAUNCH(h, k_check_zero_peaks, (unsigned)((P + 255) / 256), 256, 0,
+              h->peak_tot.as<unsigned long long>(), (int)P, dflags);
   CV_LAUNCH(h, k_var_merge, (unsigned)((K + 127) / 128), 128, 0, h->varpart.as<double>(), (int)K, T,
             h->varfinal.as<double>(), h->variab.as<double>());
-  CV_TRY(cv_ensure(h, h->dev_cm, (size_t)K * N * 8));
-  CV_TRY(cv_ensure(h, h->z_cm, (size_t)K * N * 8));
-  {
-    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((K + 31) / 32));
-    CV_LAUNCH(h, k_transpose<double>, grid, 256, 0, h->dev_rm.as<double>(), h->dev_cm.as<double>(), K, N);
-    CV_LAUNCH(h, k_transpose<double>, grid, 256, 0, h->z_rm.as<double>(), h->z_cm.as<double>(), K, N);
-  }
-  CV_CUDA(h, cudaEventRecord(h->ev[5], h->stream));
-  uint32_t flags = 0;
+  cv_span_end(h);
+  uint32_t hf[16];
   unsigned long long upd = 0;
-  CV_CUDA(h, cudaMemcpyAsync(&flags, h->flags.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaMemcpyAsync(&upd, h->work_ctr.as<uint32_t>() + 2, 8, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (flags & 16u)
+  CV_CUDA(h, cudaStreamSynchronize(h->s_dn));
+  if (streaming) {
+    CV_TRY(cv_counts_verdict(h, hf));                 // counts_check on what arrived
+    int soft = 0;
+    int rc = cv_dense_check(h, pl, hf, 1, &soft);     // planes / accumulator bound, now that K1 is complete
+    if (rc != CV_OK) { io->soft_fail = soft; io->results_streamed = false; return rc; }
+  }
+  if (hf[CV_DFLAGS] & FLAG_ZEROPEAK)
     CV_FAIL(h, CV_ERR_INVALID, "All peaks must have at least one fragment in one sample");
-  if (flags & FLAG_BADIDX)
+  if (hf[CV_DFLAGS] & FLAG_BADIDX)
     CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
-  float ms;
-  // ev[2] -> ev[3]: operand layout of the chosen path together with the per-annotation tables
-  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->st.ms_counts_layout = ms;
-  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->st.ms_anno_prep = ms;
-  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->st.ms_contract = ms;
-  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->st.ms_finalize = ms;
+  double ms[CV_SPAN_N];
+  cv_spans_collect(h, ms);
+  h->st.ms_counts_layout = ms[CV_SPAN_LAYOUT] + ms[CV_SPAN_K1];
+  h->st.ms_anno_prep = ms[CV_SPAN_ANNO];
+  h->st.ms_contract = ms[CV_SPAN_CONTRACT];
+  h->st.ms_finalize = ms[CV_SPAN_FINALIZE];
   h->st.contract_updates = (int64_t)upd;
-  // gather model: every visited entry is a 4-byte load, plus the
-  // compulsory one-time traffic (layout, annotation lists, background rows, outputs)
   if (use_dense) {
     h->st.contract_bytes = 0;
     h->st.contract_flops = h->dn_flops;
     h->st.path = 1;
     h->st.acc_bytes = 4;
-    h->st.cell_tile = 128;
-    h->st.n_cell_tiles = T;
+    h->st.cell_tile = pl.pair ? 256 : 128;
+    h->st.n_cell_tiles = (int)((N + pl.chunk_cells - 1) / pl.chunk_cells);
+    h->st.planes = pl.planes;
   } else {
+    // gather model: every visited entry is a 4-byte load, plus the
+    // compulsory one-time traffic (layout, annotation lists, background rows, outputs)
     h->st.contract_bytes = (int64_t)upd * 4 + h->n_entries * 4 + (int64_t)T * P * 4 +
                            h->nnzA * 4 * T + (int64_t)P * B * 4 + 2 * K * N * 8;
     h->st.contract_flops = 0;
     h->st.path = 0;
-    h->st.acc_bytes = acc_bytes;
+    h->st.acc_bytes = wide ? 8 : 4;
+    h->st.planes = 0;
   }
   h->have_results = true;
   return CV_OK;
 }
 
-extern "C" int cv_deviations_download(cv_handle* h, double* out_dev, double* out_z,
-                                      double* out_matches, double* out_overlap,
-                                      double* out_variability, int64_t* out_observed,
-                                      int64_t* out_sampled) {
+extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, int keep_sums) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
+  if (!h->have_anno) CV_FAIL(h, CV_ERR_STATE, "annotations / background not uploaded");
+  if (!h->totals_committed)
+    CV_FAIL(h, CV_ERR_STATE, "per-peak totals handed out for a cross-shard reduction; call cv_peak_totals_commit first");
+  return deviations_run(h, rebuild_counts_layout, keep_sums, nullptr);
+}
+
+static int download_results(cv_handle* h, double* out_dev, double* out_z, double* out_matches,
+                            double* out_overlap, double* out_variability, int64_t* out_observed,
+                            int64_t* out_sampled) {
   if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no results: call cv_deviations_compute first");
   const int64_t N = h->N, K = h->K;
   const int B = h->B;
@@ -644,7 +785,7 @@ extern "C" int cv_deviations_download(cv_handle* h, double* out_dev, double* out
       // device holds [K][N]; ABI wants K x N column-major
       CV_TRY(cv_ensure(h, h->tmp1, (size_t)K * N * 8));
       dim3 grid((unsigned)((N + 31) / 32), (unsigned)((K + 31) / 32));
-      CV_LAUNCH(h, k_transpose<long long>, grid, 256, 0, h->obs.as<long long>(), h->tmp1.as<long long>(), K, N);
+      CV_LAUNCH(h, k_transpose<long long>, grid, 256, 0, h->obs.as<long long>(), h->tmp1.as<long long>(), K, N, N);
       CV_CUDA(h, cudaMemcpyAsync(out_observed, h->tmp1.p, (size_t)K * N * 8, cudaMemcpyDeviceToHost, h->stream));
       bytes += K * N * 8;
     }
@@ -659,6 +800,17 @@ extern "C" int cv_deviations_download(cv_handle* h, double* out_dev, double* out
   return CV_OK;
 }
 
+extern "C" int cv_deviations_download(cv_handle* h, double* out_dev, double* out_z,
+                                      double* out_matches, double* out_overlap,
+                                      double* out_variability, int64_t* out_observed,
+                                      int64_t* out_sampled) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  return download_results(h, out_dev, out_z, out_matches, out_overlap, out_variability, out_observed, out_sampled);
+}
+
+// counts resident: H2D of the annotations, then the kernels with the K x N results leaving chunk
+// by chunk while later chunks are still being computed
 extern "C" int cv_deviations(cv_handle* h, int64_t K, const int64_t* annoptr,
                              const int32_t* annoidx, int index_base, const int32_t* bg, int B,
                              const double* expectation, double* out_dev, double* out_z,
@@ -668,12 +820,112 @@ extern "C" int cv_deviations(cv_handle* h, int64_t K, const int64_t* annoptr,
   CV_TRY(cv_deviations_upload(h, K, annoptr, annoidx, index_base, bg, B, expectation));
   double h2d_ms = h->st.ms_h2d;
   int64_t h2d_b = h->st.h2d_bytes;
-  CV_TRY(cv_deviations_compute(h, 0, (out_observed || out_sampled) ? 1 : 0));
-  CV_TRY(cv_deviations_download(h, out_dev, out_z, out_matches, out_overlap, out_variability,
-                                out_observed, out_sampled));
+  if (!h->totals_committed)
+    CV_FAIL(h, CV_ERR_STATE, "per-peak totals handed out for a cross-shard reduction; call cv_peak_totals_commit first");
+  DevIO io;
+  io.out_dev = out_dev;
+  io.out_z = out_z;
+  CV_TRY(deviations_run(h, 0, (out_observed || out_sampled) ? 1 : 0, &io));
+  CV_TRY(download_results(h, io.results_streamed ? nullptr : out_dev, io.results_streamed ? nullptr : out_z,
+                          out_matches, out_overlap, out_variability, out_observed, out_sampled));
+  if (io.results_streamed) h->st.d2h_bytes += 2 * K * h->N * 8;
   h->st.ms_h2d = h2d_ms;
   h->st.h2d_bytes = h2d_b;
   return CV_OK;
+}
+
+// compute_deviations_core (R/compute_deviations.R:355-408) as ONE call on host data: counts
+// (CSC as in dgCMatrix), annotations, background, expectation in; deviations / z out.  The counts
+// travel in cell chunks on their own stream while earlier chunks are in the GEMM, and finished
+// chunks of the K x N results travel back while later chunks are computed; afterwards the counts
+// are resident exactly as after cv_set_counts_csc.
+extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr, int colptr_type,
+                                 const int32_t* rowidx, const void* x, int x_type, int64_t K,
+                                 const int64_t* annoptr, const int32_t* annoidx, int index_base,
+                                 const int32_t* bg, int B, const double* expectation, double* out_dev,
+                                 double* out_z, double* out_matches, double* out_overlap,
+                                 double* out_variability) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  // the streamed pipeline needs the expectation up front and the dense path; otherwise (or when
+  // the dense path turns out not to be exact for these inputs) the call is the plain sequence
+  bool try_stream = expectation != nullptr && h->opt_path != 1 && P > 0 && N > 0 && P <= 0x7fffffff &&
+                    N <= 0x7fffffff && colptr && K >= 1 && annoptr && B >= 1 && B <= 255 && x_type != CV_I64 &&
+                    (colptr_type == CV_I32 || colptr_type == CV_I64);
+  int64_t nnz = 0;
+  std::vector<int64_t> cp64;
+  if (try_stream) {
+    cp64.resize((size_t)N + 1);
+    if (colptr_type == CV_I32) for (int64_t i = 0; i <= N; ++i) cp64[(size_t)i] = ((const int32_t*)colptr)[i];
+    else memcpy(cp64.data(), colptr, (size_t)(N + 1) * 8);
+    nnz = cp64[(size_t)N];
+    bool ok = cp64[0] == 0 && nnz > 0 && nnz < (1ll << 32) && rowidx && x && annoptr[0] == 0 && annoptr[K] >= 0;
+    for (int64_t i = 0; ok && i < N; ++i) ok = cp64[(size_t)i + 1] >= cp64[(size_t)i];
+    if (ok) {
+      // same cost model as the resident call, on the host-known shape (largest count unknown yet:
+      // one u8 plane assumed, verified once the counts have passed K1)
+      h->have_counts = false;
+      h->have_anno = false;
+      h->P = P; h->N = N; h->nnz = nnz; h->K = K; h->B = B; h->nnzA = annoptr[K];
+      DensePlan pl;
+      int use_dense = 0;
+      const int opt = h->opt_path;
+      int rc = choose_path(h, 0u, std::max<int64_t>((N + 3) / 4, 1024), false, &pl, &use_dense);
+      ok = rc == CV_OK && use_dense && (opt == 2 || cv_dense_cost_ms(h, pl) > 2.0);   // tiny problems: plain sequence
+    }
+    try_stream = ok;
+  }
+  if (try_stream) {
+    size_t xb = (x_type == CV_F64) ? 8 : (x_type == CV_F32 || x_type == CV_I32) ? 4 : (x_type == CV_U8) ? 1 : 0;
+    if (!xb) try_stream = false;
+    else {
+      double t0 = wall_ms();
+      h->have_counts = false;
+      h->P = P; h->N = N; h->nnz = nnz;
+      CV_TRY(cv_ensure(h, h->colptr, (size_t)(N + 1) * 8));
+      CV_TRY(cv_ensure(h, h->rowidx, (size_t)nnz * 4));
+      CV_TRY(cv_ensure(h, h->xraw, (size_t)nnz * xb));
+      CV_TRY(cv_counts_begin(h));
+      // small inputs first, on the compute stream (the operand build needs them immediately)
+      CV_CUDA(h, cudaMemcpyAsync(h->colptr.p, cp64.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+      int rc = upload_annotations(h, K, annoptr, annoidx, index_base, bg, B, expectation, h->stream);
+      if (rc != CV_OK) return rc;
+      int64_t h2d_b = h->st.h2d_bytes + (N + 1) * 8 + nnz * (int64_t)(4 + xb);
+      h->have_anno = true;
+      DevIO io;
+      io.stream_counts = true;
+      io.h_colptr = cp64.data();
+      io.h_rowidx = rowidx;
+      io.h_x = (const char*)x;
+      io.x_type = x_type;
+      io.xb = xb;
+      io.out_dev = out_dev;
+      io.out_z = out_z;
+      rc = deviations_run(h, 0, 0, &io);
+      if (rc == CV_OK) {
+        CV_TRY(download_results(h, io.results_streamed ? nullptr : out_dev, io.results_streamed ? nullptr : out_z,
+                                out_matches, out_overlap, out_variability, nullptr, nullptr));
+        h->st.ms_h2d = wall_ms() - t0;          // whole call: copies and kernels overlap
+        h->st.h2d_bytes = h2d_b;
+        h->st.d2h_bytes += 2 * K * N * 8;
+        return CV_OK;
+      }
+      cudaStreamSynchronize(h->s_up);
+      cudaStreamSynchronize(h->s_dn);
+      cudaStreamSynchronize(h->stream);
+      if (!io.soft_fail) return rc;             // a real input error: same message as the plain sequence
+      h->have_counts = false;                   // not exact on the dense path: redo as the plain sequence
+    }
+  }
+  CV_TRY(cv_set_counts_csc(h, P, N, colptr, colptr_type, rowidx, x, x_type));
+  std::vector<double> e_default;
+  if (!expectation) {
+    e_default.resize((size_t)P);
+    CV_TRY(cv_expectations(h, 0, nullptr, 0, e_default.data()));
+    expectation = e_default.data();
+  }
+  return cv_deviations(h, K, annoptr, annoidx, index_base, bg, B, expectation, out_dev, out_z, out_matches,
+                       out_overlap, out_variability, nullptr, nullptr);
 }
 
 extern "C" int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t* n_elems) {

@@ -60,8 +60,15 @@ struct cv_handle {
   int num_sms = CV_NUM_SMS_FALLBACK;
   int max_smem_optin = 0;
   uint64_t seed = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // compute
+  cudaStream_t s_up = nullptr;        // host -> device copies of the streamed call
+  cudaStream_t s_dn = nullptr;        // device -> host copies overlapping the next chunk
   cudaEvent_t ev[8] = {};
+  // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { cudaEvent_t a, b; int cat; };
+  std::vector<Span> spans;
   std::string err;
   int64_t launches = 0;
 
@@ -77,8 +84,9 @@ struct cv_handle {
   DevBuf peak_loc;   // int64[P+1] local copy kept when totals get all-reduced
   DevBuf cell_tot;   // int64[N]
   DevBuf fps;        // double[N]  fragments per sample
-  DevBuf flags;      // uint32[8] device-side validation flags / counters
+  DevBuf flags;      // uint32[16]: [0..7] counts validation (K1), [8..15] deviations call (CV_DFLAGS)
   uint32_t max_val = 0;
+  uint64_t max_cell_tot = 0;
 
   // ---- cell-tiled row layout of the counts (derived) ----
   bool layout_valid = false;
@@ -94,6 +102,7 @@ struct cv_handle {
   int64_t K = 0, nnzA = 0;
   int B = 0;
   std::vector<int64_t> h_annoptr;
+  std::vector<int32_t> h_order;
   DevBuf annoptr;    // int64[K+1]
   DevBuf anno_raw;   // int32[nnzA] as uploaded (index_base)
   DevBuf annoidx;    // int32[nnzA] 0-based
@@ -120,9 +129,13 @@ struct cv_handle {
 
   // dense tensor-core path (cv_dense.cu)
   DevBuf dn_M;       // u8 [n_groups*256][Ppad] stacked annotation x iteration operand
-  DevBuf dn_C;       // u8 [n_cell_blocks*128][Ppad] densified counts (cells x peaks)
+  DevBuf dn_C;       // u8 [chunk cells][Ppad] densified counts of the current cell chunk / digit plane
+  DevBuf dn_S;       // int64 [K][B+1][chunk cells] exact sums when counts need several u8 planes
   double dn_flops = 0;
   int opt_path = 0;  // 0 auto, 1 force row-gather SpMM, 2 force dense tcgen05
+  int opt_pair = 1;  // dense path: CTA-pair kernel (tcgen05 cta_group::2) vs single-CTA kernel
+  int64_t opt_chunk = 0;       // dense path: cap on cells per GEMM launch (0 = memory budget)
+  int opt_check_zero = 1;      // reject peaks without fragments (off for shards of a larger matrix)
 
   // background sampler / compat-routine buffers (cv_background.cu, cv_compat.cu)
   DevBuf bk[16];
@@ -143,12 +156,37 @@ int cv_build_layout(cv_handle* h, int W);
 int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
                          const double* d_binp_colmajor, const double* d_bin_xy, double w,
                          int niter, int32_t* host_out, double* host_binprob, double* host_density);
-// cv_dense.cu
-int cv_dense_feasible(cv_handle* h, std::string* reason);
-double cv_dense_cost_ms(cv_handle* h);
-int cv_dense_contract(cv_handle* h, int keep_sums, int* T_out, int* soft_fail);
+// flag words of a deviations call live behind the K1 words
+#define CV_DFLAGS 8
+// timed-span categories (cv_stage_stats)
+enum { CV_SPAN_LAYOUT = 0, CV_SPAN_ANNO = 1, CV_SPAN_CONTRACT = 2, CV_SPAN_FINALIZE = 3, CV_SPAN_K1 = 4, CV_SPAN_N = 5 };
+void cv_span_begin(cv_handle* h, int cat);
+void cv_span_end(cv_handle* h);
+void cv_spans_reset(cv_handle* h);
+void cv_spans_collect(cv_handle* h, double* ms_by_cat /*CV_SPAN_N*/);   // after a stream sync
+
+// cv_dense.cu: shape of the dense tensor-core path for the current problem
+struct DensePlan {
+  int I = 0, G = 0, n_groups = 0;
+  int planes = 1;            // u8 digit planes of the counts (1 when max count <= 255)
+  int pair = 1;              // CTA-pair kernel
+  int64_t Ppad = 0, rowsM = 0;
+  int64_t chunk_cells = 0;   // cells per GEMM launch, multiple of 256
+  int64_t m_bytes = 0, c_bytes = 0, sums_bytes = 0;
+};
+int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan* pl, std::string* why);
+double cv_dense_cost_ms(cv_handle* h, const DensePlan& pl);
+int cv_dense_prepare(cv_handle* h, const DensePlan& pl);
+int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, int keep_sums);
+int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, int with_counts, int* soft_fail);
 // cv_dense_build.cu
-int cv_dense_build_operands(cv_handle* h, int G, int64_t Ppad, int64_t rowsM, int64_t rowsC, int* soft_fail);
+int cv_dense_build_rows(cv_handle* h, const DensePlan& pl);
+int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift);
+// cv_counts.cu: K1 in pieces so the streamed call can run it per uploaded cell chunk
+int cv_counts_begin(cv_handle* h);
+int cv_counts_range(cv_handle* h, int x_type, int64_t e0, int64_t e1, int64_t c0, int64_t c1);
+int cv_counts_finish_async(cv_handle* h);
+int cv_counts_verdict(cv_handle* h, const uint32_t* hflags);
 // cv_deviations.cu
 int cv_choose_tile(cv_handle* h, int B, int acc_bytes, int* W_out);
 

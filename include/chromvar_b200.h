@@ -57,8 +57,13 @@ void cv_destroy(cv_handle* h);
 const char* cv_last_error(const cv_handle* h); /* h == NULL: last error of a failed cv_create */
 int cv_version(void);
 int cv_set_seed(cv_handle* h, uint64_t seed);
-/* options: "path" = 0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05 (fails if the problem
- * cannot be represented exactly in u8 operands) */
+/* options:
+ *   "path"             0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05 (fails if the problem
+ *                      cannot be represented exactly in u8 operands / s32 accumulators)
+ *   "dense_cta_pair"   1 (default) tcgen05 cta_group::2 kernel, 0 single-CTA kernel
+ *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
+ *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
+ *                      0 for a shard of a larger matrix (the caller checks the reduced totals) */
 int cv_set_option(cv_handle* h, const char* key, int64_t value);
 /* the CUDA stream all of this handle's kernels run on (a cudaStream_t), for event timing */
 void* cv_stream(cv_handle* h);
@@ -113,6 +118,19 @@ int cv_deviations(cv_handle* h, int64_t K, const int64_t* annoptr, const int32_t
                   double* out_dev, double* out_z, double* out_matches, double* out_overlap,
                   double* out_variability, int64_t* out_observed, int64_t* out_sampled);
 
+/* compute_deviations_core as ONE call on host data (what the R shim's .Call passes): the counts
+ * matrix (arguments as cv_set_counts_csc), annotations / background / expectation (as
+ * cv_deviations; expectation == NULL means computeExpectations' default, :357-359) in, results out.
+ * Counts travel to the device in cell chunks while earlier chunks are already in the GEMM, and
+ * finished chunks of the K x N results travel back while later chunks are computed.  Afterwards
+ * the counts are resident exactly as after cv_set_counts_csc. */
+int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr, int colptr_type,
+                      const int32_t* rowidx, const void* x, int x_type, int64_t K,
+                      const int64_t* annoptr, const int32_t* annoidx, int index_base,
+                      const int32_t* bg, int B, const double* expectation, double* out_dev,
+                      double* out_z, double* out_matches, double* out_overlap,
+                      double* out_variability);
+
 /* The same call split in three so a caller (bench.py `value`, repeated-set callers such as
  * R/variability_synergy.R:173-177) can keep inputs resident in HBM:
  *   upload   : H2D of annotations / background / expectation (raw input formats only)
@@ -164,9 +182,11 @@ typedef struct cv_stage_stats {
   int64_t h2d_bytes, d2h_bytes;
   int64_t kernel_launches;   /* kernels launched by this handle since creation */
   int32_t path;              /* 0 = cell-tiled row-gather SpMM, 1 = dense tcgen05 */
-  int32_t cell_tile;         /* W */
-  int32_t n_cell_tiles;
+  int32_t cell_tile;         /* row-gather: W; dense: cells per tile (256 = CTA pair, 128) */
+  int32_t n_cell_tiles;      /* row-gather: tiles; dense: cell chunks (GEMM launches per plane) */
   int32_t acc_bytes;         /* accumulator width used (4 or 8) */
+  int32_t planes;            /* dense path: u8 digit planes of the counts (1 when max count <= 255) */
+  int32_t reserved;
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
 

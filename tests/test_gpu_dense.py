@@ -17,11 +17,16 @@ from test_gpu_parity import assert_close, check_against_oracle, sets_to_csr, _mi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def dense_engine(engine):
+@pytest.fixture(params=["cta_pair", "single_cta"])
+def dense_engine(engine, request):
+    """Dense path forced, once per GEMM kernel: tcgen05 cta_group::2 (256-cell tiles on two SMs,
+    the default) and the single-CTA kernel (128-cell tiles)."""
     engine.set_option("path", 2)
+    engine.set_option("dense_cta_pair", 1 if request.param == "cta_pair" else 0)
     yield engine
     engine.set_option("path", 0)
+    engine.set_option("dense_cta_pair", 1)
+    engine.set_option("cell_chunk", 0)
 
 
 def _run(engine, C, sets, bg, e, sums=True):
@@ -119,20 +124,154 @@ def test_dense_niterations(dense_engine, golden_mini, B):
     check_against_oracle(got, ref)
 
 
+def test_dense_digit_planes_for_large_counts(dense_engine):
+    """Counts above 255 run as u8 digit planes (one GEMM per plane, int64 sums combined, same fp64
+    finish): bulk-like dense counts up to ~70000 (3 planes), 300 samples (3 cell blocks, the last
+    one partial), bit-exact sums against the oracle."""
+    rng = np.random.default_rng(0)
+    P, N = 900, 300
+    D = rng.negative_binomial(2, 0.001, (P, N)).astype(np.float64)
+    D[rng.random(D.shape) < 0.05] = 0
+    D[0, 0] = 70000.0
+    D[D.sum(axis=1) == 0, 0] = 1
+    bg = rng.integers(1, P + 1, (P, 50)).astype(np.int32)
+    e = D.sum(axis=1) / D.sum()
+    sets = [np.sort(rng.choice(P, s, replace=False)) + 1 for s in (1, 30, 200, 900, 45, 77, 3)]
+    ptr, idx = sets_to_csr(sets)
+    dense_engine.set_counts_dense(D)
+    got = dense_engine.deviations(ptr, idx, bg, e, sums=True)
+    st = dense_engine.stats()
+    assert st["path"] == 1 and st["planes"] == 3
+    ref = orc.compute_deviations_core(sp.csc_matrix(D), sets, bg, e, intermediate=True)
+    check_against_oracle(got, ref)
+    assert_close(got["variability"], orc.row_sds(ref["z"], True), "variability")
+    # two planes, and the row-gather kernel agrees bit for bit on the sums
+    D2 = np.minimum(D, 60000.0)
+    dense_engine.set_counts_dense(D2)
+    e2 = D2.sum(axis=1) / D2.sum()
+    a = dense_engine.deviations(ptr, idx, bg, e2, sums=True)
+    assert dense_engine.stats()["planes"] == 2
+    dense_engine.set_option("path", 1)
+    b = dense_engine.deviations(ptr, idx, bg, e2, sums=True)
+    dense_engine.set_option("path", 2)
+    assert np.array_equal(a["observed"], b["observed"]) and np.array_equal(a["sampled"], b["sampled"])
+    assert_close(a["z"], b["z"], "z planes vs row-gather")
+
+
 def test_dense_refuses_what_it_cannot_represent(dense_engine):
+    """A peak listed 300 times in one annotation does not fit the u8 operand: forced dense refuses,
+    auto mode falls back to the exact row-gather kernel."""
     from chromvar_b200 import _lib
     rng = np.random.default_rng(0)
-    D = rng.integers(0, 1000, (300, 20)).astype(np.float64)       # counts above 255
+    D = rng.integers(0, 200, (300, 20)).astype(np.float64)
     D[D.sum(axis=1) == 0, 0] = 1
     bg = rng.integers(1, 301, (300, 10)).astype(np.int32)
     dense_engine.set_counts_dense(D)
-    ptr, idx = sets_to_csr([np.arange(1, 100)])
+    sets = [np.concatenate([np.full(300, 7), np.arange(1, 100)]), np.arange(5, 50)]
+    ptr, idx = sets_to_csr(sets)
     with pytest.raises(_lib.ChromVARError) as ei:
         dense_engine.deviations(ptr, idx, bg, D.sum(axis=1) / D.sum())
     assert ei.value.code == _lib.CV_ERR_UNSUPPORTED
-    # auto mode falls back to the exact row-gather kernel
     dense_engine.set_option("path", 0)
     got = dense_engine.deviations(ptr, idx, bg, D.sum(axis=1) / D.sum(), sums=True)
-    ref = orc.compute_deviations_core(sp.csc_matrix(D), [np.arange(1, 100)], bg, D.sum(axis=1) / D.sum(), intermediate=True)
+    ref = orc.compute_deviations_core(sp.csc_matrix(D), sets, bg, D.sum(axis=1) / D.sum(), intermediate=True)
     check_against_oracle(got, ref)
     assert dense_engine.stats()["path"] == 0
+
+
+def _small_problem():
+    from chromvar_b200 import synthetic
+    d = synthetic.make_config("small")
+    C = d["counts"]
+    P, N = C.shape
+    bg = synthetic.random_background(P, 50, np.random.default_rng(2))
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    sets = [d["annoidx"][d["annoptr"][k]:d["annoptr"][k + 1]] for k in range(12)]
+    sets.insert(6, np.zeros(0, np.int32))
+    ptr, idx = sets_to_csr(sets)
+    return C, P, N, bg, e, ptr, idx
+
+
+def test_dense_cell_chunks_and_kernels_agree_bitwise(engine):
+    """20000 x 2000: one chunk vs chunks of 256 / 768 cells (the last one partial), CTA-pair vs
+    single-CTA kernel: every output is bit-identical (same integer sums, same fp64 epilogue)."""
+    C, P, N, bg, e, ptr, idx = _small_problem()
+    engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    engine.set_option("path", 2)
+    try:
+        base = engine.deviations(ptr, idx, bg, e, sums=True)
+        assert engine.stats()["cell_tile"] == 256
+        for pair, chunk in ((1, 256), (1, 768), (0, 0), (0, 640)):
+            engine.set_option("dense_cta_pair", pair)
+            engine.set_option("cell_chunk", chunk)
+            got = engine.deviations(ptr, idx, bg, e, sums=True)
+            st = engine.stats()
+            assert st["cell_tile"] == (256 if pair else 128)
+            if chunk:
+                assert st["n_cell_tiles"] == -(-N // (-(-chunk // 256) * 256))
+            for key in ("observed", "sampled", "dev", "z", "variability", "matches", "overlap"):
+                assert np.array_equal(got[key], base[key], equal_nan=True), (pair, chunk, key)
+    finally:
+        engine.set_option("path", 0)
+        engine.set_option("dense_cta_pair", 1)
+        engine.set_option("cell_chunk", 0)
+
+
+def test_streamed_call_equals_resident_call(engine):
+    """cv_deviations_csc (counts arriving in cell chunks while earlier chunks are in the GEMM,
+    results leaving chunk by chunk) against cv_set_counts_csc + cv_deviations: bit-identical, and
+    the counts are resident afterwards."""
+    C, P, N, bg, e, ptr, idx = _small_problem()
+    engine.set_option("path", 2)
+    try:
+        engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+        base = engine.deviations(ptr, idx, bg, e)
+        for chunk, xdtype in ((0, np.float64), (512, np.float64), (0, np.int32), (1024, np.uint8)):
+            engine.set_option("cell_chunk", chunk)
+            got = engine.deviations_csc(P, N, C.indptr.astype(np.int32), C.indices, C.data.astype(xdtype),
+                                        ptr, idx, bg, e)
+            st = engine.stats()
+            assert st["path"] == 1 and st["n_cell_tiles"] >= 2          # really chunked
+            for key in ("dev", "z", "variability", "matches", "overlap"):
+                assert np.array_equal(got[key], base[key], equal_nan=True), (chunk, key)
+            fpp, fps, tot = engine.fragments()
+            assert np.array_equal(fpp, np.asarray(C.sum(axis=1)).ravel())
+            assert np.array_equal(fps, np.asarray(C.sum(axis=0)).ravel()) and tot == C.sum()
+            assert np.array_equal(engine.expectations(), e)
+        # default expectation (NULL): the plain sequence inside the same entry point
+        got = engine.deviations_csc(P, N, C.indptr, C.indices, C.data, ptr, idx, bg, None)
+        for key in ("dev", "z"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), key
+    finally:
+        engine.set_option("path", 0)
+        engine.set_option("cell_chunk", 0)
+
+
+def test_streamed_call_validates_and_falls_back(engine):
+    from chromvar_b200 import _lib
+    C, P, N, bg, e, ptr, idx = _small_problem()
+    engine.set_option("path", 2)
+    try:
+        x = C.data.astype(np.float64).copy()
+        x[len(x) // 2] = 2.5                                   # counts_check fails in the middle chunk
+        with pytest.raises(_lib.ChromVARError) as ei:
+            engine.deviations_csc(P, N, C.indptr, C.indices, x, ptr, idx, bg, e)
+        assert ei.value.code == _lib.CV_ERR_INVALID and "integer" in str(ei.value)
+        bad_bg = bg.copy()
+        bad_bg[17, 3] = P + 1
+        with pytest.raises(_lib.ChromVARError) as ei:
+            engine.deviations_csc(P, N, C.indptr, C.indices, C.data, ptr, idx, bad_bg, e)
+        assert ei.value.code == _lib.CV_ERR_INVALID
+        # a count above 255 shows up only once K1 has seen it: the call redoes itself with digit planes
+        x = C.data.astype(np.float64).copy()
+        x[-5] = 1000.0
+        C2 = sp.csc_matrix((x, C.indices, C.indptr), shape=C.shape)
+        e2 = np.asarray(C2.sum(axis=1)).ravel() / C2.sum()
+        got = engine.deviations_csc(P, N, C.indptr, C.indices, x, ptr, idx, bg, e2)
+        assert engine.stats()["planes"] == 2
+        engine.set_counts_csc(P, N, C2.indptr, C2.indices, C2.data)
+        ref = engine.deviations(ptr, idx, bg, e2)
+        for key in ("dev", "z", "variability"):
+            assert np.array_equal(got[key], ref[key], equal_nan=True), key
+    finally:
+        engine.set_option("path", 0)
