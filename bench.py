@@ -110,7 +110,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def make_workload(rank, cells, quick):
+def make_workload(rank, cells, quick, workload=None):
     from chromvar_b200 import synthetic
     t0 = time.time()
     if quick:
@@ -118,8 +118,12 @@ def make_workload(rank, cells, quick):
         name = "small"
     else:
         over = {"N": cells} if cells else {}
-        d = synthetic.make_config(WORKLOAD, seed_offset=rank, **over)
-        name = WORKLOAD
+        name = workload or WORKLOAD
+        d = synthetic.make_config(name, seed_offset=rank, **over)
+    if not hasattr(d["counts"], "indptr"):
+        import scipy.sparse as sp
+        d["dense"] = d["counts"]                       # bulk (config 4): dense column-major counts
+        d["counts"] = sp.csc_matrix(d["counts"])
     log("[bench] rank %d: synthetic %s %s nnz=%d (%.1fs)" % (rank, name, d["counts"].shape, d["counts"].nnz,
                                                             time.time() - t0))
     return d, name
@@ -129,13 +133,32 @@ def make_workload(rank, cells, quick):
 # reference arm: CPU restatement of the reference algorithm (the reference's R path cannot run:
 # no R on this image).  Only this leg and cpu_baseline execute anything under oracle/.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(d, bg, e, anno_slice, workers):
+def cpu_reference_step(d, bg, e, anno_slice, workers, want_results=False):
     from oracle import chromvar_oracle as orc
     ptr, idx = d["annoptr"], d["annoidx"]
     sets = [idx[ptr[k]:ptr[k + 1]].astype(np.int64) for k in anno_slice]
     t0 = time.perf_counter()
-    orc.deviations_task_farm(d["counts"], sets, bg, e, workers)
-    return time.perf_counter() - t0
+    res = orc.deviations_task_farm(d["counts"], sets, bg, e, workers)
+    dt = time.perf_counter() - t0
+    return (dt, res) if want_results else dt
+
+
+def parity_report(got_dev, got_z, ref_dev, ref_z):
+    """GPU results of the timed e2e step against the CPU restatement on the sampled annotations:
+    abs(d) <= 1e-5 * max(abs(ref), 1e-3) and identical NA masks."""
+    out = {"annotations_checked": int(ref_z.shape[0]), "cells": int(ref_z.shape[1]), "tolerance": 1e-5}
+    worst = 0.0
+    ok = True
+    for g, r in ((got_dev, ref_dev), (got_z, ref_z)):
+        ng, nr = np.isnan(g), np.isnan(r)
+        ok &= bool(np.array_equal(ng, nr))
+        m = ~(nr | ng | np.isinf(r))
+        if m.any():
+            worst = max(worst, float((np.abs(g[m] - r[m]) / np.maximum(np.abs(r[m]), 1e-3)).max()))
+    out["max_rel_err"] = worst
+    out["na_masks_equal"] = ok
+    out["pass"] = bool(ok and worst <= 1e-5)
+    return out
 
 
 def host_background(d, rng):
@@ -155,7 +178,7 @@ def run_reference(args):
     rank, ws = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    d, name = make_workload(0, args.cells, args.quick)
+    d, name = make_workload(0, args.cells, args.quick, args.workload)
     C = d["counts"]
     P, N = C.shape
     K = len(d["annoptr"]) - 1
@@ -205,13 +228,21 @@ def run_ours(args):
     eng = _lib.Handle(local, seed=20173)
     eng.set_option("path", args.path)
     eng.set_option("dense_cta_pair", args.pair)
-    d, name = make_workload(rank, args.cells, args.quick)
+    if args.band:
+        eng.set_option("dense_band", args.band)
+    if args.debug_no_tma:
+        eng.set_option("debug_no_tma", args.debug_no_tma)
+    d, name = make_workload(rank, args.cells, args.quick, args.workload)
     C = d["counts"]
     P, N = C.shape
     K = len(d["annoptr"]) - 1
     nnz = int(C.nnz)
 
     def pin(a):
+        """Pinned copy of a (memory order kept: the background matrix stays column-major)."""
+        a = np.asarray(a)
+        if a.ndim == 2 and a.flags.f_contiguous and not a.flags.c_contiguous:
+            return torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory().numpy().T
         return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
     h_colptr, h_rowidx, h_x = pin(C.indptr.astype(np.int64)), pin(C.indices.astype(np.int32)), pin(C.data.astype(np.float64))
@@ -297,8 +328,11 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     n_e2e = max(1, min(args.steps, 10))
+    e2e_each = []
     for _ in range(n_e2e):
+        t1 = time.perf_counter()
         e2e_step()
+        e2e_each.append(1e3 * (time.perf_counter() - t1))
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_stats = eng.stats()
@@ -337,13 +371,15 @@ def run_ours(args):
                 "updates_per_launch": int(upd), "share_of_step": share}
 
     # ---- CPU baseline beside it (N=1 only): bounded sample of the same workload ---------------
-    cpu = None
+    cpu = parity = None
     if ws == 1 and not args.no_cpu_baseline:
         workers = os.cpu_count() or 1
-        S = max(1, min(K, 2 * workers))
-        dt = cpu_reference_step(d, bg, e, list(range(S)), workers)
+        S = max(1, min(K, (2 if nnz < 1e8 else 1) * workers))
+        dt, (ref_z, ref_dev) = cpu_reference_step(d, bg, e, list(range(S)), workers, want_results=True)
         cpu = {"value": S * N / dt, "unit": UNIT, "cores": workers, "kind": "port",
                "sample": "%d of %d annotations x all %d cells, fork pool of %d workers, %.1fs" % (S, K, N, workers, dt)}
+        parity = parity_report(out["dev"][:S], out["z"][:S], ref_dev, ref_z)
+        log("[bench] parity of the timed e2e results vs the CPU restatement: %s" % parity)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
@@ -359,13 +395,14 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
                 "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
-                "cell_chunks": int(e2e_stats["n_cell_tiles"]),
+                "cell_chunks": int(e2e_stats["n_cell_tiles"]), "ms_each_step": [round(t, 2) for t in e2e_each],
                 "device_ms": {k: round(float(e2e_stats[k]), 3) for k in
                               ("ms_counts_layout", "ms_anno_prep", "ms_contract", "ms_finalize")}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "parity": parity,
         "stages_ms": dict(zip(["counts_layout", "anno_prep", "contract", "finalize"],
                               (stage_acc / args.steps).round(4).tolist())),
         "other_paths": {"getBackgroundPeaks_ms_device": bg_ms_dev, "getBackgroundPeaks_ms_wall": 1e3 * t_bg,
@@ -382,9 +419,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (default: config 2's 10000)")
+    ap.add_argument("--workload", default=None, help="synthetic configuration (default cfg2_scatac_motifs; "
+                    "cfg3_kmers, cfg4_bulk, cfg5_atlas_shard are parity / scale cases, not the bench line)")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
+    ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
+    ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
     ap.add_argument("--pair", type=int, default=1, help="dense path: 1 CTA-pair kernel (cta_group::2), 0 single-CTA kernel")
     args = ap.parse_args()
     if args.warmup < 3 and not args.quick and args.impl == "ours":

@@ -99,6 +99,12 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
     return CV_ERR_CUDA;
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+  if (cudaHostAlloc((void**)&h->pinned, CV_PINNED_WORDS * 4, cudaHostAllocDefault) != cudaSuccess) {
+    g_create_err = "cudaHostAlloc failed";
+    cudaGetLastError();
+    delete h;
+    return CV_ERR_OOM;
+  }
   *out = h;
   return CV_OK;
 }
@@ -118,6 +124,7 @@ extern "C" void cv_destroy(cv_handle* h) {
   for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->pinned) cudaFreeHost(h->pinned);
   if (h->s_up) cudaStreamDestroy(h->s_up);
   if (h->s_dn) cudaStreamDestroy(h->s_dn);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -147,6 +154,8 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
     h->opt_chunk = value;
     return CV_OK;
   }
+  if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
+  if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
   CV_FAIL(h, CV_ERR_INVALID, "unknown option %s", key);
 }

@@ -100,6 +100,16 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the cells operand read from tensor memory (128 lanes x 32 bytes)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
 // K-major operand tile in the canonical SWIZZLE_128B layout TMA produces: rows of 128 bytes,
 // 8-row groups 1024 bytes apart (SBO), 16-byte chunks XOR-swizzled by (row % 8).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -201,6 +211,7 @@ struct DenseParams {
   // DN_EPI_SUMS: exact integer sums of one u8 digit plane, added into sums[(k*(B+1)+j)*sums_ld + (c - sums_c0)]
   long long* sums;
   int sums_ld, sums_c0, sums_shift, sums_acc;
+  int debug_no_tma;          // experiment: the producer only signals the barrier (results are garbage)
 };
 
 struct DWelford { double n, mean, m2; };
@@ -415,6 +426,7 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
         dn_decode_tile(prm.band, prm.n_groups, prm.n_cell_blocks, tile, cb, g);
         for (int kb = 0; kb < prm.n_kblocks; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1u);
+          if (prm.debug_no_tma) { mbar_arrive(full_bar + s); if (++s == DN_STAGES) { s = 0; ph ^= 1u; } continue; }
           mbar_expect_tx(full_bar + s, DN_STAGE_BYTES);
           tma_load_2d(&map_c, full_bar + s, smem_a + s * DN_A_BYTES, kb * DN_BLOCK_K, cb * DN_BLOCK_M);
           tma_load_2d(&map_m, full_bar + s, smem_b + s * DN_B_BYTES, kb * DN_BLOCK_K, g * DN_BLOCK_N);
@@ -439,6 +451,36 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * DN_A_BYTES));
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * DN_B_BYTES));
+          if (prm.debug_no_tma > 1) {
+            // issue-pattern experiments (garbage results; bench.py --debug-no-tma V)
+            const int v = prm.debug_no_tma;
+            if (v == 2) {          // alternate two accumulators: no back-to-back dependent MMAs
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_i8(tmem_base + (uint32_t)((k & 1) * DN_BLOCK_N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+            } else if (v == 3) {   // two independent N = 128 halves, alternating
+              constexpr uint32_t idesc_h = make_idesc_u8(DN_BLOCK_M, DN_BLOCK_N / 2);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_i8(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_h, 1u);
+                umma_i8(tmem_d + 128u, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2 + 1024), idesc_h, 1u);
+              }
+            } else if (v == 4) {   // overwrite instead of accumulate: no read of D
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_i8(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 0u);
+            } else if (v == 6) {   // A operand from tensor memory (garbage columns of the other stage)
+              const uint32_t ta = tmem_base + (uint32_t)((as ^ 1) * DN_BLOCK_N);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_i8_ts(tmem_d, ta + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, 1u);
+            } else {               // v == 5: same operand bytes every time (k offset 0): smem bank / swizzle effects
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_i8(tmem_d, da, db, idesc, 1u);
+            }
+            tc_commit(empty_bar + s);
+            if (++s == DN_STAGES) { s = 0; ph ^= 1u; }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < DN_BLOCK_K / DN_UMMA_K; ++k)
             umma_i8(tmem_d, da + (uint64_t)(k * DN_UMMA_K / 16), db + (uint64_t)(k * DN_UMMA_K / 16), idesc,
@@ -536,6 +578,11 @@ k_dense_contract_pair(const __grid_constant__ CUtensorMap map_c, const __grid_co
         const int ym = g * DN_BLOCK_N + (int)rank * (DN_BLOCK_N / 2);
         for (int kb = 0; kb < prm.n_kblocks; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1u);
+          if (prm.debug_no_tma) {
+            if (rank == 0) mbar_arrive(full_bar + s);
+            if (++s == DN_STAGES2) { s = 0; ph ^= 1u; }
+            continue;
+          }
           if (rank == 0) mbar_expect_tx(full_bar + s, 2 * DN_STAGE2_BYTES);
           const uint32_t fb = mapa_u32(smem_u32(full_bar + s), 0);
           tma_load_2d_pair(&map_c, fb, smem_a + s * DN_A_BYTES, kb * DN_BLOCK_K, yc);
@@ -764,6 +811,7 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
   if (c0 % 256 || c1 <= c0 || c1 - c0 > pl.chunk_cells)
     CV_FAIL(h, CV_ERR_INVALID, "dense chunk [%lld, %lld) is not aligned / too large", (long long)c0, (long long)c1);
   const int64_t rows = round_up(c1 - c0, 256);
+  if (pl.planes > 1) CV_TRY(cv_ensure(h, h->dn_S, (size_t)pl.chunk_cells * (size_t)K * (B + 1) * 8));
   CUtensorMap map_c, map_m;
   CV_TRY(make_map_u8(h, &map_c, h->dn_C.p, (uint64_t)rows, (uint64_t)pl.Ppad, DN_BLOCK_M));
   CV_TRY(make_map_u8(h, &map_m, h->dn_M.p, (uint64_t)pl.rowsM, (uint64_t)pl.Ppad, pl.pair ? DN_BLOCK_N / 2 : DN_BLOCK_N));
@@ -775,7 +823,8 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
   prm.n_cell_blocks = (int)((std::min<int64_t>(c1, N) - c0 + DN_BLOCK_M - 1) / DN_BLOCK_M);
   prm.ncb_total = (int)((N + DN_BLOCK_M - 1) / DN_BLOCK_M);
   prm.n_groups = pl.n_groups; prm.n_kblocks = (int)(pl.Ppad / DN_BLOCK_K);
-  prm.band = 12;
+  prm.band = h->opt_band > 0 ? h->opt_band : 12;
+  prm.debug_no_tma = h->opt_debug_no_tma;
   prm.annoptr = h->annoptr.as<int64_t>();
   prm.etab = h->etab.as<double>();
   prm.fps = h->fps.as<double>();
@@ -828,12 +877,6 @@ int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, in
   if ((double)h->max_cell_tot * (double)maxmult >= 2147483647.0) {
     *soft_fail = 1;
     CV_FAIL(h, CV_ERR_UNSUPPORTED, "s32 accumulator bound exceeded");
-  }
-  uint32_t planes = 1;
-  for (uint32_t v = h->max_val >> 8; v; v >>= 8) planes++;
-  if ((int)planes > pl.planes) {
-    *soft_fail = 1;
-    CV_FAIL(h, CV_ERR_UNSUPPORTED, "counts need %u u8 planes, the call assumed %d", planes, pl.planes);
   }
   return CV_OK;
 }

@@ -9,6 +9,8 @@
 //                  (:486-520; src/utils.cpp:9-25)
 //   k_var_merge    variability partials -> row SD of z
 //   k_transpose    [K][N] -> K x N column-major (ABI layout)
+#include <stdlib.h>
+
 #include <algorithm>
 #include <numeric>
 
@@ -481,7 +483,11 @@ struct DevIO {
   int soft_fail = 0;                 // set when the dense path turned out not to be exact
 };
 
-static int enqueue_counts_upload(cv_handle* h, const DevIO& io, int64_t c0, int64_t c1, cudaEvent_t done) {
+// Chunk [c0, c1) of the counts: H2D of its row indices and values, K1 on what arrived (validation,
+// u32 values, per-peak / per-cell totals, fragments per sample), and a snapshot of the K1 flag
+// words into pinned host memory -- all on the upload stream, so it runs ahead of the GEMMs.
+static int enqueue_counts_upload(cv_handle* h, const DevIO& io, int64_t c0, int64_t c1, int chunk_index,
+                                 cudaEvent_t done) {
   const int64_t e0 = io.h_colptr[c0], e1 = io.h_colptr[c1];
   if (e1 > e0) {
     CV_CUDA(h, cudaMemcpyAsync(h->rowidx.as<int32_t>() + e0, io.h_rowidx + e0, (size_t)(e1 - e0) * 4,
@@ -489,6 +495,12 @@ static int enqueue_counts_upload(cv_handle* h, const DevIO& io, int64_t c0, int6
     CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0 * io.xb, io.h_x + (size_t)e0 * io.xb,
                                (size_t)(e1 - e0) * io.xb, cudaMemcpyHostToDevice, h->s_up));
   }
+  cudaStream_t compute = h->stream;
+  h->stream = h->s_up;                                   // CV_LAUNCH targets h->stream
+  int rc = cv_counts_range(h, io.x_type, e0, e1, c0, c1);
+  h->stream = compute;
+  CV_TRY(rc);
+  CV_CUDA(h, cudaMemcpyAsync(h->pinned + 4 * chunk_index, h->flags.p, 16, cudaMemcpyDeviceToHost, h->s_up));
   CV_CUDA(h, cudaEventRecord(done, h->s_up));
   return CV_OK;
 }
@@ -595,12 +607,21 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   if (use_dense) {
     const int64_t chunk = pl.chunk_cells;
     const int n_chunks = (int)((N + chunk - 1) / chunk);
-    std::vector<cudaEvent_t> ev_up((size_t)n_chunks), ev_done((size_t)n_chunks);
-    for (int i = 0; i < n_chunks; ++i) { ev_up[i] = pool_event(h); ev_done[i] = pool_event(h); }
+    std::vector<cudaEvent_t> ev_up((size_t)n_chunks), ev_done((size_t)n_chunks), ev_dn((size_t)n_chunks);
+    for (int i = 0; i < n_chunks; ++i) { ev_up[i] = pool_event(h); ev_done[i] = pool_event(h); ev_dn[i] = pool_event(h); }
+    const bool trace = getenv("CV_TRACE") != nullptr;
+    cudaEvent_t ev_t0 = pool_event(h), ev_prep = pool_event(h);
+    CV_CUDA(h, cudaEventRecord(ev_t0, h->stream));         // origin of the timeline; orders the upload stream
     auto lo = [&](int i) { return (int64_t)i * chunk; };
     auto hi = [&](int i) { return std::min<int64_t>(N, (int64_t)(i + 1) * chunk); };
     CV_TRY(cv_dense_prepare(h, pl));                          // operand M + tables: cell independent
-    if (streaming) CV_TRY(enqueue_counts_upload(h, *io, lo(0), hi(0), ev_up[0]));
+    if (trace) cudaEventRecord(ev_prep, h->stream);
+    if (streaming) {
+      if (n_chunks > CV_PINNED_WORDS / 4) CV_FAIL(h, CV_ERR_UNSUPPORTED, "too many cell chunks (%d)", n_chunks);
+      // the zeroing of the totals / flags (cv_counts_begin, compute stream) precedes the first K1
+      CV_CUDA(h, cudaStreamWaitEvent(h->s_up, ev_t0, 0));
+      CV_TRY(enqueue_counts_upload(h, *io, lo(0), hi(0), 0, ev_up[0]));
+    }
     // multiplicity bounds of the u8 operand before any GEMM runs (one short host sync; the first
     // counts chunk is already in flight)
     uint32_t hf[16];
@@ -616,26 +637,55 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     }
     if (use_dense) {
       const bool dl = io && (io->out_dev || io->out_z);
+      int planes_max = pl.planes;
       for (int i = 0; i < n_chunks; ++i) {
+        DensePlan pli = pl;
         if (streaming) {
+          // K1 of this chunk has run on the upload stream: its verdict and the largest count so far
+          // decide how many u8 digit planes this chunk's GEMM needs
+          CV_CUDA(h, cudaEventSynchronize(ev_up[i]));
+          const uint32_t* kf = h->pinned + 4 * i;
+          if (kf[0]) return cv_counts_verdict(h, kf);            // counts_check failed: message from K1
+          pli.planes = 1;
+          for (uint32_t v = kf[1] >> 8; v; v >>= 8) pli.planes++;
+          planes_max = std::max(planes_max, pli.planes);
           CV_CUDA(h, cudaStreamWaitEvent(h->stream, ev_up[i], 0));
-          cv_span_begin(h, CV_SPAN_K1);
-          CV_TRY(cv_counts_range(h, io->x_type, io->h_colptr[lo(i)], io->h_colptr[hi(i)], lo(i), hi(i)));
-          cv_span_end(h);
         }
-        CV_TRY(cv_dense_chunk(h, pl, lo(i), hi(i), keep_sums));
+        CV_TRY(cv_dense_chunk(h, pli, lo(i), hi(i), keep_sums));
         cv_span_begin(h, CV_SPAN_FINALIZE);
         CV_TRY(enqueue_transposes(h, lo(i), hi(i)));
         cv_span_end(h);
         CV_CUDA(h, cudaEventRecord(ev_done[i], h->stream));
         // host copies: next chunk in, previous chunk out (one behind, so that a blocking copy of
         // pageable memory still leaves a queued chunk for the GPU)
-        if (streaming && i + 1 < n_chunks) CV_TRY(enqueue_counts_upload(h, *io, lo(i + 1), hi(i + 1), ev_up[i + 1]));
-        if (dl && i > 0) CV_TRY(enqueue_result_download(h, *io, lo(i - 1), hi(i - 1), ev_done[i - 1]));
+        if (streaming && i + 1 < n_chunks)
+          CV_TRY(enqueue_counts_upload(h, *io, lo(i + 1), hi(i + 1), i + 1, ev_up[i + 1]));
+        if (dl && i > 0) {
+          CV_TRY(enqueue_result_download(h, *io, lo(i - 1), hi(i - 1), ev_done[i - 1]));
+          if (trace) cudaEventRecord(ev_dn[i - 1], h->s_dn);
+        }
       }
+      pl.planes = planes_max;
       if (dl) {
         CV_TRY(enqueue_result_download(h, *io, lo(n_chunks - 1), hi(n_chunks - 1), ev_done[n_chunks - 1]));
+        if (trace) cudaEventRecord(ev_dn[n_chunks - 1], h->s_dn);
         io->results_streamed = true;
+      }
+      if (trace) {
+        // timeline of the call (ms since its first kernel): CV_TRACE=1
+        cudaStreamSynchronize(h->stream);
+        cudaStreamSynchronize(h->s_dn);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev_t0, ev_prep);
+        fprintf(stderr, "[cv trace] operand M ready %.2f ms; chunks of %lld cells\n", t, (long long)chunk);
+        for (int i = 0; i < n_chunks; ++i) {
+          float a = -1.f, b = -1.f, c = -1.f;
+          if (streaming) cudaEventElapsedTime(&a, ev_t0, ev_up[i]);
+          cudaEventElapsedTime(&b, ev_t0, ev_done[i]);
+          if (dl) cudaEventElapsedTime(&c, ev_t0, ev_dn[i]);
+          fprintf(stderr, "[cv trace] chunk %d: counts on device %.2f, computed %.2f, results on host %.2f\n", i, a, b, c);
+        }
+        cudaGetLastError();
       }
       T = (int)((N + 127) / 128);
     }
@@ -704,7 +754,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
 
   // ---- stage 3: totals, zero-peak check, variability merge -----------------------------------------
   cv_span_begin(h, CV_SPAN_FINALIZE);
-  if (streaming) CV_TRY(cv_counts_finish_async(h));
+  if (streaming) CV_TRY(cv_counts_finish_async(h));       // every K1 chunk was waited for above
   if (h->opt_check_zero)
     CV_LAUNCH(h, k_check_zero_peaks, (unsigned)((P + 255) / 256), 256, 0,
               h->peak_tot.as<unsigned long long>(), (int)P, dflags);

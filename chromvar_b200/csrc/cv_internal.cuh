@@ -12,6 +12,7 @@
 #include "../../include/chromvar_b200.h"
 
 #define CV_NUM_SMS_FALLBACK 148
+#define CV_PINNED_WORDS 4096
 
 // ---- error plumbing -------------------------------------------------------------------
 #define CV_FAIL(h, code, ...)                                \
@@ -64,6 +65,7 @@ struct cv_handle {
   cudaStream_t s_up = nullptr;        // host -> device copies of the streamed call
   cudaStream_t s_dn = nullptr;        // device -> host copies overlapping the next chunk
   cudaEvent_t ev[8] = {};
+  uint32_t* pinned = nullptr;         // CV_PINNED_WORDS of page-locked host memory (flag snapshots)
   // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -135,6 +137,8 @@ struct cv_handle {
   int opt_path = 0;  // 0 auto, 1 force row-gather SpMM, 2 force dense tcgen05
   int opt_pair = 1;  // dense path: CTA-pair kernel (tcgen05 cta_group::2) vs single-CTA kernel
   int64_t opt_chunk = 0;       // dense path: cap on cells per GEMM launch (0 = memory budget)
+  int opt_band = 0;            // dense path: groups per raster band (0 = default)
+  int opt_debug_no_tma = 0;    // experiment only: GEMM without operand loads (garbage results)
   int opt_check_zero = 1;      // reject peaks without fragments (off for shards of a larger matrix)
 
   // background sampler / compat-routine buffers (cv_background.cu, cv_compat.cu)

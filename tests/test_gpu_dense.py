@@ -275,3 +275,26 @@ def test_streamed_call_validates_and_falls_back(engine):
             assert np.array_equal(got[key], ref[key], equal_nan=True), key
     finally:
         engine.set_option("path", 0)
+
+
+@pytest.mark.parametrize("maxcount", [9, 3000])
+def test_dense_many_peaks(dense_engine, maxcount):
+    """260k peaks: operand rows longer than one shared-memory chunk (three chunks in the row
+    builder, two in the cell builder), one and two u8 planes, against the oracle."""
+    rng = np.random.default_rng(11)
+    P, N, B = 260_000, 70, 50
+    nnz_col = 9000
+    rows = np.concatenate([np.sort(rng.choice(P, nnz_col, replace=False)) for _ in range(N)])
+    vals = rng.integers(1, maxcount + 1, rows.size).astype(np.float64)
+    indptr = np.arange(N + 1, dtype=np.int64) * nnz_col
+    C = sp.csc_matrix((vals, rows, indptr), shape=(P, N))
+    empty = np.nonzero(np.asarray(C.sum(axis=1)).ravel() == 0)[0]
+    C = (C + sp.csc_matrix((np.ones(empty.size), (empty, rng.integers(0, N, empty.size))), shape=(P, N))).tocsc()
+    bg = rng.integers(1, P + 1, (P, B)).astype(np.int32)
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    sets = [np.sort(rng.choice(P, s, replace=False)) + 1 for s in (1, 700, 40_000, 130_000, 2_500, 260_000, 9)]
+    got = _run(dense_engine, C, sets, bg, e)
+    st = dense_engine.stats()
+    assert st["path"] == 1 and st["planes"] == (1 if maxcount < 256 else 2)
+    ref = orc.compute_deviations_core(C, sets, bg, e, intermediate=True)
+    check_against_oracle(got, ref)
