@@ -118,7 +118,8 @@ extern "C" void cv_destroy(cv_handle* h) {
                     &h->scan_tmp, &h->annoptr, &h->anno_raw, &h->annoidx, &h->bg_raw, &h->bgT, &h->expect,
                     &h->etab, &h->overlap, &h->matches, &h->mark, &h->order, &h->work_ctr,
                     &h->dev_rm, &h->z_rm, &h->dev_cm, &h->z_cm, &h->varpart, &h->varfinal,
-                    &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C, &h->dn_S};
+                    &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C, &h->dn_S,
+                    &h->dn_abits, &h->dn_invptr, &h->dn_invsrc, &h->dn_E2, &h->dn_ov};
   for (DevBuf* b : bufs) cv_release(*b);
   for (DevBuf& b : h->bk) cv_release(b);
   for (int i = 0; i < 8; ++i)
@@ -154,6 +155,7 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
     h->opt_chunk = value;
     return CV_OK;
   }
+  if (!strcmp(key, "dense_rows_scatter")) { h->opt_rows_scatter = value != 0; return CV_OK; }
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
@@ -552,9 +554,8 @@ k_scan_add(uint32_t* __restrict__ out, int64_t n, const unsigned long long* __re
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (uint32_t)(*total);
 }
 
-// out has n+1 slots; returns total through *total_host
-static int exclusive_scan_u32(cv_handle* h, const uint32_t* in, uint32_t* out, int64_t n,
-                              unsigned long long* total_host) {
+// out has n+1 slots; asynchronous (the total stays on the device behind the block sums)
+int cv_exclusive_scan_u32_async(cv_handle* h, const uint32_t* in, uint32_t* out, int64_t n) {
   int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   if (nb < 1) nb = 1;
   CV_TRY(cv_ensure(h, h->scan_tmp, (size_t)(nb + 1) * 8));
@@ -562,7 +563,16 @@ static int exclusive_scan_u32(cv_handle* h, const uint32_t* in, uint32_t* out, i
   CV_LAUNCH(h, k_scan_block, (unsigned)nb, SCAN_THREADS, 0, in, out, n, sums);
   CV_LAUNCH(h, k_scan_sums, 1, 1024, 0, sums, nb, sums + nb);
   CV_LAUNCH(h, k_scan_add, (unsigned)nb, SCAN_THREADS, 0, out, n, sums, sums + nb);
-  CV_CUDA(h, cudaMemcpyAsync(total_host, sums + nb, 8, cudaMemcpyDeviceToHost, h->stream));
+  return CV_OK;
+}
+
+// out has n+1 slots; returns total through *total_host
+static int exclusive_scan_u32(cv_handle* h, const uint32_t* in, uint32_t* out, int64_t n,
+                              unsigned long long* total_host) {
+  CV_TRY(cv_exclusive_scan_u32_async(h, in, out, n));
+  int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (nb < 1) nb = 1;
+  CV_CUDA(h, cudaMemcpyAsync(total_host, h->scan_tmp.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   return CV_OK;
 }

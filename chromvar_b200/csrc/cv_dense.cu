@@ -790,14 +790,14 @@ static int launch_gemm(cv_handle* h, const DensePlan& pl, const CUtensorMap& map
 
 // Operand M, per-annotation tables and the exactness counters: everything that does not depend on
 // the cells.  Asynchronous on the handle's stream.
-int cv_dense_prepare(cv_handle* h, const DensePlan& pl) {
+int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows) {
   CV_TRY(cv_ensure(h, h->dn_M, (size_t)pl.m_bytes));
   CV_TRY(cv_ensure(h, h->dn_C, (size_t)pl.c_bytes));
   if (pl.sums_bytes) CV_TRY(cv_ensure(h, h->dn_S, (size_t)pl.sums_bytes));
   const int ncb_total = (int)((h->N + DN_BLOCK_M - 1) / DN_BLOCK_M);
   CV_TRY(cv_ensure(h, h->varpart, (size_t)h->K * ncb_total * 4 * 8));
   cv_span_begin(h, CV_SPAN_LAYOUT);
-  CV_TRY(cv_dense_build_rows(h, pl));
+  CV_TRY(cv_dense_build_rows(h, pl, scatter_rows));
   cv_span_end(h);
   h->dn_flops = 0;
   return CV_OK;

@@ -248,10 +248,232 @@ k_zero_pad_rows(uint8_t* __restrict__ M, int K, int G, int I, int64_t Ppad) {
   for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) base[i] = make_uint4(0, 0, 0, 0);
 }
 
+// =====================================================================================================
+// Gather formulation of the operand rows (default).  With the annotations as bit columns
+// Abits[w][p] (bit b of word w = peak p belongs to annotation 32 w + b) and the inverse background
+// map of every iteration (sources p of each destination peak q: bg[p, j] = q),
+//     M[(k, j), q] = sum over the sources p of (j, q) of bit_k(p),        M[(k, 0), q] = bit_k(q),
+// one thread produces 4 consecutive peaks of one iteration for 32 annotations at once: every
+// operand byte is written exactly once, coalesced (128 B per warp and row), with no shared-memory
+// staging, no zero fill and no atomics on the operand.  The overlap counts
+// sum_q M[(k, j), q] * M[(k, 0), q] (R/compute_deviations.R:506) fall out of the same registers;
+// the expected-fraction table is a row-gather sum over E2[p][j] = e[bg[p, j]] (:488, :502).
+// Lists that repeat a peak (multiplicity > 1 inside one annotation) cannot be bit columns: the
+// per-annotation scatter kernel above handles those inputs.
+// =====================================================================================================
+#define GR_THREADS 256
+#define GR_TQ 1024           // peaks per tile: 4 per thread
+
+__global__ void __launch_bounds__(256)
+k_anno_bits(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx, int K, int P,
+            uint32_t* __restrict__ Abits, uint32_t* __restrict__ dflags) {
+  const int k = blockIdx.x;
+  const uint32_t bit = 1u << (k & 31);
+  uint32_t* __restrict__ col = Abits + (int64_t)(k >> 5) * P;
+  const int64_t beg = annoptr[k], end = annoptr[k + 1];
+  bool dup = false;
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const uint32_t old = atomicOr(col + annoidx[i], bit);
+    dup |= (old & bit) != 0;
+  }
+  if (dup) atomicOr(dflags + 3, 1u);
+}
+
+// invsrc[invptr[j*P + q] ...] = the peaks p with bg[p, j] = q (cursor = the counts, consumed)
+__global__ void __launch_bounds__(256)
+k_inv_fill(const int32_t* __restrict__ bg, int base, int64_t PB, int P, const uint32_t* __restrict__ invptr,
+           uint32_t* __restrict__ cursor, int32_t* __restrict__ invsrc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= PB) return;
+  const int q = bg[i] - base;
+  if (q < 0 || q >= P) return;                    // flagged by k_bg_mult_count_cm
+  const int64_t j = i / P;
+  const int64_t idx = j * P + q;
+  const uint32_t old = atomicSub(cursor + idx, 1u);
+  invsrc[invptr[idx] + old - 1u] = (int32_t)(i - j * P);
+}
+
+// One CTA = one tile of 32 annotations (word w) x GR_TQ peaks of iteration j, built in shared
+// memory: thread t owns the 4 consecutive peaks 4t .. 4t+3 (one 32-bit column of every row), so
+// the byte increments need no atomics and lane t always hits bank t; only the SET bits of a source
+// word are visited (annotations are ~7 % dense).  The tile leaves as 16-byte stores, 1 KB per row.
+__global__ void __launch_bounds__(GR_THREADS)
+k_dense_rows_gather(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ invptr,
+                    const int32_t* __restrict__ invsrc, int K, int P, int B, int G, int64_t Ppad,
+                    uint8_t* __restrict__ M) {
+  __shared__ __align__(16) uint8_t tile[32 * GR_TQ];
+  __shared__ long long s_row[32];                 // byte offset of row (k, j) for the 32 annotations of this word
+  const int j = blockIdx.y, w = blockIdx.z;
+  const int I = B + 1;
+  if (threadIdx.x < 32) {
+    const int k = w * 32 + threadIdx.x;
+    s_row[threadIdx.x] = k < K ? ((long long)(k / G) * DB_BLOCK_N + (long long)(k % G) * I + j) * Ppad : -1ll;
+  }
+  {
+    uint4* t4 = reinterpret_cast<uint4*>(tile);
+#pragma unroll
+    for (int i = 0; i < (32 * GR_TQ / 16) / GR_THREADS; ++i) t4[i * GR_THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const uint32_t* __restrict__ Aw = Abits + (int64_t)w * P;
+  const int64_t q0 = (int64_t)blockIdx.x * GR_TQ + threadIdx.x * 4;
+  uint8_t* col = tile + threadIdx.x * 4;
+  if (j == 0) {
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      uint32_t wd = (q0 + qi < P) ? __ldg(Aw + q0 + qi) : 0u;
+      while (wd) {
+        const int b = __ffs(wd) - 1;
+        wd &= wd - 1;
+        col[b * GR_TQ + qi] = 1;
+      }
+    }
+  } else if (q0 < P) {
+    const uint32_t* __restrict__ ip = invptr + (int64_t)(j - 1) * P;
+    uint32_t sp[5];
+#pragma unroll
+    for (int qi = 0; qi < 5; ++qi) sp[qi] = __ldg(ip + min(q0 + qi, (int64_t)P));   // ip[P] = start of the next iteration
+    // all sources of the 4 peaks in one loop (less divergence than 4 short loops)
+    for (uint32_t s = sp[0]; s < sp[4]; ++s) {
+      uint32_t wd = __ldg(Aw + __ldg(invsrc + s));
+      const int qi = (s >= sp[1]) + (s >= sp[2]) + (s >= sp[3]);
+      while (wd) {
+        const int b = __ffs(wd) - 1;
+        wd &= wd - 1;
+        col[b * GR_TQ + qi] += 1;
+      }
+    }
+  }
+  __syncthreads();
+  // rows out: 64 x 16 B per row
+  for (int i = threadIdx.x; i < 32 * (GR_TQ / 16); i += GR_THREADS) {
+    const int r = i / (GR_TQ / 16), c = i % (GR_TQ / 16);
+    const long long ro = s_row[r];
+    const int64_t q = (int64_t)blockIdx.x * GR_TQ + c * 16;
+    if (ro >= 0 && q < Ppad)
+      *reinterpret_cast<uint4*>(M + ro + q) = *reinterpret_cast<const uint4*>(tile + r * GR_TQ + c * 16);
+  }
+}
+
+// Background overlap counts (R/compute_deviations.R:506): ov[k] = sum_j sum_p bit_k(p) * bit_k(bg[p, j]).
+// Thread = one annotation word x GR_NPAIR (peak, iteration) pairs; the per-annotation counts of a
+// thread are bit-sliced (7 carry-save planes), expanded once and reduced through the warp.
+#define GR_NPAIR 64
+__global__ void __launch_bounds__(256)
+k_overlap_bits(const uint32_t* __restrict__ Abits, const int32_t* __restrict__ bg, int base, int64_t PB, int P, int K,
+               unsigned long long* __restrict__ ov_total) {
+  __shared__ unsigned int s_ov[32];
+  const int w = blockIdx.y;
+  if (threadIdx.x < 32) s_ov[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t* __restrict__ Aw = Abits + (int64_t)w * P;
+  uint32_t c[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int t = 0; t < GR_NPAIR; ++t) {
+    const int64_t i = ((int64_t)blockIdx.x * GR_NPAIR + t) * 256 + threadIdx.x;
+    uint32_t x = 0u;
+    if (i < PB) {
+      const int p = (int)(i % P);
+      const int q = __ldg(bg + i) - base;
+      if (q >= 0 && q < P) x = __ldg(Aw + p) & __ldg(Aw + q);
+    }
+#pragma unroll
+    for (int pl = 0; pl < 7; ++pl) {           // ripple-carry add of the one-bit vector x
+      const uint32_t carry = c[pl] & x;
+      c[pl] ^= x;
+      x = carry;
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int pl = 0; pl < 7; ++pl) v |= ((c[pl] >> b) & 1u) << pl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(s_ov + b, v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int k = w * 32 + threadIdx.x;
+    if (k < K && s_ov[threadIdx.x]) atomicAdd(ov_total + k, (unsigned long long)s_ov[threadIdx.x]);
+  }
+}
+
+// E2[p][0] = e[p], E2[p][j] = e[bg[p, j]]
+__global__ void __launch_bounds__(256)
+k_e2_build(const int32_t* __restrict__ bg, int base, int P, int B, const double* __restrict__ e,
+           double* __restrict__ E2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = B + 1;
+  if (i >= (int64_t)P * I) return;
+  const int j = (int)(i / P);
+  const int p = (int)(i - (int64_t)j * P);
+  double v;
+  if (j == 0) v = e[p];
+  else {
+    const int q = bg[(int64_t)(j - 1) * P + p] - base;
+    v = (q >= 0 && q < P) ? __ldg(e + q) : 0.0;
+  }
+  E2[(int64_t)p * I + j] = v;
+}
+
+// etab[k][j] = sum_{p in set_k} E2[p][j] in a fixed order (warps stride over the list, lanes own
+// iterations, warps are merged in order); matches, overlap from the counts of the gather kernel
+__global__ void __launch_bounds__(256)
+k_etab_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx,
+            const int32_t* __restrict__ order, const double* __restrict__ E2, int K, int P, int B,
+            const unsigned long long* __restrict__ ov_total, double* __restrict__ etab,
+            double* __restrict__ overlap, double* __restrict__ matches, uint32_t* __restrict__ work_ctr) {
+  extern __shared__ double s_part[];               // [8][I]
+  __shared__ int s_item;
+  const int I = B + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = (int)atomicAdd(work_ctr, 1u);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= K) break;
+    const int k = order[item];
+    const int64_t beg = annoptr[k], end = annoptr[k + 1];
+    for (int j0 = 0; j0 < I; j0 += 32) {
+      const int j = j0 + lane;
+      if (j < I) {
+        // 8 independent (list entry -> E2 row) chains per lane, summed in list order
+        double acc = 0.0;
+        for (int64_t idx = beg + warp; idx < end; idx += 64) {
+          int pp[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pp[u] = (idx + 8 * u < end) ? __ldg(annoidx + idx + 8 * u) : -1;
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = pp[u] >= 0 ? __ldg(E2 + (int64_t)pp[u] * I + j) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        s_part[warp * I + j] = acc;
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < I; j += blockDim.x) {
+      double s = 0.0;
+      for (int wv = 0; wv < 8; ++wv) s += s_part[wv * I + j];
+      etab[(int64_t)k * I + j] = s;
+    }
+    if (threadIdx.x == 0) {
+      const double cnt = (double)(end - beg);
+      matches[k] = cnt / (double)P;
+      overlap[k] = (end > beg) ? ((double)ov_total[k] / (double)B) / cnt : cv_na_real();
+    }
+    __syncthreads();
+  }
+}
+
 // Host: operand M + per-annotation tables + the multiplicity counters (dflags[1]: largest
-// #{p : bg[p, j] = q}; dflags[2]: largest multiplicity inside one list, 0xFFFF when a byte wrapped).
-// Asynchronous; cv_dense_check reads the counters after the caller's stream sync.
-int cv_dense_build_rows(cv_handle* h, const DensePlan& pl) {
+// #{p : bg[p, j] = q}; dflags[2]: largest multiplicity inside one list, 0xFFFF when a byte wrapped;
+// dflags[3]: a list repeats a peak -> the gather formulation does not apply, rebuild with scatter = 1).
+// Asynchronous; the caller reads the counters after its stream sync.
+int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   const int64_t P = h->P, K = h->K;
   const int B = h->B, I = B + 1, G = pl.G;
   const int64_t Ppad = pl.Ppad;
@@ -261,20 +483,51 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl) {
   CV_LAUNCH(h, k_bg_mult_count_cm, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(),
             h->index_base, P * B, (int)P, h->tmp1.as<uint32_t>(), dflags);
   CV_LAUNCH(h, k_u32_max_db, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, dflags + 1);
-  const int budget = h->max_smem_optin - 2048;
-  const int chunk2 = (int)std::min<int64_t>(Ppad, ((budget / 2) / 128) * 128);   // two row chunks resident
   CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
   // rows of a group that no (annotation, iteration) owns must be zero
   if (G * I < DB_BLOCK_N || K % G)
     CV_LAUNCH(h, k_zero_pad_rows, pl.n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, Ppad);
-  CV_CUDA(h, cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * chunk2));
-  CV_LAUNCH(h, k_dense_rows, (unsigned)std::min<int64_t>(K, h->num_sms), DB_THREADS, (size_t)2 * chunk2,
-            h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
-            h->expect.as<double>(), h->order.as<int32_t>(), (int)K, (int)P, B, G, Ppad, chunk2,
-            h->dn_M.as<uint8_t>(), h->etab.as<double>(), h->overlap.as<double>(), h->matches.as<double>(),
-            h->work_ctr.as<uint32_t>(), dflags);
-  CV_LAUNCH(h, k_row0_max, (unsigned)K, 256, 0, h->dn_M.as<uint8_t>(), h->annoptr.as<int64_t>(), (int)K, G, I, Ppad,
-            dflags + 2);
+  if (scatter || h->opt_rows_scatter) {
+    const int budget = h->max_smem_optin - 2048;
+    const int chunk2 = (int)std::min<int64_t>(Ppad, ((budget / 2) / 128) * 128);   // two row chunks resident
+    CV_CUDA(h, cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * chunk2));
+    CV_LAUNCH(h, k_dense_rows, (unsigned)std::min<int64_t>(K, h->num_sms), DB_THREADS, (size_t)2 * chunk2,
+              h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
+              h->expect.as<double>(), h->order.as<int32_t>(), (int)K, (int)P, B, G, Ppad, chunk2,
+              h->dn_M.as<uint8_t>(), h->etab.as<double>(), h->overlap.as<double>(), h->matches.as<double>(),
+              h->work_ctr.as<uint32_t>(), dflags);
+    CV_LAUNCH(h, k_row0_max, (unsigned)K, 256, 0, h->dn_M.as<uint8_t>(), h->annoptr.as<int64_t>(), (int)K, G, I, Ppad,
+              dflags + 2);
+    return CV_OK;
+  }
+  const int64_t Kw = (K + 31) / 32;
+  CV_TRY(cv_ensure(h, h->dn_abits, (size_t)Kw * P * 4));
+  CV_TRY(cv_ensure(h, h->dn_invptr, (size_t)(P * B + 1) * 4));
+  CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)P * B * 4));
+  CV_TRY(cv_ensure(h, h->dn_E2, (size_t)P * I * 8));
+  CV_TRY(cv_ensure(h, h->dn_ov, (size_t)K * 8));
+  CV_CUDA(h, cudaMemsetAsync(h->dn_abits.p, 0, (size_t)Kw * P * 4, h->stream));
+  CV_CUDA(h, cudaMemsetAsync(h->dn_ov.p, 0, (size_t)K * 8, h->stream));
+  CV_LAUNCH(h, k_anno_bits, (unsigned)K, 256, 0, h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), (int)K, (int)P,
+            h->dn_abits.as<uint32_t>(), dflags);
+  // inverse background map: counting sort of (iteration, destination peak)
+  CV_TRY(cv_exclusive_scan_u32_async(h, h->tmp1.as<uint32_t>(), h->dn_invptr.as<uint32_t>(), P * B));
+  CV_LAUNCH(h, k_inv_fill, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(), h->index_base, P * B,
+            (int)P, h->dn_invptr.as<uint32_t>(), h->tmp1.as<uint32_t>(), h->dn_invsrc.as<int32_t>());
+  {
+    dim3 grid((unsigned)((Ppad + GR_TQ - 1) / GR_TQ), (unsigned)I, (unsigned)Kw);
+    CV_LAUNCH(h, k_dense_rows_gather, grid, GR_THREADS, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
+              h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, G, Ppad, h->dn_M.as<uint8_t>());
+    dim3 grid2((unsigned)((P * B + (int64_t)GR_NPAIR * 256 - 1) / ((int64_t)GR_NPAIR * 256)), (unsigned)Kw);
+    CV_LAUNCH(h, k_overlap_bits, grid2, 256, 0, h->dn_abits.as<uint32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
+              P * B, (int)P, (int)K, h->dn_ov.as<unsigned long long>());
+  }
+  CV_LAUNCH(h, k_e2_build, (unsigned)((P * I + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(), h->index_base, (int)P, B,
+            h->expect.as<double>(), h->dn_E2.as<double>());
+  CV_LAUNCH(h, k_etab_rows, (unsigned)std::min<int64_t>(K, (int64_t)h->num_sms * 4), 256, (size_t)8 * I * 8,
+            h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->order.as<int32_t>(), h->dn_E2.as<double>(), (int)K,
+            (int)P, B, h->dn_ov.as<unsigned long long>(), h->etab.as<double>(), h->overlap.as<double>(),
+            h->matches.as<double>(), h->work_ctr.as<uint32_t>());
   return CV_OK;
 }
 

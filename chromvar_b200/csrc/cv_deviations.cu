@@ -614,7 +614,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     CV_CUDA(h, cudaEventRecord(ev_t0, h->stream));         // origin of the timeline; orders the upload stream
     auto lo = [&](int i) { return (int64_t)i * chunk; };
     auto hi = [&](int i) { return std::min<int64_t>(N, (int64_t)(i + 1) * chunk); };
-    CV_TRY(cv_dense_prepare(h, pl));                          // operand M + tables: cell independent
+    CV_TRY(cv_dense_prepare(h, pl, 0));                       // operand M + tables: cell independent
     if (trace) cudaEventRecord(ev_prep, h->stream);
     if (streaming) {
       if (n_chunks > CV_PINNED_WORDS / 4) CV_FAIL(h, CV_ERR_UNSUPPORTED, "too many cell chunks (%d)", n_chunks);
@@ -629,6 +629,13 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     CV_CUDA(h, cudaStreamSynchronize(h->stream));
     if (hf[CV_DFLAGS] & FLAG_BADIDX)
       CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
+    if (hf[CV_DFLAGS + 3]) {
+      // a list repeats a peak: bit columns cannot hold the multiplicity, rebuild the rows by scatter
+      CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));
+      CV_TRY(cv_dense_prepare(h, pl, 1));
+      CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
+      CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     int soft = 0;
     int rc = cv_dense_check(h, pl, hf, streaming ? 0 : 1, &soft);
     if (rc != CV_OK) {

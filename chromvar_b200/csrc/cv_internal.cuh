@@ -133,6 +133,12 @@ struct cv_handle {
   DevBuf dn_M;       // u8 [n_groups*256][Ppad] stacked annotation x iteration operand
   DevBuf dn_C;       // u8 [chunk cells][Ppad] densified counts of the current cell chunk / digit plane
   DevBuf dn_S;       // int64 [K][B+1][chunk cells] exact sums when counts need several u8 planes
+  DevBuf dn_abits;   // u32 [ceil(K/32)][P] annotation membership bits
+  DevBuf dn_invptr;  // u32 [B*P + 1] inverse background map: sources of (iteration, peak)
+  DevBuf dn_invsrc;  // i32 [B*P]
+  DevBuf dn_E2;      // f64 [P][B+1] e[p], e[bg[p, j]]
+  DevBuf dn_ov;      // u64 [K] background overlap counts
+  int opt_rows_scatter = 0;   // build the operand rows with the per-annotation scatter kernel only
   double dn_flops = 0;
   int opt_path = 0;  // 0 auto, 1 force row-gather SpMM, 2 force dense tcgen05
   int opt_pair = 1;  // dense path: CTA-pair kernel (tcgen05 cta_group::2) vs single-CTA kernel
@@ -180,12 +186,13 @@ struct DensePlan {
 };
 int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan* pl, std::string* why);
 double cv_dense_cost_ms(cv_handle* h, const DensePlan& pl);
-int cv_dense_prepare(cv_handle* h, const DensePlan& pl);
+int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows);
 int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, int keep_sums);
 int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, int with_counts, int* soft_fail);
 // cv_dense_build.cu
-int cv_dense_build_rows(cv_handle* h, const DensePlan& pl);
+int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter);
 int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift);
+int cv_exclusive_scan_u32_async(cv_handle* h, const uint32_t* in, uint32_t* out, int64_t n);
 // cv_counts.cu: K1 in pieces so the streamed call can run it per uploaded cell chunk
 int cv_counts_begin(cv_handle* h);
 int cv_counts_range(cv_handle* h, int x_type, int64_t e0, int64_t e1, int64_t c0, int64_t c1);

@@ -211,10 +211,21 @@ def test_dense_cell_chunks_and_kernels_agree_bitwise(engine):
                 assert st["n_cell_tiles"] == -(-N // (-(-chunk // 256) * 256))
             for key in ("observed", "sampled", "dev", "z", "variability", "matches", "overlap"):
                 assert np.array_equal(got[key], base[key], equal_nan=True), (pair, chunk, key)
+        # operand rows built by the per-annotation scatter kernel instead of the gather kernel:
+        # identical operand (identical integer sums); the expected-fraction table is summed in a
+        # different order, so dev / z agree to rounding
+        engine.set_option("dense_rows_scatter", 1)
+        got = engine.deviations(ptr, idx, bg, e, sums=True)
+        for key in ("observed", "sampled", "matches", "overlap"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), key
+        ok = ~np.isnan(base["z"])
+        assert np.array_equal(np.isnan(got["z"]), ~ok)
+        assert np.max(np.abs(got["z"][ok] - base["z"][ok]) / np.maximum(np.abs(base["z"][ok]), 1e-3)) < 1e-9
     finally:
         engine.set_option("path", 0)
         engine.set_option("dense_cta_pair", 1)
         engine.set_option("cell_chunk", 0)
+        engine.set_option("dense_rows_scatter", 0)
 
 
 def test_streamed_call_equals_resident_call(engine):
