@@ -74,6 +74,9 @@ def make_counts(P, N, density, rng, annoptr=None, annoidx=None, n_types=5, plant
         owner = np.repeat(np.arange(cells.size, dtype=np.int64), depth[cells])
         key = owner * P + draws
         uniq, cnt = np.unique(key, return_counts=True)
+        # single-cell counts stay <= 127 (bundled data: max 8); the log-normal tails of
+        # depth x accessibility would otherwise put a handful of entries in the hundreds
+        np.minimum(cnt, 127, out=cnt)
         o = uniq // P
         r = (uniq - o * P).astype(np.int32)
         bounds = np.searchsorted(o, np.arange(cells.size + 1))
