@@ -395,6 +395,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
                 "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
+                "gemm_kernel": "k_dense_contract_pair" if e2e_stats["cell_tile"] == 256 else
+                ("k_dense_contract" if e2e_stats["path"] == 1 else "k_contract"),
                 "cell_chunks": int(e2e_stats["n_cell_tiles"]), "ms_each_step": [round(t, 2) for t in e2e_each],
                 "device_ms": {k: round(float(e2e_stats[k]), 3) for k in
                               ("ms_counts_layout", "ms_anno_prep", "ms_contract", "ms_finalize")}},
@@ -426,7 +428,7 @@ def main():
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
     ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
-    ap.add_argument("--pair", type=int, default=1, help="dense path: 1 CTA-pair kernel (cta_group::2), 0 single-CTA kernel")
+    ap.add_argument("--pair", type=int, default=-1, help="dense GEMM kernel: 1 CTA pair (cta_group::2), 0 single CTA, -1 library default (by context)")
     args = ap.parse_args()
     if args.warmup < 3 and not args.quick and args.impl == "ours":
         log("[bench] warning: fewer than 3 warm-up steps")

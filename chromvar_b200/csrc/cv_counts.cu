@@ -149,7 +149,7 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
     h->opt_path = (int)value;
     return CV_OK;
   }
-  if (!strcmp(key, "dense_cta_pair")) { h->opt_pair = value != 0; return CV_OK; }
+  if (!strcmp(key, "dense_cta_pair")) { h->opt_pair = value < 0 ? -1 : (value != 0); return CV_OK; }
   if (!strcmp(key, "cell_chunk")) {
     if (value < 0) CV_FAIL(h, CV_ERR_INVALID, "cell_chunk must be >= 0");
     h->opt_chunk = value;

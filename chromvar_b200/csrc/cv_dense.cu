@@ -737,7 +737,9 @@ int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan*
   pl->rowsM = (int64_t)pl->n_groups * DN_BLOCK_N;
   pl->planes = 1;
   for (uint32_t v = max_val >> 8; v; v >>= 8) pl->planes++;
-  pl->pair = h->opt_pair ? 1 : 0;
+  // alone on the GPU the single-CTA kernel is ~4 % faster; beside host copies and the next chunk's
+  // K1 (streamed calls: want_chunk > 0) the CTA pair loses less (profiles/r01f)
+  pl->pair = h->opt_pair < 0 ? (want_chunk > 0 ? 1 : 0) : (h->opt_pair ? 1 : 0);
   pl->m_bytes = pl->rowsM * pl->Ppad;
   // per cell: one u8 row of the operand (+ the int64 sums scratch when digit planes are combined)
   const double per_cell = (double)pl->Ppad + (pl->planes > 1 ? (double)h->K * I * 8.0 : 0.0);

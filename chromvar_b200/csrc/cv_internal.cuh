@@ -141,7 +141,7 @@ struct cv_handle {
   int opt_rows_scatter = 0;   // build the operand rows with the per-annotation scatter kernel only
   double dn_flops = 0;
   int opt_path = 0;  // 0 auto, 1 force row-gather SpMM, 2 force dense tcgen05
-  int opt_pair = 1;  // dense path: CTA-pair kernel (tcgen05 cta_group::2) vs single-CTA kernel
+  int opt_pair = -1; // dense GEMM kernel: 1 CTA pair (tcgen05 cta_group::2), 0 single CTA, -1 by context
   int64_t opt_chunk = 0;       // dense path: cap on cells per GEMM launch (0 = memory budget)
   int opt_band = 0;            // dense path: groups per raster band (0 = default)
   int opt_debug_no_tma = 0;    // experiment only: GEMM without operand loads (garbage results)

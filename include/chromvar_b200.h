@@ -60,7 +60,10 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
 /* options:
  *   "path"             0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05 (fails if the problem
  *                      cannot be represented exactly in u8 operands / s32 accumulators)
- *   "dense_cta_pair"   1 (default) tcgen05 cta_group::2 kernel, 0 single-CTA kernel
+ *   "dense_cta_pair"   GEMM kernel: 1 tcgen05 cta_group::2 (256-cell tiles on two SMs), 0 single CTA
+ *                      (128-cell tiles), -1 (default) by context: the pair when host copies run
+ *                      beside the GEMM (cv_deviations, cv_deviations_csc), single CTA otherwise
+ *   "dense_rows_scatter" 1 builds the operand rows with the per-annotation scatter kernel only
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
  *                      0 for a shard of a larger matrix (the caller checks the reduced totals) */

@@ -49,7 +49,6 @@ get_background_peaks_core <- function(object, bias, niterations = 50, w = 0.1, b
 
 compute_deviations_core <- function(counts_mat, peak_indices, background_peaks, expectation,
                                     rowData = NULL, colData = NULL) {
-  .cvb_load_counts(counts_mat)
   stopifnot(nrow(counts_mat) == nrow(background_peaks))
   stopifnot(length(expectation) == nrow(counts_mat))
   if (is.null(colData))
@@ -60,8 +59,18 @@ compute_deviations_core <- function(counts_mat, peak_indices, background_peaks, 
   if (is.null(names(peak_indices))) names(peak_indices) <- seq_along(peak_indices)
   annoptr <- c(0, cumsum(lengths(peak_indices)))
   storage.mode(background_peaks) <- "integer"
-  res <- .Call("cvb_deviations", as.numeric(annoptr), as.integer(tmp), background_peaks,
-               as.numeric(expectation), ncol(counts_mat), PACKAGE = "chromVARb200")
+  fresh <- is.null(.cvb$counts) || !identical(.cvb$counts, counts_mat)
+  if (fresh && is(counts_mat, "dgCMatrix")) {
+    # counts not on the GPU yet: one call, H2D of the counts / kernels / D2H of the results overlap
+    res <- .Call("cvb_deviations_csc", counts_mat@p, counts_mat@i, counts_mat@x, counts_mat@Dim,
+                 as.numeric(annoptr), as.integer(tmp), background_peaks, as.numeric(expectation),
+                 PACKAGE = "chromVARb200")
+    .cvb$counts <- counts_mat
+  } else {
+    .cvb_load_counts(counts_mat)
+    res <- .Call("cvb_deviations", as.numeric(annoptr), as.integer(tmp), background_peaks,
+                 as.numeric(expectation), ncol(counts_mat), PACKAGE = "chromVARb200")
+  }
   dev <- res[[1]]; z <- res[[2]]
   rownames(z) <- rownames(dev) <- names(peak_indices)
   colnames(z) <- colnames(dev) <- colnames(counts_mat)

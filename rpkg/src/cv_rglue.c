@@ -108,6 +108,33 @@ SEXP cvb_deviations(SEXP annoptr, SEXP annoidx, SEXP bg, SEXP expectation, SEXP 
   return out;
 }
 
+/* compute_deviations_core in ONE library call on R's own buffers: dgCMatrix slots of the counts
+ * plus everything cvb_deviations takes.  The library streams the counts to the GPU in cell chunks
+ * while earlier chunks are in the GEMM and streams finished chunks of deviations / z back; the
+ * counts stay resident afterwards (later cvb_expectations / cvb_background_peaks calls reuse them).
+ * expectation may be NULL: computeExpectations' default (R/compute_deviations.R:357-359). */
+SEXP cvb_deviations_csc(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP annoptr, SEXP annoidx, SEXP bg,
+                        SEXP expectation) {
+  int64_t K = (int64_t) XLENGTH(annoptr) - 1;
+  int P = INTEGER(dim)[0], n = INTEGER(dim)[1];
+  int64_t *ptr = (int64_t *) R_alloc(K + 1, sizeof(int64_t));
+  for (int64_t k = 0; k <= K; ++k) ptr[k] = (int64_t) REAL(annoptr)[k];
+  SEXP bdim = Rf_getAttrib(bg, R_DimSymbol);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
+  SEXP dev = PROTECT(Rf_allocMatrix(REALSXP, (int) K, n));
+  SEXP z = PROTECT(Rf_allocMatrix(REALSXP, (int) K, n));
+  SEXP m = PROTECT(Rf_allocVector(REALSXP, K));
+  SEXP o = PROTECT(Rf_allocVector(REALSXP, K));
+  SEXP v = PROTECT(Rf_allocVector(REALSXP, K));
+  check(cv_deviations_csc(H, P, n, INTEGER(p), CV_I32, INTEGER(i), REAL(x), CV_F64, K, ptr, INTEGER(annoidx), 1,
+                          INTEGER(bg), INTEGER(bdim)[1], Rf_isNull(expectation) ? NULL : REAL(expectation),
+                          REAL(dev), REAL(z), REAL(m), REAL(o), REAL(v)));
+  SET_VECTOR_ELT(out, 0, dev); SET_VECTOR_ELT(out, 1, z); SET_VECTOR_ELT(out, 2, m);
+  SET_VECTOR_ELT(out, 3, o); SET_VECTOR_ELT(out, 4, v);
+  UNPROTECT(6);
+  return out;
+}
+
 /* row_sds / row_sds_perm (src/utils.cpp:9-33) */
 SEXP cvb_row_sds(SEXP x, SEXP na_rm) {
   SEXP dim = Rf_getAttrib(x, R_DimSymbol);
@@ -138,6 +165,7 @@ static const R_CallMethodDef CallEntries[] = {
   {"cvb_expectations", (DL_FUNC) &cvb_expectations, 4},
   {"cvb_background_peaks", (DL_FUNC) &cvb_background_peaks, 4},
   {"cvb_deviations", (DL_FUNC) &cvb_deviations, 5},
+  {"cvb_deviations_csc", (DL_FUNC) &cvb_deviations_csc, 8},
   {"cvb_row_sds", (DL_FUNC) &cvb_row_sds, 2},
   {"cvb_row_sds_perm", (DL_FUNC) &cvb_row_sds_perm, 3},
   {NULL, NULL, 0}

@@ -25,7 +25,7 @@ def dense_engine(engine, request):
     engine.set_option("dense_cta_pair", 1 if request.param == "cta_pair" else 0)
     yield engine
     engine.set_option("path", 0)
-    engine.set_option("dense_cta_pair", 1)
+    engine.set_option("dense_cta_pair", -1)
     engine.set_option("cell_chunk", 0)
 
 
@@ -200,7 +200,7 @@ def test_dense_cell_chunks_and_kernels_agree_bitwise(engine):
     engine.set_option("path", 2)
     try:
         base = engine.deviations(ptr, idx, bg, e, sums=True)
-        assert engine.stats()["cell_tile"] == 256
+        assert engine.stats()["cell_tile"] == 256          # host copies beside the GEMM: CTA pair by default
         for pair, chunk in ((1, 256), (1, 768), (0, 0), (0, 640)):
             engine.set_option("dense_cta_pair", pair)
             engine.set_option("cell_chunk", chunk)
@@ -223,7 +223,7 @@ def test_dense_cell_chunks_and_kernels_agree_bitwise(engine):
         assert np.max(np.abs(got["z"][ok] - base["z"][ok]) / np.maximum(np.abs(base["z"][ok]), 1e-3)) < 1e-9
     finally:
         engine.set_option("path", 0)
-        engine.set_option("dense_cta_pair", 1)
+        engine.set_option("dense_cta_pair", -1)
         engine.set_option("cell_chunk", 0)
         engine.set_option("dense_rows_scatter", 0)
 
