@@ -327,12 +327,13 @@ def run_ours(args):
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 10))
-    e2e_each = []
+    n_e2e = max(1, min(args.steps, 10)) if not args.e2e_steps else args.e2e_steps
+    e2e_each, e2e_lib = [], []
     for _ in range(n_e2e):
         t1 = time.perf_counter()
         e2e_step()
         e2e_each.append(1e3 * (time.perf_counter() - t1))
+        e2e_lib.append(eng.stats()["ms_h2d"])          # wall clock inside cv_deviations_csc
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_stats = eng.stats()
@@ -398,6 +399,7 @@ def run_ours(args):
                 "gemm_kernel": "k_dense_contract_pair" if e2e_stats["cell_tile"] == 256 else
                 ("k_dense_contract" if e2e_stats["path"] == 1 else "k_contract"),
                 "cell_chunks": int(e2e_stats["n_cell_tiles"]), "ms_each_step": [round(t, 2) for t in e2e_each],
+                "ms_inside_library": [round(t, 2) for t in e2e_lib],
                 "device_ms": {k: round(float(e2e_stats[k]), 3) for k in
                               ("ms_counts_layout", "ms_anno_prep", "ms_contract", "ms_finalize")}},
         "gpu_launches": int(launches),
@@ -423,6 +425,7 @@ def main():
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (default: config 2's 10000)")
     ap.add_argument("--workload", default=None, help="synthetic configuration (default cfg2_scatac_motifs; "
                     "cfg3_kmers, cfg4_bulk, cfg5_atlas_shard are parity / scale cases, not the bench line)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="number of timed e2e steps (default min(steps, 10))")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")

@@ -286,9 +286,19 @@ def compute_deviations_core(counts_mat, annoptr, annoidx, background_peaks, expe
         background_peaks = bgf.astype(np.int32)
         if not np.array_equal(background_peaks, bgf):
             raise ValueError("background_peaks must hold integer peak indices")
-    eng = _load_counts(counts_mat)
     try:
-        res = eng.deviations(annoptr, annoidx.astype(np.int32), background_peaks, expectation, index_base=1)
+        eng = get_engine()
+        resident = _CountsCache.obj is counts_mat and eng.P == P and eng.N == N
+        if not resident and sp.isspmatrix_csc(counts_mat):
+            # counts not on the GPU yet: ONE library call, the H2D of the counts, the kernels and the
+            # D2H of the results overlap (cv_deviations_csc); the counts are resident afterwards
+            invalidate_counts_cache()
+            res = eng.deviations_csc(P, N, counts_mat.indptr, counts_mat.indices, counts_mat.data, annoptr,
+                                     annoidx.astype(np.int32), background_peaks, expectation, index_base=1)
+            _CountsCache.obj = counts_mat
+        else:
+            eng = _load_counts(counts_mat)
+            res = eng.deviations(annoptr, annoidx.astype(np.int32), background_peaks, expectation, index_base=1)
     except ChromVARError as e:
         if e.code == _lib.CV_ERR_INVALID:
             raise ValueError(str(e)) from e

@@ -93,12 +93,14 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
     return CV_ERR_CUDA;
   }
   if (cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking) != cudaSuccess) {
     g_create_err = "cudaStreamCreate failed";
     delete h;
     return CV_ERR_CUDA;
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev_aux[i], cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&h->pinned, CV_PINNED_WORDS * 4, cudaHostAllocDefault) != cudaSuccess) {
     g_create_err = "cudaHostAlloc failed";
     cudaGetLastError();
@@ -125,9 +127,12 @@ extern "C" void cv_destroy(cv_handle* h) {
   for (int i = 0; i < 8; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev_aux[i]) cudaEventDestroy(h->ev_aux[i]);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->s_up) cudaStreamDestroy(h->s_up);
   if (h->s_dn) cudaStreamDestroy(h->s_dn);
+  if (h->s_aux) cudaStreamDestroy(h->s_aux);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -423,8 +423,7 @@ k_e2_build(const int32_t* __restrict__ bg, int base, int P, int B, const double*
 __global__ void __launch_bounds__(256)
 k_etab_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx,
             const int32_t* __restrict__ order, const double* __restrict__ E2, int K, int P, int B,
-            const unsigned long long* __restrict__ ov_total, double* __restrict__ etab,
-            double* __restrict__ overlap, double* __restrict__ matches, uint32_t* __restrict__ work_ctr) {
+            double* __restrict__ etab, uint32_t* __restrict__ work_ctr) {
   extern __shared__ double s_part[];               // [8][I]
   __shared__ int s_item;
   const int I = B + 1;
@@ -460,13 +459,18 @@ k_etab_rows(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ ann
       for (int wv = 0; wv < 8; ++wv) s += s_part[wv * I + j];
       etab[(int64_t)k * I + j] = s;
     }
-    if (threadIdx.x == 0) {
-      const double cnt = (double)(end - beg);
-      matches[k] = cnt / (double)P;
-      overlap[k] = (end > beg) ? ((double)ov_total[k] / (double)B) / cnt : cv_na_real();
-    }
     __syncthreads();
   }
+}
+
+// fractionMatches (:533) and fractionBackgroundOverlap (:506, :530-534) from the overlap counts
+__global__ void k_overlap_finish(const int64_t* __restrict__ annoptr, const unsigned long long* __restrict__ ov_total,
+                                 int K, int P, int B, double* __restrict__ overlap, double* __restrict__ matches) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const double cnt = (double)(annoptr[k + 1] - annoptr[k]);
+  matches[k] = cnt / (double)P;
+  overlap[k] = cnt > 0.0 ? ((double)ov_total[k] / (double)B) / cnt : cv_na_real();
 }
 
 // Host: operand M + per-annotation tables + the multiplicity counters (dflags[1]: largest
@@ -506,10 +510,15 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)P * B * 4));
   CV_TRY(cv_ensure(h, h->dn_E2, (size_t)P * I * 8));
   CV_TRY(cv_ensure(h, h->dn_ov, (size_t)K * 8));
-  CV_CUDA(h, cudaMemsetAsync(h->dn_abits.p, 0, (size_t)Kw * P * 4, h->stream));
-  CV_CUDA(h, cudaMemsetAsync(h->dn_ov.p, 0, (size_t)K * 8, h->stream));
+  // Two streams: the operand rows (write-bound) on the compute stream; the expected-fraction table
+  // (L2-read-bound) and the overlap counts beside them on the auxiliary stream.  The GEMM waits for
+  // the table (ev[6]); the overlap / matches vectors are only joined at the end of the call (ev[7]).
+  cudaStream_t compute = h->stream;
+  CV_CUDA(h, cudaEventRecord(h->ev_aux[0], compute));                    // inputs are on the device
+  CV_CUDA(h, cudaMemsetAsync(h->dn_abits.p, 0, (size_t)Kw * P * 4, compute));
   CV_LAUNCH(h, k_anno_bits, (unsigned)K, 256, 0, h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), (int)K, (int)P,
             h->dn_abits.as<uint32_t>(), dflags);
+  CV_CUDA(h, cudaEventRecord(h->ev_aux[1], compute));                    // bit columns ready
   // inverse background map: counting sort of (iteration, destination peak)
   CV_TRY(cv_exclusive_scan_u32_async(h, h->tmp1.as<uint32_t>(), h->dn_invptr.as<uint32_t>(), P * B));
   CV_LAUNCH(h, k_inv_fill, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(), h->index_base, P * B,
@@ -518,16 +527,35 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
     dim3 grid((unsigned)((Ppad + GR_TQ - 1) / GR_TQ), (unsigned)I, (unsigned)Kw);
     CV_LAUNCH(h, k_dense_rows_gather, grid, GR_THREADS, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
               h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, G, Ppad, h->dn_M.as<uint8_t>());
-    dim3 grid2((unsigned)((P * B + (int64_t)GR_NPAIR * 256 - 1) / ((int64_t)GR_NPAIR * 256)), (unsigned)Kw);
-    CV_LAUNCH(h, k_overlap_bits, grid2, 256, 0, h->dn_abits.as<uint32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
-              P * B, (int)P, (int)K, h->dn_ov.as<unsigned long long>());
   }
-  CV_LAUNCH(h, k_e2_build, (unsigned)((P * I + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(), h->index_base, (int)P, B,
-            h->expect.as<double>(), h->dn_E2.as<double>());
-  CV_LAUNCH(h, k_etab_rows, (unsigned)std::min<int64_t>(K, (int64_t)h->num_sms * 4), 256, (size_t)8 * I * 8,
-            h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->order.as<int32_t>(), h->dn_E2.as<double>(), (int)K,
-            (int)P, B, h->dn_ov.as<unsigned long long>(), h->etab.as<double>(), h->overlap.as<double>(),
-            h->matches.as<double>(), h->work_ctr.as<uint32_t>());
+  // ---- auxiliary stream ----
+  h->stream = h->s_aux;
+  int rc = CV_OK;
+  do {
+    if (cudaStreamWaitEvent(h->s_aux, h->ev_aux[0], 0) != cudaSuccess) { rc = CV_ERR_CUDA; break; }
+    if (cudaMemsetAsync(h->work_ctr.as<uint32_t>() + 4, 0, 4, h->s_aux) != cudaSuccess) { rc = CV_ERR_CUDA; break; }
+    k_e2_build<<<(unsigned)((P * I + 255) / 256), 256, 0, h->s_aux>>>(h->bg_raw.as<int32_t>(), h->index_base, (int)P, B,
+                                                                      h->expect.as<double>(), h->dn_E2.as<double>());
+    k_etab_rows<<<(unsigned)std::min<int64_t>(K, (int64_t)h->num_sms * 4), 256, (size_t)8 * I * 8, h->s_aux>>>(
+        h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->order.as<int32_t>(), h->dn_E2.as<double>(), (int)K,
+        (int)P, B, h->etab.as<double>(), h->work_ctr.as<uint32_t>() + 4);
+    cudaEventRecord(h->ev_aux[2], h->s_aux);                               // expected-fraction table ready
+    cudaStreamWaitEvent(h->s_aux, h->ev_aux[1], 0);
+    cudaMemsetAsync(h->dn_ov.p, 0, (size_t)K * 8, h->s_aux);
+    dim3 grid2((unsigned)((P * B + (int64_t)GR_NPAIR * 256 - 1) / ((int64_t)GR_NPAIR * 256)), (unsigned)Kw);
+    k_overlap_bits<<<grid2, 256, 0, h->s_aux>>>(h->dn_abits.as<uint32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
+                                                P * B, (int)P, (int)K, h->dn_ov.as<unsigned long long>());
+    k_overlap_finish<<<(unsigned)((K + 127) / 128), 128, 0, h->s_aux>>>(h->annoptr.as<int64_t>(),
+                                                                        h->dn_ov.as<unsigned long long>(), (int)K, (int)P,
+                                                                        B, h->overlap.as<double>(), h->matches.as<double>());
+    cudaEventRecord(h->ev_aux[3], h->s_aux);                               // overlap / matches ready
+    h->launches += 4;
+    if (cudaGetLastError() != cudaSuccess) rc = CV_ERR_CUDA;
+  } while (0);
+  h->stream = compute;
+  if (rc != CV_OK) CV_FAIL(h, rc, "launch on the auxiliary stream failed");
+  CV_CUDA(h, cudaStreamWaitEvent(compute, h->ev_aux[2], 0));               // the GEMM epilogue reads the table
+  h->aux_pending = true;
   return CV_OK;
 }
 

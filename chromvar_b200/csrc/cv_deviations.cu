@@ -631,6 +631,8 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
     if (hf[CV_DFLAGS + 3]) {
       // a list repeats a peak: bit columns cannot hold the multiplicity, rebuild the rows by scatter
+      CV_CUDA(h, cudaStreamSynchronize(h->s_aux));           // the first attempt's table kernels
+      h->aux_pending = false;
       CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));
       CV_TRY(cv_dense_prepare(h, pl, 1));
       CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
@@ -698,6 +700,10 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     }
   }
   if (!use_dense) {
+    if (h->aux_pending) {                                    // a dense attempt was abandoned
+      CV_CUDA(h, cudaStreamSynchronize(h->s_aux));
+      h->aux_pending = false;
+    }
     wide = (double)set_max * (double)h->max_val >= 2147483647.0;
     const int acc_bytes = wide ? 8 : 4;
     // background matrix -> [P][B] 0-based, expected-fraction table, overlap, matches
@@ -760,6 +766,10 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   }
 
   // ---- stage 3: totals, zero-peak check, variability merge -----------------------------------------
+  if (h->aux_pending) {                                  // overlap / matches from the auxiliary stream
+    CV_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_aux[3], 0));
+    h->aux_pending = false;
+  }
   cv_span_begin(h, CV_SPAN_FINALIZE);
   if (streaming) CV_TRY(cv_counts_finish_async(h));       // every K1 chunk was waited for above
   if (h->opt_check_zero)

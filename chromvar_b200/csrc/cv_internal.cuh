@@ -64,7 +64,10 @@ struct cv_handle {
   cudaStream_t stream = nullptr;      // compute
   cudaStream_t s_up = nullptr;        // host -> device copies of the streamed call
   cudaStream_t s_dn = nullptr;        // device -> host copies overlapping the next chunk
+  cudaStream_t s_aux = nullptr;       // per-annotation tables beside the operand build
+  bool aux_pending = false;           // ev[7] (overlap / matches ready) still has to be joined
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_aux[4] = {};         // operand build: inputs ready, bit columns, table, overlap
   uint32_t* pinned = nullptr;         // CV_PINNED_WORDS of page-locked host memory (flag snapshots)
   // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
   std::vector<cudaEvent_t> ev_pool;
