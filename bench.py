@@ -228,6 +228,8 @@ def run_ours(args):
     eng = _lib.Handle(local, seed=20173)
     eng.set_option("path", args.path)
     eng.set_option("dense_cta_pair", args.pair)
+    if args.chunk:
+        eng.set_option("cell_chunk", args.chunk)
     if args.band:
         eng.set_option("dense_band", args.band)
     if args.debug_no_tma:
@@ -326,6 +328,9 @@ def run_ours(args):
     e2e_step()
     e2e_step()
     barrier()
+    import gc
+    gc.collect()
+    gc.disable()                 # a gen-2 collection of the harness costs ~10 ms when it lands inside a step
     t0 = time.perf_counter()
     n_e2e = max(1, min(args.steps, 10)) if not args.e2e_steps else args.e2e_steps
     e2e_each, e2e_lib = [], []
@@ -336,6 +341,7 @@ def run_ours(args):
         e2e_lib.append(eng.stats()["ms_h2d"])          # wall clock inside cv_deviations_csc
     barrier()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
     e2e_stats = eng.stats()
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if ws > 1:
@@ -386,7 +392,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8 x u8 -> s32 (tcgen05), f64 epilogue" if path == 1 else "int32 sums, f64 epilogue",
+        "dtype": ("u8 x u8 -> s32 (tcgen05), %s epilogue" % ("u64 fixed-point / f32 / f64" if st.get("epilogue") == 32 else "f64"))
+                 if path == 1 else "int32 sums, f64 epilogue",
         "data": "synthetic",
         "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
                    "niterations": NITER, "nnz_per_gpu": nnz, "nnz_annotations": int(d["annoptr"][-1]),
@@ -429,6 +436,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
+    ap.add_argument("--chunk", type=int, default=0, help="dense path: cap on cells per GEMM launch (experiment)")
     ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
     ap.add_argument("--pair", type=int, default=-1, help="dense GEMM kernel: 1 CTA pair (cta_group::2), 0 single CTA, -1 library default (by context)")

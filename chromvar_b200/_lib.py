@@ -40,7 +40,7 @@ class StageStats(C.Structure):
         ("contract_updates", C.c_int64), ("contract_bytes", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64),
         ("path", C.c_int32), ("cell_tile", C.c_int32), ("n_cell_tiles", C.c_int32),
-        ("acc_bytes", C.c_int32), ("planes", C.c_int32), ("reserved", C.c_int32),
+        ("acc_bytes", C.c_int32), ("planes", C.c_int32), ("epilogue", C.c_int32),
     ]
 
     def as_dict(self):
@@ -249,8 +249,11 @@ class Handle:
     def deviations_compute(self, rebuild_counts_layout=False, keep_sums=False):
         self._check(self.lib.cv_deviations_compute(self._h, int(rebuild_counts_layout), int(keep_sums)))
 
-    def deviations_download(self, sums=False, out=None):
+    def deviations_download(self, sums=False, out=None, vectors_only=False):
         K, N, B = self.K, self.N, self.B
+        if vectors_only:
+            out = dict(dev=None, z=None, matches=np.empty(K, np.float64), overlap=np.empty(K, np.float64),
+                       variability=np.empty(K, np.float64))
         if out is None:
             out = dict(dev=np.empty((K, N), np.float64, order="F"),
                        z=np.empty((K, N), np.float64, order="F"),

@@ -95,6 +95,23 @@ def annotationMatches(object):
 # --------------------------------------------------------------------------------------------
 _engine = None
 _device = None
+_seed_rng = None     # set_seed(): the analogue of R's set.seed() for the samplers
+
+
+def set_seed(seed):
+    """Like set.seed() in R: every later getBackgroundPeaks() call draws a fresh sampler seed from
+    this stream (the R shim does the same with sample.int(.Machine$integer.max, 1))."""
+    global _seed_rng
+    _seed_rng = np.random.default_rng(seed)
+
+
+def _next_sampler_seed(force=False):
+    global _seed_rng
+    if _seed_rng is None:
+        if not force:
+            return None
+        _seed_rng = np.random.default_rng()
+    return int(_seed_rng.integers(1, 2 ** 31 - 1))
 
 
 def set_device(device):
@@ -229,6 +246,9 @@ def getBackgroundPeaks(object, bias=None, niterations=50, w=0.1, bs=50):
     if bias.shape[0] != mat.shape[0]:
         raise ValueError("length(bias) == length(fragments_per_peak) is not TRUE")   # :123
     eng = _load_counts(mat)
+    seed = _next_sampler_seed()
+    if seed is not None:
+        eng.set_seed(seed)
     try:
         return eng.background_peaks(bias, int(niterations), float(w), int(bs))
     except ChromVARError as e:

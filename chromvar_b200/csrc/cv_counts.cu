@@ -121,7 +121,7 @@ extern "C" void cv_destroy(cv_handle* h) {
                     &h->etab, &h->overlap, &h->matches, &h->mark, &h->order, &h->work_ctr,
                     &h->dev_rm, &h->z_rm, &h->dev_cm, &h->z_cm, &h->varpart, &h->varfinal,
                     &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C, &h->dn_S,
-                    &h->dn_abits, &h->dn_invptr, &h->dn_invsrc, &h->dn_E2, &h->dn_ov};
+                    &h->dn_abits, &h->dn_invptr, &h->dn_invsrc, &h->dn_E2, &h->dn_ov, &h->dn_winv};
   for (DevBuf* b : bufs) cv_release(*b);
   for (DevBuf& b : h->bk) cv_release(b);
   for (int i = 0; i < 8; ++i)
@@ -161,6 +161,11 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
     return CV_OK;
   }
   if (!strcmp(key, "dense_rows_scatter")) { h->opt_rows_scatter = value != 0; return CV_OK; }
+  if (!strcmp(key, "dense_epilogue")) {
+    if (value < 0 || value > 2) CV_FAIL(h, CV_ERR_INVALID, "dense_epilogue must be 0 (auto), 1 (float pairs) or 2 (fp64)");
+    h->opt_epilogue = (int)value;
+    return CV_OK;
+  }
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }

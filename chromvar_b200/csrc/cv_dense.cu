@@ -78,6 +78,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// waits that are long by design (epilogue warps wait a whole tile for the accumulator, producers
+// wait for a free stage): back off between polls so the polling warps do not burn issue slots and
+// power next to the tensor pipe
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -189,7 +207,14 @@ __device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, u
 }
 
 // ---- the GEMM + fused epilogue -----------------------------------------------------------------------
-enum { DN_EPI_FUSED = 0, DN_EPI_SUMS = 1 };
+// epilogue arithmetic: FUSED = fp64 throughout; FUSED32 = per-iteration statistics without fp64:
+// the mean over iterations in exact 64-bit fixed point (sum_j s_j * W_j, W_j = 1 / E_j scaled to 32
+// bits), the variance in fp32 of the exact integer differences; fp64 only once per annotation;
+// SUMS = raw integer sums (digit planes).
+// FP64 instructions issue ~25x slower while the tensor pipe is busy (stall_math_pipe_throttle; the
+// same code runs at 37 TFLOP/s alone, tools/fp64_probe.cu), so the fp64 epilogue of a tile takes
+// ~265 us -- hidden behind the next tile's MMAs only when a tile has >= ~1000 k-blocks.
+enum { DN_EPI_FUSED = 0, DN_EPI_SUMS = 1, DN_EPI_FUSED32 = 2 };
 
 struct DenseParams {
   int N, K, B, G;            // cells (whole shard), annotations, iterations, annotations per 256-row group
@@ -212,6 +237,8 @@ struct DenseParams {
   long long* sums;
   int sums_ld, sums_c0, sums_shift, sums_acc;
   int debug_no_tma;          // experiment: the producer only signals the barrier (results are garbage)
+  const uint32_t* winv_fx;   // [K][B+1] W[k][j] = round(2^F_k / E[k][j]) < 2^32 (DN_EPI_FUSED32)
+  const double* wscale;      // [K] 2^-F_k
 };
 
 struct DWelford { double n, mean, m2; };
@@ -236,6 +263,38 @@ __device__ __forceinline__ void dw_warp_reduce(DWelford& wf, double& nonfinite, 
     b.m2 = __shfl_xor_sync(full, wf.m2, o);
     wf = (lane & o) ? dw_merge(b, wf) : dw_merge(wf, b);
     nonfinite += __shfl_xor_sync(full, nonfinite, o);
+  }
+}
+
+// (n, mean, M2, #non-finite) of the z values of one warp's 32 cells: sums shifted by the first finite
+// value (xor-shuffle trees: every lane ends with the same bits), converted once.  Non-live lanes
+// (padding cells) do not count.
+__device__ __forceinline__ void dn_warp_variability(double zv, bool live, int lane, double* w4) {
+  const unsigned full = 0xffffffffu;
+  const bool fin = live && isfinite(zv);
+  const unsigned mfin = __ballot_sync(full, fin);
+  const unsigned mbad = __ballot_sync(full, live && !fin);
+  double s1 = 0.0, s2 = 0.0, p = 0.0;
+  if (mfin) {
+    p = __shfl_sync(full, zv, __ffs(mfin) - 1);
+    const double d = fin ? zv - p : 0.0;
+    s1 = d;
+    s2 = d * d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(full, s1, o);
+      s2 += __shfl_xor_sync(full, s2, o);
+    }
+  }
+  if (lane == 0) {
+    const double n = (double)__popc(mfin);
+    double mean = 0.0, m2 = 0.0;
+    if (mfin) {
+      mean = p + s1 / n;
+      m2 = s2 - s1 * (s1 / n);
+      if (m2 < 0.0) m2 = 0.0;
+    }
+    w4[0] = n; w4[1] = mean; w4[2] = m2; w4[3] = (double)__popc(mbad);
   }
 }
 
@@ -283,12 +342,18 @@ __device__ __forceinline__ void dn_decode_tile(int band, int n_groups, int n_uni
 }
 
 // 1 / E[k][j] of the group's annotations -> shared memory (epilogue warps only: bar 1, 128 threads)
+template <int MODE>
 __device__ __forceinline__ void dn_epi_stage_tables(const DenseParams& prm, int g, double* s_winv, int et) {
   const int I = prm.B + 1;
   const int k0 = g * prm.G;
   const int nk = min(prm.G, prm.K - k0);
   asm volatile("bar.sync 1, 128;" ::: "memory");
-  for (int i = et; i < nk * I; i += 128) s_winv[i] = 1.0 / prm.etab[(int64_t)k0 * I + i];
+  if (MODE == DN_EPI_FUSED32) {
+    uint32_t* s2 = reinterpret_cast<uint32_t*>(s_winv);
+    for (int i = et; i < nk * I; i += 128) s2[i] = prm.winv_fx[(int64_t)k0 * I + i];
+  } else {
+    for (int i = et; i < nk * I; i += 128) s_winv[i] = 1.0 / prm.etab[(int64_t)k0 * I + i];
+  }
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
@@ -307,6 +372,9 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
   const double rf = 1.0 / fpsv;
   int a = 0, j = 0;
   DnCell cell = {0.0, 0.0, 0.0, 0.0};
+  unsigned long long f_piv = 0ull, f_sumi = 0ull;
+  float f_sumsq = 0.f;
+  int f_obs = 0;
   const int ncols = nk * I;
   for (int col0 = 0; col0 < ncols; col0 += 32) {
     uint32_t r[32];
@@ -324,29 +392,54 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
           }
           if (++j == I) { j = 0; ++a; }
         } else {
-          const double sv = (double)(int)r[u];
-          dn_cell_add(cell, j, sv, s_winv[a * I + j], rf);
           if (live) {
             if (j == 0) { if (prm.obs) prm.obs[(int64_t)k * prm.N + c] = (long long)(int)r[u]; }
             else if (prm.samp) prm.samp[((int64_t)k * prm.B + (j - 1)) * prm.N + c] = (long long)(int)r[u];
           }
+          if (MODE == DN_EPI_FUSED32) {
+            // y_j = s_j * W_j (exact, < 2^56): their sum gives the mean over iterations exactly; the
+            // differences to the first iteration, exact integers, feed an fp32 sum of squares.  The
+            // cell's 1 / fps, the "- 1" and every cancellation happen once per annotation in fp64.
+            if (j == 0) {
+              f_obs = (int)r[u];
+              f_sumi = 0ull;
+              f_sumsq = 0.f;
+            } else {
+              const unsigned long long prod =
+                  (unsigned long long)r[u] * (unsigned long long)reinterpret_cast<const uint32_t*>(s_winv)[a * I + j];
+              if (j == 1) f_piv = prod;
+              f_sumi += prod;
+              const float df = (float)(long long)(prod - f_piv);
+              f_sumsq = fmaf(df, df, f_sumsq);
+            }
+          } else {
+            dn_cell_add(cell, j, (double)(int)r[u], s_winv[a * I + j], rf);
+          }
           if (++j == I) {
             const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
             double devv, zv;
-            dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
-            DWelford wf = {0.0, 0.0, 0.0};
-            double nonfinite = 0.0;
+            if (MODE == DN_EPI_FUSED32) {
+              const double E0 = prm.etab[(int64_t)k * I];
+              const double Bd = (double)prm.B;
+              const double scale = prm.wscale[k];
+              const double expected = E0 * fpsv;                                        // :488
+              const double obs_dev = ((double)f_obs - expected) / expected;             // :489
+              const double mean = rf * (scale * ((double)f_sumi / Bd)) - 1.0;           // :511
+              const double s1 = (double)(long long)(f_sumi - (unsigned long long)prm.B * f_piv);
+              const double var = ((double)f_sumsq - s1 * (s1 / Bd)) / (Bd - 1.0);
+              const double sd = rf * scale * sqrt(var > 0.0 ? var : (var == var ? 0.0 : var));   // :512
+              devv = obs_dev - mean;                                                    // :514
+              zv = devv / sd;                                                           // :515
+              if (empty || expected < 1.0) devv = zv = cv_na_real();
+            } else {
+              dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
+            }
             if (live) {
               prm.dev_rm[(int64_t)k * prm.N + c] = devv;
               prm.z_rm[(int64_t)k * prm.N + c] = zv;
-              if (isfinite(zv)) { wf.n = 1.0; wf.mean = zv; } else nonfinite = 1.0;
             }
-            // variability partial of (k, cell block): warp tree, then the 4 epilogue warps
-            dw_warp_reduce(wf, nonfinite, lane);
-            if (lane == 0) {
-              double* w = s_wred + (a * 4 + q4) * 4;
-              w[0] = wf.n; w[1] = wf.mean; w[2] = wf.m2; w[3] = nonfinite;
-            }
+            // variability partial of (k, cell block): this warp's 32 cells, then the 4 epilogue warps
+            dn_warp_variability(zv, live, lane, s_wred + (a * 4 + q4) * 4);
             j = 0;
             ++a;
           }
@@ -425,7 +518,7 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
         int cb, g;
         dn_decode_tile(prm.band, prm.n_groups, prm.n_cell_blocks, tile, cb, g);
         for (int kb = 0; kb < prm.n_kblocks; ++kb) {
-          mbar_wait(empty_bar + s, ph ^ 1u);
+          mbar_wait_relaxed(empty_bar + s, ph ^ 1u, 32);
           if (prm.debug_no_tma) { mbar_arrive(full_bar + s); if (++s == DN_STAGES) { s = 0; ph ^= 1u; } continue; }
           mbar_expect_tx(full_bar + s, DN_STAGE_BYTES);
           tma_load_2d(&map_c, full_bar + s, smem_a + s * DN_A_BYTES, kb * DN_BLOCK_K, cb * DN_BLOCK_M);
@@ -451,7 +544,7 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * DN_A_BYTES));
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * DN_B_BYTES));
-          if (prm.debug_no_tma > 1) {
+          if (prm.debug_no_tma > 1 && prm.debug_no_tma < 7) {
             // issue-pattern experiments (garbage results; bench.py --debug-no-tma V)
             const int v = prm.debug_no_tma;
             if (v == 2) {          // alternate two accumulators: no back-to-back dependent MMAs
@@ -500,15 +593,29 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
       int cb, g;
       dn_decode_tile(prm.band, prm.n_groups, prm.n_cell_blocks, tile, cb, g);
       const int as = (int)(it & 1);
-      if (MODE == DN_EPI_FUSED) dn_epi_stage_tables(prm, g, s_winv, et);
-      mbar_wait(tfull_bar + as, (uint32_t)((it >> 1) & 1));
+      if (MODE != DN_EPI_SUMS) dn_epi_stage_tables<MODE>(prm, g, s_winv, et);
+      mbar_wait_relaxed(tfull_bar + as, (uint32_t)((it >> 1) & 1), 256);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * DN_BLOCK_N);
+      if (prm.debug_no_tma == 7) {
+        // experiment: no epilogue work at all
+      } else if (prm.debug_no_tma == 8) {
+        // experiment: TMEM loads only
+        uint32_t r[32];
+        uint32_t acc = 0;
+        for (int col0 = 0; col0 < 256; col0 += 32) {
+          tmem_ld32(taddr + (uint32_t)col0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 32; ++u) acc ^= r[u];
+        }
+        if (acc == 0xdeadbeefu) prm.z_rm[0] = 0.0;
+      } else
       dn_epi_consume<MODE>(prm, cb, g, taddr, s_winv, s_wred, q4, lane);
       // every TMEM column of this stage has been read: hand the accumulator back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar + as);
-      if (MODE == DN_EPI_FUSED) dn_epi_merge(prm, cb, g, s_wred, et);
+      if (MODE != DN_EPI_SUMS) dn_epi_merge(prm, cb, g, s_wred, et);
     }
   }
   tc_fence_before();
@@ -577,7 +684,7 @@ k_dense_contract_pair(const __grid_constant__ CUtensorMap map_c, const __grid_co
         const int yc = (2 * unit + (int)rank) * DN_BLOCK_M;
         const int ym = g * DN_BLOCK_N + (int)rank * (DN_BLOCK_N / 2);
         for (int kb = 0; kb < prm.n_kblocks; ++kb) {
-          mbar_wait(empty_bar + s, ph ^ 1u);
+          mbar_wait_relaxed(empty_bar + s, ph ^ 1u, 32);
           if (prm.debug_no_tma) {
             if (rank == 0) mbar_arrive(full_bar + s);
             if (++s == DN_STAGES2) { s = 0; ph ^= 1u; }
@@ -628,15 +735,15 @@ k_dense_contract_pair(const __grid_constant__ CUtensorMap map_c, const __grid_co
       dn_decode_tile(prm.band, prm.n_groups, n_units, tile, unit, g);
       const int cb = 2 * unit + (int)rank;
       const int as = (int)(it & 1);
-      if (MODE == DN_EPI_FUSED) dn_epi_stage_tables(prm, g, s_winv, et);
-      mbar_wait(tfull_bar + as, (uint32_t)((it >> 1) & 1));
+      if (MODE != DN_EPI_SUMS) dn_epi_stage_tables<MODE>(prm, g, s_winv, et);
+      mbar_wait_relaxed(tfull_bar + as, (uint32_t)((it >> 1) & 1), 256);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * DN_BLOCK_N);
       dn_epi_consume<MODE>(prm, cb, g, taddr, s_winv, s_wred, q4, lane);
       tc_fence_before();
       mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar + as), 0));
-      if (MODE == DN_EPI_FUSED && cb < prm.n_cell_blocks) dn_epi_merge(prm, cb, g, s_wred, et);
-      else if (MODE == DN_EPI_FUSED) asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (MODE != DN_EPI_SUMS && cb < prm.n_cell_blocks) dn_epi_merge(prm, cb, g, s_wred, et);
+      else if (MODE != DN_EPI_SUMS) asm volatile("bar.sync 1, 128;" ::: "memory");
     }
   }
   // no CTA may leave (or free TMEM) while its peer can still read its shared memory / signal it
@@ -674,15 +781,11 @@ k_dense_finalize_sums(const DenseParams prm) {
   const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
   double devv, zv;
   dn_cell_finish(cell, et[0], fpsv, prm.B, empty, devv, zv);
-  DWelford wf = {0.0, 0.0, 0.0};
-  double nonfinite = 0.0;
   if (live) {
     prm.dev_rm[(int64_t)k * prm.N + c] = devv;
     prm.z_rm[(int64_t)k * prm.N + c] = zv;
-    if (isfinite(zv)) { wf.n = 1.0; wf.mean = zv; } else nonfinite = 1.0;
   }
-  dw_warp_reduce(wf, nonfinite, lane);
-  if (lane == 0) { s_w[w4][0] = wf.n; s_w[w4][1] = wf.mean; s_w[w4][2] = wf.m2; s_w[w4][3] = nonfinite; }
+  dn_warp_variability(zv, live, lane, &s_w[w4][0]);
   __syncthreads();
   if (threadIdx.x == 0) {
     DWelford tot = {0.0, 0.0, 0.0};
@@ -695,6 +798,34 @@ k_dense_finalize_sums(const DenseParams prm) {
     double* vp = prm.varpart + ((int64_t)k * prm.ncb_total + prm.cb0 + cb_local) * 4;
     vp[0] = tot.n; vp[1] = tot.mean; vp[2] = tot.m2; vp[3] = nf;
   }
+}
+
+// Fixed-point table of the integer epilogue: W[k][j] = round(2^F_k / E[k][j]) with F_k chosen so
+// that the largest entry of annotation k lies in [2^31, 2^32).  An annotation whose table holds a
+// zero or non-finite expectation sum cannot be scaled: flagged, the call then uses the fp64 epilogue.
+__global__ void k_winv_fixed(const double* __restrict__ etab, int K, int I, uint32_t* __restrict__ W,
+                             double* __restrict__ wscale, uint32_t* __restrict__ dflags) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const double* e = etab + (int64_t)k * I;
+  double wmax = 0.0;
+  bool bad = false;
+  for (int j = 0; j < I; ++j) {
+    const double w = 1.0 / e[j];
+    if (!(w > 0.0) || !isfinite(w)) bad = true;
+    else wmax = fmax(wmax, w);
+  }
+  int ex = 0;
+  if (!bad) frexp(wmax, &ex);                       // wmax = m * 2^ex, m in [0.5, 1)
+  const int F = 32 - ex;
+  for (int j = 0; j < I; ++j) {
+    double v = bad ? 0.0 : rint(ldexp(1.0 / e[j], F));
+    if (v > 4294967295.0) v = 4294967295.0;
+    W[(int64_t)k * I + j] = (uint32_t)v;
+  }
+  wscale[k] = bad ? 0.0 : ldexp(1.0, -F);
+  // an empty annotation has an all-zero table and all-NA results whatever the arithmetic
+  if (bad && e[0] != 0.0) atomicOr(dflags + 4, 1u);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
@@ -737,9 +868,9 @@ int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan*
   pl->rowsM = (int64_t)pl->n_groups * DN_BLOCK_N;
   pl->planes = 1;
   for (uint32_t v = max_val >> 8; v; v >>= 8) pl->planes++;
-  // alone on the GPU the single-CTA kernel is ~4 % faster; beside host copies and the next chunk's
-  // K1 (streamed calls: want_chunk > 0) the CTA pair loses less (profiles/r01f)
-  pl->pair = h->opt_pair < 0 ? (want_chunk > 0 ? 1 : 0) : (h->opt_pair ? 1 : 0);
+  // the CTA pair moves a third less through the L2 -> SM crossbar; once the epilogue stopped
+  // being the limiter it is the faster kernel in every configuration measured (profiles/r01h)
+  pl->pair = h->opt_pair < 0 ? 1 : (h->opt_pair ? 1 : 0);
   pl->m_bytes = pl->rowsM * pl->Ppad;
   // per cell: one u8 row of the operand (+ the int64 sums scratch when digit planes are combined)
   const double per_cell = (double)pl->Ppad + (pl->planes > 1 ? (double)h->K * I * 8.0 : 0.0);
@@ -800,6 +931,10 @@ int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows) {
   CV_TRY(cv_ensure(h, h->varpart, (size_t)h->K * ncb_total * 4 * 8));
   cv_span_begin(h, CV_SPAN_LAYOUT);
   CV_TRY(cv_dense_build_rows(h, pl, scatter_rows));
+  CV_TRY(cv_ensure(h, h->dn_winv, (size_t)h->K * pl.I * 4 + (size_t)h->K * 8 + 16));
+  CV_LAUNCH(h, k_winv_fixed, (unsigned)((h->K + 127) / 128), 128, 0, h->etab.as<double>(), (int)h->K, pl.I,
+            h->dn_winv.as<uint32_t>() + 2 * h->K, reinterpret_cast<double*>(h->dn_winv.p),
+            h->flags.as<uint32_t>() + CV_DFLAGS);
   cv_span_end(h);
   h->dn_flops = 0;
   return CV_OK;
@@ -835,6 +970,8 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
   prm.varpart = h->varpart.as<double>();
   prm.obs = keep_sums ? h->obs.as<long long>() : nullptr;
   prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
+  prm.wscale = reinterpret_cast<const double*>(h->dn_winv.p);            // [K] doubles, then [K][I] u32
+  prm.winv_fx = h->dn_winv.as<uint32_t>() + 2 * K;
   prm.sums = h->dn_S.as<long long>();
   prm.sums_ld = (int)pl.chunk_cells;
   prm.sums_c0 = (int)c0;
@@ -844,8 +981,17 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
     cv_span_end(h);
     cv_span_begin(h, CV_SPAN_CONTRACT);
     if (pl.planes == 1) {
-      CV_TRY(launch_gemm<DN_EPI_FUSED>(h, pl, map_c, map_m, prm));
+      // fp64 epilogue when it hides behind the next tile's MMAs anyway (long tiles) or when the sums
+      // may not fit a float exactly; the float-pair epilogue otherwise ("dense_epilogue": 1 / 2 force)
+      const bool exact32 = h->dn_fixed_ok && (double)pl.cell_tot_bound * (double)h->dn_maxmult < 16777216.0;
+      const int64_t tiles = (int64_t)prm.n_cell_blocks * prm.n_groups;
+      const bool want32 = h->opt_epilogue == 1 ||
+                          (h->opt_epilogue == 0 && prm.n_kblocks < 1100 && tiles >= 4 * (int64_t)h->num_sms);
+      if (want32 && exact32) CV_TRY(launch_gemm<DN_EPI_FUSED32>(h, pl, map_c, map_m, prm));
+      else CV_TRY(launch_gemm<DN_EPI_FUSED>(h, pl, map_c, map_m, prm));
+      h->st.epilogue = (want32 && exact32) ? 32 : 64;
     } else {
+      h->st.epilogue = 64;
       prm.sums_shift = 8 * plane;
       prm.sums_acc = plane > 0;
       CV_TRY(launch_gemm<DN_EPI_SUMS>(h, pl, map_c, map_m, prm));
@@ -874,6 +1020,8 @@ int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, in
     CV_FAIL(h, CV_ERR_UNSUPPORTED, "annotation multiplicity bound %llu exceeds the u8 operand",
             (unsigned long long)maxmult);
   }
+  h->dn_maxmult = maxmult;
+  h->dn_fixed_ok = df[4] == 0;                 // every expectation sum could be scaled to 32 bits
   if (!with_counts) return CV_OK;
   // every digit plane's sum is bounded by (cell total) x multiplicity
   if ((double)h->max_cell_tot * (double)maxmult >= 2147483647.0) {

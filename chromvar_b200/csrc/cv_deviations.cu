@@ -571,8 +571,10 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   int use_dense = 0;
   DensePlan pl;
   {
-    // host copies overlap the GEMMs: about four chunks, none smaller than a few waves of tiles
-    const int64_t want_chunk = (io && (io->out_dev || io->out_z || streaming)) ? std::max<int64_t>((N + 3) / 4, 1024) : 0;
+    // about four GEMM launches per call: host copies overlap them chunk by chunk, and four short
+    // launches of the CTA-pair kernel also finish sooner than one long one (22.3 vs 24.5 ms on
+    // config 2, profiles/r01h); none smaller than a few waves of tiles
+    const int64_t want_chunk = std::max<int64_t>((N + 3) / 4, 1024);
     CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
   }
 
@@ -649,6 +651,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       int planes_max = pl.planes;
       for (int i = 0; i < n_chunks; ++i) {
         DensePlan pli = pl;
+        pli.cell_tot_bound = h->max_cell_tot;              // resident counts: known since K1
         if (streaming) {
           // K1 of this chunk has run on the upload stream: its verdict and the largest count so far
           // decide how many u8 digit planes this chunk's GEMM needs
@@ -657,6 +660,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
           if (kf[0]) return cv_counts_verdict(h, kf);            // counts_check failed: message from K1
           pli.planes = 1;
           for (uint32_t v = kf[1] >> 8; v; v >>= 8) pli.planes++;
+          pli.cell_tot_bound = (uint64_t)kf[2] | ((uint64_t)kf[3] << 32);   // running maximum incl. this chunk
           planes_max = std::max(planes_max, pli.planes);
           CV_CUDA(h, cudaStreamWaitEvent(h->stream, ev_up[i], 0));
         }
@@ -818,6 +822,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     h->st.path = 0;
     h->st.acc_bytes = wide ? 8 : 4;
     h->st.planes = 0;
+    h->st.epilogue = 64;
   }
   h->have_results = true;
   return CV_OK;

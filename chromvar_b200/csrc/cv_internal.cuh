@@ -141,6 +141,10 @@ struct cv_handle {
   DevBuf dn_invsrc;  // i32 [B*P]
   DevBuf dn_E2;      // f64 [P][B+1] e[p], e[bg[p, j]]
   DevBuf dn_ov;      // u64 [K] background overlap counts
+  DevBuf dn_winv;    // f64 [K] 2^-F_k, then u32 [K][B+1] W[k][j] = round(2^F_k / E[k][j])
+  bool dn_fixed_ok = true;
+  uint64_t dn_maxmult = 1;     // bound on the entries of M (set by cv_dense_check)
+  int opt_epilogue = 0;        // dense fused epilogue: 0 by tile length, 1 fixed point / fp32, 2 fp64
   int opt_rows_scatter = 0;   // build the operand rows with the per-annotation scatter kernel only
   double dn_flops = 0;
   int opt_path = 0;  // 0 auto, 1 force row-gather SpMM, 2 force dense tcgen05
@@ -186,6 +190,7 @@ struct DensePlan {
   int64_t Ppad = 0, rowsM = 0;
   int64_t chunk_cells = 0;   // cells per GEMM launch, multiple of 256
   int64_t m_bytes = 0, c_bytes = 0, sums_bytes = 0;
+  uint64_t cell_tot_bound = ~0ull;   // largest cell total of the cells a launch covers (exactness of fp32 sums)
 };
 int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan* pl, std::string* why);
 double cv_dense_cost_ms(cv_handle* h, const DensePlan& pl);

@@ -60,9 +60,14 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
 /* options:
  *   "path"             0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05 (fails if the problem
  *                      cannot be represented exactly in u8 operands / s32 accumulators)
- *   "dense_cta_pair"   GEMM kernel: 1 tcgen05 cta_group::2 (256-cell tiles on two SMs), 0 single CTA
- *                      (128-cell tiles), -1 (default) by context: the pair when host copies run
- *                      beside the GEMM (cv_deviations, cv_deviations_csc), single CTA otherwise
+ *   "dense_cta_pair"   GEMM kernel: 1 or -1 (default) tcgen05 cta_group::2 (256-cell tiles on two
+ *                      SMs), 0 single CTA (128-cell tiles)
+ *   "dense_epilogue"   arithmetic of the fused epilogue: 2 fp64 throughout; 1 the per-iteration
+ *                      statistics without fp64 (mean over iterations in exact 64-bit fixed point,
+ *                      variance in fp32 of exact integer differences, fp64 once per annotation;
+ *                      needs sums < 2^24; dev agrees with fp64 to ~1e-9, sd to ~1e-6 relative);
+ *                      0 (default) fp64 when a tile is long enough to hide it (>= 1100 k-blocks of
+ *                      128 peaks) or the problem is tiny, the fixed-point form otherwise
  *   "dense_rows_scatter" 1 builds the operand rows with the per-annotation scatter kernel only
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
@@ -189,7 +194,7 @@ typedef struct cv_stage_stats {
   int32_t n_cell_tiles;      /* row-gather: tiles; dense: cell chunks (GEMM launches per plane) */
   int32_t acc_bytes;         /* accumulator width used (4 or 8) */
   int32_t planes;            /* dense path: u8 digit planes of the counts (1 when max count <= 255) */
-  int32_t reserved;
+  int32_t epilogue;          /* dense path: 32 = fixed-point / fp32 epilogue, 64 = fp64 epilogue */
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
 

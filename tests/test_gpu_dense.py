@@ -27,6 +27,7 @@ def dense_engine(engine, request):
     engine.set_option("path", 0)
     engine.set_option("dense_cta_pair", -1)
     engine.set_option("cell_chunk", 0)
+    engine.set_option("dense_epilogue", 0)
 
 
 def _run(engine, C, sets, bg, e, sums=True):
@@ -40,9 +41,15 @@ def test_dense_known_answer(dense_engine, golden_deviations_test):
     g = golden_deviations_test
     got = _run(dense_engine, g["counts"], [g["set0"], g["set1"], g["set2"]], g["bg"],
                g["counts"].sum(axis=1) / g["counts"].sum())
-    assert dense_engine.stats()["path"] == 1
+    assert dense_engine.stats()["path"] == 1 and dense_engine.stats()["epilogue"] == 64   # tiny: fp64 epilogue
     assert np.max(np.abs(got["dev"] - g["deviations"])) < 1e-12
     assert np.max(np.abs(got["z"] - g["z"])) < 1e-12
+    dense_engine.set_option("dense_epilogue", 1)          # float-pair epilogue on the reference's known answer
+    got = _run(dense_engine, g["counts"], [g["set0"], g["set1"], g["set2"]], g["bg"],
+               g["counts"].sum(axis=1) / g["counts"].sum())
+    assert dense_engine.stats()["epilogue"] == 32
+    assert np.max(np.abs(got["dev"] - g["deviations"]) / np.maximum(np.abs(g["deviations"]), 1e-3)) < 1e-5
+    assert np.max(np.abs(got["z"] - g["z"]) / np.maximum(np.abs(g["z"]), 1e-3)) < 1e-5
 
 
 def test_dense_mini_against_oracle(dense_engine, golden_mini):
@@ -98,11 +105,22 @@ def test_dense_equals_row_gather_at_size(engine):
     a = engine.deviations(ptr, idx, bg, e, sums=True)
     assert engine.stats()["path"] == 0
     engine.set_option("path", 2)
+    engine.set_option("dense_epilogue", 2)                    # fp64 epilogue: agrees with the row-gather kernel to rounding
     try:
         b = engine.deviations(ptr, idx, bg, e, sums=True)
-        assert engine.stats()["path"] == 1
+        assert engine.stats()["path"] == 1 and engine.stats()["epilogue"] == 64
+        engine.set_option("dense_epilogue", 1)                # float-pair epilogue: same sums, z / dev to ~1e-7
+        f = engine.deviations(ptr, idx, bg, e, sums=True)
+        assert engine.stats()["epilogue"] == 32
     finally:
         engine.set_option("path", 0)
+        engine.set_option("dense_epilogue", 0)
+    assert np.array_equal(f["observed"], b["observed"]) and np.array_equal(f["sampled"], b["sampled"])
+    assert np.array_equal(np.isnan(f["z"]), np.isnan(b["z"]))
+    okf = ~np.isnan(b["z"])
+    assert np.max(np.abs(f["z"][okf] - b["z"][okf]) / np.maximum(np.abs(b["z"][okf]), 1e-3)) < 5e-6
+    assert np.max(np.abs(f["dev"][okf] - b["dev"][okf]) / np.maximum(np.abs(b["dev"][okf]), 1e-3)) < 5e-6
+    assert np.allclose(f["variability"], b["variability"], rtol=5e-6, equal_nan=True)
     assert np.array_equal(a["observed"], b["observed"])
     assert np.array_equal(a["sampled"], b["sampled"])
     assert np.array_equal(np.isnan(a["z"]), np.isnan(b["z"]))
