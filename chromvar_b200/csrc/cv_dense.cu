@@ -102,6 +102,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// one lane of a converged warp; the code around it runs on all 32 lanes with warp-uniform values, so
+// the descriptors of the tcgen05 instructions stay in uniform registers (a lane-0-only branch makes
+// the compiler move every operand through an ELECT / R2UR.BROADCAST loop per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -528,8 +536,8 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the pipeline, one elected lane issues =====
+    {
       constexpr uint32_t idesc = make_idesc_u8(DN_BLOCK_M, DN_BLOCK_N);
       int s = 0;
       uint32_t ph = 0;
@@ -547,6 +555,7 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
           if (prm.debug_no_tma > 1 && prm.debug_no_tma < 7) {
             // issue-pattern experiments (garbage results; bench.py --debug-no-tma V)
             const int v = prm.debug_no_tma;
+            if (elect_one()) {
             if (v == 2) {          // alternate two accumulators: no back-to-back dependent MMAs
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -571,17 +580,23 @@ k_dense_contract(const __grid_constant__ CUtensorMap map_c, const __grid_constan
               for (int k = 0; k < 4; ++k) umma_i8(tmem_d, da, db, idesc, 1u);
             }
             tc_commit(empty_bar + s);
+            }
+            __syncwarp();
             if (++s == DN_STAGES) { s = 0; ph ^= 1u; }
             continue;
           }
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DN_BLOCK_K / DN_UMMA_K; ++k)
-            umma_i8(tmem_d, da + (uint64_t)(k * DN_UMMA_K / 16), db + (uint64_t)(k * DN_UMMA_K / 16), idesc,
-                    (kb | k) ? 1u : 0u);
-          tc_commit(empty_bar + s);            // frees the smem stage when these MMAs retire
+            for (int k = 0; k < DN_BLOCK_K / DN_UMMA_K; ++k)
+              umma_i8(tmem_d, da + (uint64_t)(k * DN_UMMA_K / 16), db + (uint64_t)(k * DN_UMMA_K / 16), idesc,
+                      (kb | k) ? 1u : 0u);
+            tc_commit(empty_bar + s);          // frees the smem stage when these MMAs retire
+          }
+          __syncwarp();
           if (++s == DN_STAGES) { s = 0; ph ^= 1u; }
         }
-        tc_commit(tfull_bar + as);             // accumulator tile complete
+        if (elect_one()) tc_commit(tfull_bar + as);   // accumulator tile complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -700,7 +715,7 @@ k_dense_contract_pair(const __grid_constant__ CUtensorMap map_c, const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_u8(2 * DN_BLOCK_M, DN_BLOCK_N);
       int s = 0;
       uint32_t ph = 0;
@@ -715,14 +730,18 @@ k_dense_contract_pair(const __grid_constant__ CUtensorMap map_c, const __grid_co
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * DN_A_BYTES));
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * DN_A_BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DN_BLOCK_K / DN_UMMA_K; ++k)
-            umma_i8_pair(tmem_d, da + (uint64_t)(k * DN_UMMA_K / 16), db + (uint64_t)(k * DN_UMMA_K / 16), idesc,
-                         (kb | k) ? 1u : 0u);
-          tc_commit_pair(empty_bar + s, 3);    // frees the stage in both CTAs when these MMAs retire
+            for (int k = 0; k < DN_BLOCK_K / DN_UMMA_K; ++k)
+              umma_i8_pair(tmem_d, da + (uint64_t)(k * DN_UMMA_K / 16), db + (uint64_t)(k * DN_UMMA_K / 16), idesc,
+                           (kb | k) ? 1u : 0u);
+            tc_commit_pair(empty_bar + s, 3);  // frees the stage in both CTAs when these MMAs retire
+          }
+          __syncwarp();
           if (++s == DN_STAGES2) { s = 0; ph ^= 1u; }
         }
-        tc_commit_pair(tfull_bar + as, 3);     // accumulator tile complete: both epilogues may start
+        if (elect_one()) tc_commit_pair(tfull_bar + as, 3);   // accumulator tile complete: both epilogues may start
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

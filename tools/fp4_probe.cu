@@ -34,12 +34,14 @@ enum { KIND_I8 = 0, KIND_F8 = 1, KIND_MXF4 = 2 };
 
 template <int KIND>
 __global__ void __launch_bounds__(128, 1) k_probe(int nmma, uint32_t seed_bits, uint32_t byteA, uint32_t byteB,
-                                                  long long* cycles, uint32_t* out_d) {
+                                                  long long* cycles, uint32_t* out_d, int commit_every,
+                                                  int fence_every, int ncols) {
   extern __shared__ unsigned char raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sa = smem;             // 16 KB: 128 rows x 128 bytes
   unsigned char* sb = smem + 16384;     // 32 KB: 256 rows x 128 bytes
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[4];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 16384 / 4; i += 128) reinterpret_cast<uint32_t*>(sa)[i] = byteA * 0x01010101u;
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(int nmma, uint32_t seed_bits, 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2[i])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -72,11 +75,22 @@ __global__ void __launch_bounds__(128, 1) k_probe(int nmma, uint32_t seed_bits, 
     const uint64_t da0 = make_smem_desc(smem_u32(sa));
     const uint64_t db0 = make_smem_desc(smem_u32(sb));
     uint32_t idesc;
-    if (KIND == KIND_I8) idesc = (2u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-    else if (KIND == KIND_F8) idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-    else idesc = (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+    const uint32_t nc = (uint32_t)ncols;
+    if (KIND == KIND_I8) idesc = (2u << 4) | ((nc >> 3) << 17) | ((128u >> 4) << 24);
+    else if (KIND == KIND_F8) idesc = (1u << 4) | ((nc >> 3) << 17) | ((128u >> 4) << 24);
+    else idesc = (1u << 7) | (1u << 10) | ((nc >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
     const long long t0 = clock64();
     for (int i = 0; i < nmma; ++i) {
+      if (fence_every && (i & 3) == 0) {
+        if (fence_every & 2) {      // poll a barrier whose phase is already complete, like a full-stage wait
+          uint32_t dn;
+          do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(dn) : "r"(smem_u32(&bar2[3])), "r"(1u) : "memory");
+          } while (!dn);
+        }
+        if (fence_every & 1) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       const uint64_t da = da0 + (uint64_t)((i & 3) * 2);      // 32 bytes along K inside the 128-byte row
       const uint64_t db = db0 + (uint64_t)((i & 3) * 2);
       if (KIND == KIND_I8) {
@@ -93,6 +107,8 @@ __global__ void __launch_bounds__(128, 1) k_probe(int nmma, uint32_t seed_bits, 
                      ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(1u), "r"(tmem_base + 256u), "r"(tmem_base + 320u)
                      : "memory");
       }
+      if (commit_every && (i & (commit_every - 1)) == commit_every - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[(i >> 2) & 1])) : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     uint32_t done;
@@ -123,12 +139,13 @@ static uint32_t* d_out;
 
 struct Result { double cyc_per_mma; bool uniform; uint32_t first; };
 
-static Result run(int kind, int nmma, uint32_t seed_bits, uint32_t a, uint32_t b, int grid) {
+static Result run(int kind, int nmma, uint32_t seed_bits, uint32_t a, uint32_t b, int grid, int commit_every = 0,
+                  int fence_every = 0, int ncols = 256) {
   const size_t smem = 49152 + 1024;
   switch (kind) {
-    case KIND_I8: CK(cudaFuncSetAttribute(k_probe<KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_probe<KIND_I8><<<grid, 128, smem>>>(nmma, seed_bits, a, b, d_cycles, d_out); break;
-    case KIND_F8: CK(cudaFuncSetAttribute(k_probe<KIND_F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_probe<KIND_F8><<<grid, 128, smem>>>(nmma, seed_bits, a, b, d_cycles, d_out); break;
-    default: CK(cudaFuncSetAttribute(k_probe<KIND_MXF4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_probe<KIND_MXF4><<<grid, 128, smem>>>(nmma, seed_bits, a, b, d_cycles, d_out); break;
+    case KIND_I8: CK(cudaFuncSetAttribute(k_probe<KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_probe<KIND_I8><<<grid, 128, smem>>>(nmma, seed_bits, a, b, d_cycles, d_out, commit_every, fence_every, ncols); break;
+    case KIND_F8: CK(cudaFuncSetAttribute(k_probe<KIND_F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_probe<KIND_F8><<<grid, 128, smem>>>(nmma, seed_bits, a, b, d_cycles, d_out, commit_every, fence_every, ncols); break;
+    default: CK(cudaFuncSetAttribute(k_probe<KIND_MXF4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_probe<KIND_MXF4><<<grid, 128, smem>>>(nmma, seed_bits, a, b, d_cycles, d_out, commit_every, fence_every, ncols); break;
   }
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -142,7 +159,7 @@ static Result run(int kind, int nmma, uint32_t seed_bits, uint32_t a, uint32_t b
   r.cyc_per_mma = (double)mx / nmma;
   r.first = out[0];
   r.uniform = true;
-  for (uint32_t v : out) if (v != out[0]) r.uniform = false;
+  for (int l = 0; l < 128; ++l) for (int c = 0; c < ncols; ++c) if (out[l * 256 + c] != out[0]) r.uniform = false;
   return r;
 }
 
@@ -167,6 +184,18 @@ int main() {
       const double got = kind == KIND_I8 ? (double)(int)r.first : (double)bits2f(r.first);
       printf("rate %-20s %7.1f cycles per M128 N256 instruction (%d SMs busy); D = %.1f (expected %.1f) uniform %d\n",
              names[kind], r.cyc_per_mma, grid, got, expect, (int)r.uniform);
+    }
+  // ---- what a per-stage tcgen05.commit / fence costs the issue rate
+  for (int kind : {0, 2})
+    for (int ce : {0, 1, 2, 4, 8, 16})
+      for (int fe : {0, 1, 2, 3}) {
+        Result r = run(kind, 8192, 0u, one[kind], one[kind], grid, ce, fe);
+        printf("rate %-20s commit every %2d, per 4 instructions: fence(1) | barrier poll(2) = %d: %7.1f cycles per instruction\n", names[kind], ce, fe, r.cyc_per_mma);
+      }
+  for (int kind : {0, 2})
+    for (int nc : {64, 128, 192, 256}) {
+      Result r = run(kind, 8192, 0u, one[kind], one[kind], grid, 0, 0, nc);
+      printf("rate %-20s N = %3d: %7.1f cycles per instruction (uniform %d)\n", names[kind], nc, r.cyc_per_mma, (int)r.uniform);
     }
   // ---- exactness of the f32 accumulate: seed X (odd, just below 2^m), add n instructions of all-ones
   for (int kind = 1; kind < 3; ++kind) {
