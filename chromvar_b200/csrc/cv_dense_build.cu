@@ -489,7 +489,7 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   CV_LAUNCH(h, k_u32_max_db, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, dflags + 1);
   CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
   // rows of a group that no (annotation, iteration) owns must be zero
-  if (G * I < DB_BLOCK_N || K % G)
+  if (!pl.fp4 && (G * I < DB_BLOCK_N || K % G))
     CV_LAUNCH(h, k_zero_pad_rows, pl.n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, Ppad);
   if (scatter || h->opt_rows_scatter) {
     const int budget = h->max_smem_optin - 2048;
@@ -523,7 +523,9 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   CV_TRY(cv_exclusive_scan_u32_async(h, h->tmp1.as<uint32_t>(), h->dn_invptr.as<uint32_t>(), P * B));
   CV_LAUNCH(h, k_inv_fill, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(), h->index_base, P * B,
             (int)P, h->dn_invptr.as<uint32_t>(), h->tmp1.as<uint32_t>(), h->dn_invsrc.as<int32_t>());
-  {
+  if (pl.fp4) {
+    CV_TRY(cv_f4_build_rows(h, pl));               // nibble-packed rows in the super-group layout
+  } else {
     dim3 grid((unsigned)((Ppad + GR_TQ - 1) / GR_TQ), (unsigned)I, (unsigned)Kw);
     CV_LAUNCH(h, k_dense_rows_gather, grid, GR_THREADS, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
               h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, G, Ppad, h->dn_M.as<uint8_t>());

@@ -636,6 +636,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       CV_CUDA(h, cudaStreamSynchronize(h->s_aux));           // the first attempt's table kernels
       h->aux_pending = false;
       CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));
+      cv_dense_plan_set_fp4(&pl, 0);                         // the e2m1 rows exist only in the gather formulation
       CV_TRY(cv_dense_prepare(h, pl, 1));
       CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
       CV_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -645,6 +646,19 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     if (rc != CV_OK) {
       if (soft && h->opt_path != 2 && !streaming) use_dense = 0;     // exact fallback below
       else { if (io) io->soft_fail = soft; return rc; }
+    }
+    if (use_dense && pl.fp4 && !streaming &&
+        !((double)h->max_cell_tot * (double)h->dn_maxmult < 16777216.0)) {
+      // sums may not fit a float exactly: u8 operands / s32 accumulators instead
+      CV_CUDA(h, cudaStreamSynchronize(h->s_aux));
+      h->aux_pending = false;
+      CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));
+      cv_dense_plan_set_fp4(&pl, 0);
+      CV_TRY(cv_dense_prepare(h, pl, 0));
+      CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
+      CV_CUDA(h, cudaStreamSynchronize(h->stream));
+      int soft2 = 0;
+      CV_TRY(cv_dense_check(h, pl, hf, 1, &soft2));
     }
     if (use_dense) {
       const bool dl = io && (io->out_dev || io->out_z);
@@ -664,7 +678,13 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
           planes_max = std::max(planes_max, pli.planes);
           CV_CUDA(h, cudaStreamWaitEvent(h->stream, ev_up[i], 0));
         }
-        CV_TRY(cv_dense_chunk(h, pli, lo(i), hi(i), keep_sums));
+        {
+          const int rcc = cv_dense_chunk(h, pli, lo(i), hi(i), keep_sums);
+          if (rcc != CV_OK) {
+            if (h->f4_veto && io) io->soft_fail = 1;         // not exact on the e2m1 path: the caller retries with u8
+            return rcc;
+          }
+        }
         cv_span_begin(h, CV_SPAN_FINALIZE);
         CV_TRY(enqueue_transposes(h, lo(i), hi(i)));
         cv_span_end(h);
@@ -798,6 +818,19 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     CV_FAIL(h, CV_ERR_INVALID, "All peaks must have at least one fragment in one sample");
   if (hf[CV_DFLAGS] & FLAG_BADIDX)
     CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
+  if (use_dense && pl.fp4 && hf[CV_DFLAGS + 5]) {
+    // the e2m1 operands could not hold this problem (overflow columns beyond the reserve, or a
+    // column listing a peak twice): the results are void, redo with the u8 kernel
+    h->f4_veto = true;
+    if (streaming) {
+      io->soft_fail = 1;
+      io->results_streamed = false;
+      CV_FAIL(h, CV_ERR_UNSUPPORTED, "counts not representable on the e2m1 path (flags %u)", hf[CV_DFLAGS + 5]);
+    }
+    const int rc2 = deviations_run(h, rebuild_counts_layout, keep_sums, io);
+    h->f4_veto = false;
+    return rc2;
+  }
   double ms[CV_SPAN_N];
   cv_spans_collect(h, ms);
   h->st.ms_counts_layout = ms[CV_SPAN_LAYOUT] + ms[CV_SPAN_K1];
@@ -808,11 +841,15 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   if (use_dense) {
     h->st.contract_bytes = 0;
     h->st.contract_flops = h->dn_flops;
+    if (pl.fp4)                                            // + the overflow columns of every chunk
+      h->st.contract_flops += 2.0 * (double)pl.rowsM4 * (double)std::min<int64_t>(pl.chunk_cells, N) * (double)hf[CV_DFLAGS + 6];
     h->st.path = 1;
     h->st.acc_bytes = 4;
     h->st.cell_tile = pl.pair ? 256 : 128;
     h->st.n_cell_tiles = (int)((N + pl.chunk_cells - 1) / pl.chunk_cells);
     h->st.planes = pl.planes;
+    h->st.operand_bits = pl.fp4 ? 4 : 8;
+    h->st.overflow_columns = pl.fp4 ? (int32_t)hf[CV_DFLAGS + 6] : 0;
   } else {
     // gather model: every visited entry is a 4-byte load, plus the
     // compulsory one-time traffic (layout, annotation lists, background rows, outputs)
@@ -823,6 +860,8 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     h->st.acc_bytes = wide ? 8 : 4;
     h->st.planes = 0;
     h->st.epilogue = 64;
+    h->st.operand_bits = 0;
+    h->st.overflow_columns = 0;
   }
   h->have_results = true;
   return CV_OK;
@@ -996,8 +1035,10 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
     CV_TRY(cv_expectations(h, 0, nullptr, 0, e_default.data()));
     expectation = e_default.data();
   }
-  return cv_deviations(h, K, annoptr, annoidx, index_base, bg, B, expectation, out_dev, out_z, out_matches,
-                       out_overlap, out_variability, nullptr, nullptr);
+  const int rc_plain = cv_deviations(h, K, annoptr, annoidx, index_base, bg, B, expectation, out_dev, out_z, out_matches,
+                                     out_overlap, out_variability, nullptr, nullptr);
+  h->f4_veto = false;
+  return rc_plain;
 }
 
 extern "C" int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t* n_elems) {

@@ -142,6 +142,16 @@ struct cv_handle {
   DevBuf dn_E2;      // f64 [P][B+1] e[p], e[bg[p, j]]
   DevBuf dn_ov;      // u64 [K] background overlap counts
   DevBuf dn_winv;    // f64 [K] 2^-F_k, then u32 [K][B+1] W[k][j] = round(2^F_k / E[k][j])
+  // e2m1 variant (cv_dense_fp4.cu); dn_M / dn_C then hold the nibble-packed operands
+  DevBuf f4_Tq;      // u32 [P] terms of the largest operand entry of peak q (0 = none outside S)
+  DevBuf f4_Sq;      // u32 [P] terms of the largest count of peak q in the current cell chunk
+  DevBuf f4_ncol;    // u32 [P] overflow columns of peak q in the current chunk
+  DevBuf f4_off;     // u32 [P+1] exclusive scan of f4_ncol
+  DevBuf f4_colq;    // i32 [Hcap] peak of overflow column x
+  DevBuf f4_colt;    // u32 [Hcap] multiplicity term of overflow column x
+  DevBuf f4_info;    // u32 [16]: k-blocks and overflow columns of the current chunk
+  int opt_fp4 = -1;            // -1 / 1 use the e2m1 kernel when the problem allows it, 0 never
+  bool f4_veto = false;        // this problem turned out not to fit the e2m1 path: retry with u8
   bool dn_fixed_ok = true;
   uint64_t dn_maxmult = 1;     // bound on the entries of M (set by cv_dense_check)
   int opt_epilogue = 0;        // dense fused epilogue: 0 by tile length, 1 fixed point / fp32, 2 fp64
@@ -191,7 +201,18 @@ struct DensePlan {
   int64_t chunk_cells = 0;   // cells per GEMM launch, multiple of 256
   int64_t m_bytes = 0, c_bytes = 0, sums_bytes = 0;
   uint64_t cell_tot_bound = ~0ull;   // largest cell total of the cells a launch covers (exactness of fp32 sums)
+  // e2m1 variant: annotations per 256- / 208-row sub-tile, super-groups of 464 rows, peak columns
+  // padded to 256, reserved overflow columns, bytes per operand row, operand sizes of both variants
+  int fp4 = 0, Ga = 0, Gb = 0, n_sg = 0;
+  int64_t Ppad4 = 0, Hcap = 0, rowb = 0, rowsM4 = 0;
+  int64_t m_bytes_u8 = 0, c_bytes_u8 = 0;
 };
+int cv_f4_plan(cv_handle* h, DensePlan* pl);
+void cv_dense_plan_set_fp4(DensePlan* pl, int on);
+int cv_f4_build_rows(cv_handle* h, const DensePlan& pl);
+struct DenseParams;
+int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm, int64_t c0, int64_t c1, int64_t rows,
+                int fixed_point_epilogue);
 int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan* pl, std::string* why);
 double cv_dense_cost_ms(cv_handle* h, const DensePlan& pl);
 int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows);

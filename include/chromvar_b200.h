@@ -68,6 +68,11 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *                      needs sums < 2^24; dev agrees with fp64 to ~1e-9, sd to ~1e-6 relative);
  *                      0 (default) fp64 when a tile is long enough to hide it (>= 1100 k-blocks of
  *                      128 peaks) or the problem is tiny, the fixed-point form otherwise
+ *   "dense_fp4"        -1 (default) / 1: the dense contraction runs on 4-bit e2m1 operands (tcgen05
+ *                      kind::mxf4, f32 accumulators holding exact integers < 2^24, twice the MAC rate
+ *                      of u8) whenever the problem can be represented exactly that way -- values
+ *                      outside {0,1,2,3,4,6} are split into terms in extra "overflow" columns -- and
+ *                      falls back to u8 otherwise; 0: never
  *   "dense_rows_scatter" 1 builds the operand rows with the per-annotation scatter kernel only
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
@@ -195,6 +200,8 @@ typedef struct cv_stage_stats {
   int32_t acc_bytes;         /* accumulator width used (4 or 8) */
   int32_t planes;            /* dense path: u8 digit planes of the counts (1 when max count <= 255) */
   int32_t epilogue;          /* dense path: 32 = fixed-point / fp32 epilogue, 64 = fp64 epilogue */
+  int32_t operand_bits;      /* dense path: 8 = u8 operands (tcgen05 kind::i8), 4 = e2m1 operands (kind::mxf4) */
+  int32_t overflow_columns;  /* e2m1 operands: extra columns holding the terms of values outside {0,1,2,3,4,6}, all chunks */
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
 
