@@ -228,6 +228,8 @@ def run_ours(args):
     eng = _lib.Handle(local, seed=20173)
     eng.set_option("path", args.path)
     eng.set_option("dense_cta_pair", args.pair)
+    eng.set_option("dense_fp4", args.fp4)
+    eng.set_option("dense_lockstep", args.lockstep)
     if args.chunk:
         eng.set_option("cell_chunk", args.chunk)
     if args.band:
@@ -360,16 +362,20 @@ def run_ours(args):
         # dense tcgen05 path: algorithmic ops = 2 (B+1) K P N, int8 peak = 2 x the
         # measured bf16 figure (sustained: the kernel runs inside a multi-step loop)
         flops = 2.0 * (NITER + 1) * K * P * N
-        peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        fp4 = st.get("operand_bits") == 4
+        # e2m1 operands (kind::mxf4) retire twice the MACs per cycle of u8: peak = 4 x bf16
+        mult = 4.0 if fp4 else 2.0
+        peak = mult * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         achieved = flops / (c_ms * 1e-3) / 1e12
-        kname = "k_dense_contract_pair" if tile_cells == 256 else "k_dense_contract"
+        kname = "k_dense_contract_fp4" if fp4 else ("k_dense_contract_pair" if tile_cells == 256 else "k_dense_contract")
         roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(kname, name),
-                "peak_kind": peaks_kind + " (2 x bf16 sustained = int8 dense)",
-                "peak_burst": 2.0 * peaks["bf16_tflops"], "peak_nominal": 4500.0,
+                "peak_kind": peaks_kind + (" (4 x bf16 sustained = e2m1 dense)" if fp4 else " (2 x bf16 sustained = int8 dense)"),
+                "peak_burst": mult * peaks["bf16_tflops"], "peak_nominal": 9000.0 if fp4 else 4500.0,
                 "ms_per_launch": c_ms / max(gemm_launches, 1), "launches_per_step": int(gemm_launches),
                 "algorithmic_ops_per_launch": flops / max(gemm_launches, 1),
-                "padded_ops_per_step": padded_flops, "share_of_step": share}
+                "padded_ops_per_step": padded_flops, "share_of_step": share,
+                "operand_bits": st.get("operand_bits"), "overflow_columns_per_step": st.get("overflow_columns")}
     else:
         achieved = bytes_alg / (c_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"],
@@ -392,7 +398,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("u8 x u8 -> s32 (tcgen05), %s epilogue" % ("u64 fixed-point / f32 / f64" if st.get("epilogue") == 32 else "f64"))
+        "dtype": ("%s, %s epilogue" % ("e2m1 x e2m1 -> f32 holding exact integers (tcgen05 kind::mxf4)" if st.get("operand_bits") == 4
+                                       else "u8 x u8 -> s32 (tcgen05 kind::i8)",
+                                       "u64 fixed-point / f32 / f64" if st.get("epilogue") == 32 else "f64"))
                  if path == 1 else "int32 sums, f64 epilogue",
         "data": "synthetic",
         "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
@@ -436,6 +444,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
+    ap.add_argument("--lockstep", type=int, default=1, help="e2m1 GEMM: producers of all CTAs start each sub-tile together")
+    ap.add_argument("--fp4", type=int, default=-1, help="dense path: e2m1 operands when representable (-1 / 1) or never (0)")
     ap.add_argument("--chunk", type=int, default=0, help="dense path: cap on cells per GEMM launch (experiment)")
     ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")

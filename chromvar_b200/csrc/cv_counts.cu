@@ -122,7 +122,7 @@ extern "C" void cv_destroy(cv_handle* h) {
                     &h->dev_rm, &h->z_rm, &h->dev_cm, &h->z_cm, &h->varpart, &h->varfinal,
                     &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C, &h->dn_S,
                     &h->dn_abits, &h->dn_invptr, &h->dn_invsrc, &h->dn_E2, &h->dn_ov, &h->dn_winv,
-                    &h->f4_Tq, &h->f4_Sq, &h->f4_ncol, &h->f4_off, &h->f4_colq, &h->f4_colt, &h->f4_info};
+                    &h->f4_Tq, &h->f4_Sq, &h->f4_ncol, &h->f4_off, &h->f4_colq, &h->f4_colt, &h->f4_info, &h->f4_sync};
   for (DevBuf* b : bufs) cv_release(*b);
   for (DevBuf& b : h->bk) cv_release(b);
   for (int i = 0; i < 8; ++i)
@@ -167,6 +167,7 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
     h->opt_epilogue = (int)value;
     return CV_OK;
   }
+  if (!strcmp(key, "dense_lockstep")) { h->opt_lockstep = value != 0; return CV_OK; }
   if (!strcmp(key, "dense_fp4")) { h->opt_fp4 = value < 0 ? -1 : (value ? 1 : 0); return CV_OK; }
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }

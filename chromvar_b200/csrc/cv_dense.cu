@@ -404,7 +404,11 @@ __global__ void k_winv_fixed(const double* __restrict__ etab, int K, int I, uint
     if (v > 4294967295.0) v = 4294967295.0;
     W[(int64_t)k * I + j] = (uint32_t)v;
   }
-  wscale[k] = bad ? 0.0 : ldexp(1.0, -F);
+  // per-annotation constants of the fixed-point epilogue: 2^-F / B (mean), 2^F (1 / sd), 1 / E_0, E_0
+  wscale[4 * k + 0] = bad ? 0.0 : ldexp(1.0, -F) / (double)(I - 1);
+  wscale[4 * k + 1] = bad ? 0.0 : ldexp(1.0, F);
+  wscale[4 * k + 2] = 1.0 / e[0];
+  wscale[4 * k + 3] = e[0];
   // an empty annotation has an all-zero table and all-NA results whatever the arithmetic
   if (bad && e[0] != 0.0) atomicOr(dflags + 4, 1u);
 }
@@ -470,8 +474,8 @@ int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan*
   int64_t chunk = (int64_t)(budget / per_cell / 256.0) * 256;
   if (chunk < 256) { *why = "dense operands do not fit in device memory"; return 0; }
   const int64_t n256 = round_up(h->N, 256);
-  if (want_chunk > 0) chunk = std::min<int64_t>(chunk, round_up(want_chunk, 256));
-  if (h->opt_chunk > 0) chunk = std::min<int64_t>(chunk, round_up(h->opt_chunk, 256));
+  if (h->opt_chunk > 0) chunk = std::min<int64_t>(chunk, round_up(h->opt_chunk, 256));   // "cell_chunk" overrides the caller's wish
+  else if (want_chunk > 0) chunk = std::min<int64_t>(chunk, round_up(want_chunk, 256));
   pl->chunk_cells = std::min(chunk, n256);
   pl->c_bytes = pl->chunk_cells * pl->Ppad;
   pl->sums_bytes = pl->planes > 1 ? pl->chunk_cells * (int64_t)h->K * I * 8 : 0;
@@ -533,9 +537,9 @@ int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows) {
   CV_TRY(cv_ensure(h, h->varpart, (size_t)h->K * ncb_total * 4 * 8));
   cv_span_begin(h, CV_SPAN_LAYOUT);
   CV_TRY(cv_dense_build_rows(h, pl, scatter_rows));
-  CV_TRY(cv_ensure(h, h->dn_winv, (size_t)h->K * pl.I * 4 + (size_t)h->K * 8 + 16));
+  CV_TRY(cv_ensure(h, h->dn_winv, (size_t)h->K * pl.I * 4 + (size_t)h->K * 32 + 16));
   CV_LAUNCH(h, k_winv_fixed, (unsigned)((h->K + 127) / 128), 128, 0, h->etab.as<double>(), (int)h->K, pl.I,
-            h->dn_winv.as<uint32_t>() + 2 * h->K, reinterpret_cast<double*>(h->dn_winv.p),
+            h->dn_winv.as<uint32_t>() + 8 * h->K, reinterpret_cast<double*>(h->dn_winv.p),
             h->flags.as<uint32_t>() + CV_DFLAGS);
   cv_span_end(h);
   h->dn_flops = 0;
@@ -574,8 +578,8 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
   prm.varpart = h->varpart.as<double>();
   prm.obs = keep_sums ? h->obs.as<long long>() : nullptr;
   prm.samp = keep_sums ? h->samp.as<long long>() : nullptr;
-  prm.wscale = reinterpret_cast<const double*>(h->dn_winv.p);            // [K] doubles, then [K][I] u32
-  prm.winv_fx = h->dn_winv.as<uint32_t>() + 2 * K;
+  prm.wscale = reinterpret_cast<const double*>(h->dn_winv.p);            // [K][4] doubles, then [K][I] u32
+  prm.winv_fx = h->dn_winv.as<uint32_t>() + 8 * K;
   prm.sums = h->dn_S.as<long long>();
   prm.sums_ld = (int)pl.chunk_cells;
   prm.sums_c0 = (int)c0;

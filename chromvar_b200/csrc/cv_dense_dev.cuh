@@ -225,6 +225,7 @@ struct DenseParams {
   // number of 256-peak k-blocks of this chunk (main + overflow columns), written on the device
   int Ga, Gb, n_sg;
   const uint32_t* n_kblocks_dev;
+  uint32_t* sync_ctr;        // one counter per (wave of work items, sub-tile): producers start together
 };
 
 struct DWelford { double n, mean, m2; };
@@ -278,6 +279,38 @@ __device__ __forceinline__ void dn_warp_variability(double zv, bool live, int la
     if (mfin) {
       mean = p + s1 / n;
       m2 = s2 - s1 * (s1 / n);
+      if (m2 < 0.0) m2 = 0.0;
+    }
+    w4[0] = n; w4[1] = mean; w4[2] = m2; w4[3] = (double)__popc(mbad);
+  }
+}
+
+// the same with the within-warp sums in fp32 (deviations from the first finite value; 32 terms):
+// two fp64 operations per lane instead of twelve -- fp64 is throttled while the tensor pipe runs
+__device__ __forceinline__ void dn_warp_variability_f32(double zv, bool live, int lane, double* w4) {
+  const unsigned full = 0xffffffffu;
+  const bool fin = live && isfinite(zv);
+  const unsigned mfin = __ballot_sync(full, fin);
+  const unsigned mbad = __ballot_sync(full, live && !fin);
+  double p = 0.0;
+  float s1 = 0.f, s2 = 0.f;
+  if (mfin) {
+    p = __shfl_sync(full, zv, __ffs(mfin) - 1);
+    const float d = fin ? (float)(zv - p) : 0.f;
+    s1 = d;
+    s2 = d * d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(full, s1, o);
+      s2 += __shfl_xor_sync(full, s2, o);
+    }
+  }
+  if (lane == 0) {
+    const double n = (double)__popc(mfin);
+    double mean = 0.0, m2 = 0.0;
+    if (mfin) {
+      mean = p + (double)s1 / n;
+      m2 = (double)s2 - (double)s1 * ((double)s1 / n);
       if (m2 < 0.0) m2 = 0.0;
     }
     w4[0] = n; w4[1] = mean; w4[2] = m2; w4[3] = (double)__popc(mbad);
@@ -357,6 +390,7 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
   DnCell cell = {0.0, 0.0, 0.0, 0.0};
   unsigned long long f_piv = 0ull, f_sumi = 0ull;
   float f_sumsq = 0.f;
+  const double inv_b = 1.0 / (double)prm.B, inv_bm1 = 1.0 / (double)(prm.B - 1);
   int f_obs = 0;
   const int ncols = nk * I;
   for (int col0 = 0; col0 < ncols; col0 += 32) {
@@ -406,17 +440,21 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
             const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
             double devv, zv;
             if (MODE == DN_EPI_FUSED32) {
-              const double E0 = prm.etab[(int64_t)k * I];
-              const double Bd = (double)prm.B;
-              const double scale = prm.wscale[k];
-              const double expected = E0 * fpsv;                                        // :488
-              const double obs_dev = ((double)f_obs - expected) / expected;             // :489
-              const double mean = rf * (scale * ((double)f_sumi / Bd)) - 1.0;           // :511
+              // FP64 issues ~25x slower while the tensor pipe runs, so this tail (once per annotation
+              // and cell) uses a dozen fp64 operations: reciprocals come from tables, the square
+              // root is an fp32 rsqrt + one Newton step (the variance is an fp32 sum anyway)
+              const double4 cst = *reinterpret_cast<const double4*>(prm.wscale + 4 * (int64_t)k);   // 2^-F / B, 2^F, 1 / E0, E0
+              const double expected = cst.w * fpsv;                                                 // :488
+              const double obs_dev = (double)f_obs * (rf * cst.z) - 1.0;                            // :489
+              const double mean = (double)f_sumi * (rf * cst.x) - 1.0;                              // :511
               const double s1 = (double)(long long)(f_sumi - (unsigned long long)prm.B * f_piv);
-              const double var = ((double)f_sumsq - s1 * (s1 / Bd)) / (Bd - 1.0);
-              const double sd = rf * scale * sqrt(var > 0.0 ? var : (var == var ? 0.0 : var));   // :512
-              devv = obs_dev - mean;                                                    // :514
-              zv = devv / sd;                                                           // :515
+              float var = (float)(((double)f_sumsq - s1 * (s1 * inv_b)) * inv_bm1);                 // :512, scaled units
+              var = var > 0.f ? var : (var == var ? 0.f : var);
+              float rs = rsqrtf(var);
+              rs = rs * (1.5f - 0.5f * ((var * rs) * rs));                                          // inf / nan pass through
+              if (var == 0.f) rs = __int_as_float(0x7f800000);
+              devv = obs_dev - mean;                                                                // :514
+              zv = devv * ((fpsv * cst.y) * (double)rs);                                            // :515
               if (empty || expected < 1.0) devv = zv = cv_na_real();
             } else {
               dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
@@ -426,7 +464,8 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
               prm.z_rm[(int64_t)k * prm.N + c] = zv;
             }
             // variability partial of (k, cell block): this warp's 32 cells, then the 4 epilogue warps
-            dn_warp_variability(zv, live, lane, s_wred + (a * 4 + q4) * 4);
+            if (MODE == DN_EPI_FUSED32) dn_warp_variability_f32(zv, live, lane, s_wred + (a * 4 + q4) * 4);
+            else dn_warp_variability(zv, live, lane, s_wred + (a * 4 + q4) * 4);
             j = 0;
             ++a;
           }

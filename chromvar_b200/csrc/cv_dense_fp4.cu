@@ -135,18 +135,27 @@ k_f4_rows_main(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ 
     const uint4 lo = *reinterpret_cast<const uint4*>(tile + r * F4_TQ + c * 32);
     const uint4 hi = *reinterpret_cast<const uint4*>(tile + r * F4_TQ + c * 32 + 16);
     const uint32_t in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    uint32_t out[4];
+    uint32_t out[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) {
-      uint32_t packed = 0u;
+      const uint32_t x = in[wv];
+      if (x == 0u) continue;                        // annotations are a few percent dense
+      uint32_t packed;
+      if ((x & 0xFCFCFCFCu) == 0u) {
+        // every byte is 0..3: code = 2v for v <= 2, 5 for v = 3  ->  2v - (v == 3), per byte, no carries
+        const uint32_t three = x & (x >> 1) & 0x01010101u;
+        const uint32_t c = (x << 1) - three;        // bytes 0, 2, 4, 5
+        packed = (c & 0xFu) | ((c >> 4) & 0xF0u) | ((c >> 8) & 0xF00u) | ((c >> 12) & 0xF000u);
+      } else {
+        packed = 0u;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t v = (in[wv] >> (8 * e)) & 0xFFu;
-        if (v > 4u && v != 6u) atomicMax(Tq + q + wv * 4 + e, f4_nterms(v));
-        packed |= f4_code0(v) << (4 * e);
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t v = (x >> (8 * e)) & 0xFFu;
+          if (v > 4u && v != 6u) atomicMax(Tq + q + wv * 4 + e, f4_nterms(v));
+          packed |= f4_code0(v) << (4 * e);
+        }
       }
-      if (wv & 1) out[wv >> 1] |= packed << 16;
-      else out[wv >> 1] = packed;
+      out[wv >> 1] |= (wv & 1) ? packed << 16 : packed;
     }
     *reinterpret_cast<uint4*>(M4 + ro + (q >> 1)) = make_uint4(out[0], out[1], out[2], out[3]);
   }
@@ -394,10 +403,29 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
         dn_decode_tile(prm.band, prm.n_sg, n_units, item, unit, sg);
         const int yc = (2 * unit + (int)rank) * DN_BLOCK_M;
         for (int half = 0; half < 2; ++half) {
-          if (sg * Gsg + (half ? prm.Ga : 0) >= prm.K) continue;
+          if (sg * Gsg + (half ? prm.Ga : 0) >= prm.K) {
+            // the last super-group may have no second sub-tile: still counted by the others' rendezvous
+            if (prm.sync_ctr) atomicAdd(prm.sync_ctr + (((item - pair_id) / n_pairs) * 2 + half), 1u);
+            continue;
+          }
           const int nh = half ? F4_NB / 2 : F4_NA / 2;                 // stacked rows per CTA
           const int ym = sg * F4_SG_ROWS + (half ? F4_NA : 0) + (int)rank * nh;
           const uint32_t bytes = 2u * (uint32_t)(DN_A_BYTES + nh * DN_BLOCK_K);
+          if (prm.sync_ctr) {
+            // all producers start a sub-tile together: the CTAs that share an operand stream then ask
+            // for the same k-block within a few microseconds and L2 serves all but the first
+            // (without it the pairs drift apart by more than L2 holds and re-read from DRAM)
+            const int64_t wave = (item - pair_id) / n_pairs;
+            const int64_t left = prm.n_tiles - wave * n_pairs;
+            const uint32_t target = 2u * (uint32_t)(left < n_pairs ? left : n_pairs);
+            uint32_t* ctr = prm.sync_ctr + (wave * 2 + half);
+            atomicAdd(ctr, 1u);
+            uint32_t seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+              if (seen < target) __nanosleep(64);
+            } while (seen < target);
+          }
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait_relaxed(empty_bar + s, ph ^ 1u, 32);
             if (rank == 0) mbar_expect_tx(full_bar + s, bytes);
@@ -568,12 +596,22 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   CV_TRY(cv_make_map_u8(h, &map_mb, h->dn_M.p, (uint64_t)pl.rowsM4, (uint64_t)pl.rowb, (uint64_t)pl.rowb, F4_NB / 2));
   DenseParams prm = prm_in;
   prm.Ga = pl.Ga; prm.Gb = pl.Gb; prm.n_sg = pl.n_sg;
+  prm.sync_ctr = nullptr;
+  if (h->opt_lockstep) {
+    CV_TRY(cv_ensure(h, h->f4_sync, 65536 * 4));
+    prm.sync_ctr = h->f4_sync.as<uint32_t>();
+  }
   prm.n_kblocks_dev = info;
   prm.band = h->opt_band > 0 ? h->opt_band : 6;
   const int n_units = (prm.n_cell_blocks + 1) / 2;
   prm.n_tiles = (int64_t)n_units * pl.n_sg;
   int pairs = h->num_sms / 2;
   if (prm.n_tiles < pairs) pairs = (int)prm.n_tiles;
+  if (prm.sync_ctr) {
+    const int64_t waves = (prm.n_tiles + pairs - 1) / pairs;
+    if (2 * waves > 65536) prm.sync_ctr = nullptr;
+    else CV_CUDA(h, cudaMemsetAsync(prm.sync_ctr, 0, (size_t)(2 * waves) * 4, h->stream));
+  }
   if (fixed_point_epilogue) {
     CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract_fp4<DN_EPI_FUSED32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     F4_SMEM_BYTES));

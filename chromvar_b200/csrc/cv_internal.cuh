@@ -150,6 +150,8 @@ struct cv_handle {
   DevBuf f4_colq;    // i32 [Hcap] peak of overflow column x
   DevBuf f4_colt;    // u32 [Hcap] multiplicity term of overflow column x
   DevBuf f4_info;    // u32 [16]: k-blocks and overflow columns of the current chunk
+  DevBuf f4_sync;    // u32 [65536] producer lockstep counters of one GEMM launch
+  int opt_lockstep = 1;        // e2m1 GEMM: TMA producers of all CTAs start each sub-tile together
   int opt_fp4 = -1;            // -1 / 1 use the e2m1 kernel when the problem allows it, 0 never
   bool f4_veto = false;        // this problem turned out not to fit the e2m1 path: retry with u8
   bool dn_fixed_ok = true;
