@@ -334,6 +334,7 @@ k_dense_rows_gather(const uint32_t* __restrict__ Abits, const uint32_t* __restri
 #pragma unroll
     for (int qi = 0; qi < 5; ++qi) sp[qi] = __ldg(ip + min(q0 + qi, (int64_t)P));   // ip[P] = start of the next iteration
     // all sources of the 4 peaks in one loop (less divergence than 4 short loops)
+    // all sources of the 4 peaks in one loop (less divergence than 4 short loops)
     for (uint32_t s = sp[0]; s < sp[4]; ++s) {
       uint32_t wd = __ldg(Aw + __ldg(invsrc + s));
       const int qi = (s >= sp[1]) + (s >= sp[2]) + (s >= sp[3]);

@@ -35,7 +35,7 @@
 #define F4_SG_ROWS (F4_NA + F4_NB)
 #define F4_SF_COL 464                    // first TMEM column of the scale bytes
 #define F4_SMEM_BYTES DN_SMEM2_BYTES
-enum { F4_FAIL_CAPACITY = 1u, F4_FAIL_DUPLICATE = 2u };
+enum { F4_FAIL_CAPACITY = 1u, F4_FAIL_DUPLICATE = 2u, F4_FAIL_NIBBLE = 4u };
 
 // ---- terms over S = {1, 2, 3, 4, 6} ---------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t f4_nterms(uint32_t v) {
@@ -76,14 +76,30 @@ k_f4_zero_pad(uint8_t* __restrict__ M4, int K, int Ga, int Gb, int I, int64_t ro
 }
 
 // ---- operand M4: the P peak columns (gather formulation of cv_dense_build.cu, nibble-packed) ----------------
-// One CTA = 32 annotations (word w) x 1024 peaks of iteration j in shared memory as bytes; on the way
-// out every value becomes the e2m1 code of its term 0, and a value outside S raises T_q.
+// One CTA = 32 annotations (word w) x 1024 peaks of iteration j.  The tile lives in shared memory as
+// 4-bit COUNTS: thread t owns peaks 4t .. 4t+3 = one 16-bit word of every row (no atomics, no bank
+// conflicts), visits only the set bits of each source's membership word, and the tile leaves as
+// 16-byte stores after a SWAR map count -> e2m1 code of term 0 (0,1,2,3 -> 0,2,4,5 without carries;
+// larger counts take the slow path and raise T_q).  A count that would pass 15 is flagged
+// (F4_FAIL_NIBBLE): such an operand goes to the u8 kernel.  The kernel is instruction-bound, hence
+// the packed tile: a quarter of the instructions of the byte tile it replaced.
 #define F4_TQ 1024
+__device__ __forceinline__ uint32_t f4_codes_of_counts(uint32_t x, int64_t q, uint32_t* __restrict__ Tq) {
+  if ((x & 0xCCCCCCCCu) == 0u) return (x << 1) - (x & (x >> 1) & 0x11111111u);       // every count <= 3
+  uint32_t out = 0u;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t v = (x >> (4 * e)) & 0xFu;
+    if (v > 4u && v != 6u) atomicMax(Tq + q + e, f4_nterms(v));
+    out |= f4_code0(v) << (4 * e);
+  }
+  return out;
+}
 __global__ void __launch_bounds__(256)
 k_f4_rows_main(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ invptr,
                const int32_t* __restrict__ invsrc, int K, int P, int B, int Ga, int Gb, int64_t rowb, int64_t Ppad4,
-               uint8_t* __restrict__ M4, uint32_t* __restrict__ Tq) {
-  __shared__ __align__(16) uint8_t tile[32 * F4_TQ];
+               uint8_t* __restrict__ M4, uint32_t* __restrict__ Tq, uint32_t* __restrict__ dflags) {
+  __shared__ __align__(16) uint16_t tile[32 * (F4_TQ / 4)];
   __shared__ long long s_row[32];
   const int j = blockIdx.y, w = blockIdx.z;
   const int I = B + 1;
@@ -94,12 +110,12 @@ k_f4_rows_main(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ 
   {
     uint4* t4 = reinterpret_cast<uint4*>(tile);
 #pragma unroll
-    for (int i = 0; i < (32 * F4_TQ / 16) / 256; ++i) t4[i * 256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < (32 * (F4_TQ / 4) * 2 / 16) / 256; ++i) t4[i * 256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   const uint32_t* __restrict__ Aw = Abits + (int64_t)w * P;
   const int64_t q0 = (int64_t)blockIdx.x * F4_TQ + threadIdx.x * 4;
-  uint8_t* col = tile + threadIdx.x * 4;
+  uint16_t* col = tile + threadIdx.x;
   if (j == 0) {
 #pragma unroll
     for (int qi = 0; qi < 4; ++qi) {
@@ -107,7 +123,7 @@ k_f4_rows_main(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ 
       while (wd) {
         const int b = __ffs(wd) - 1;
         wd &= wd - 1;
-        col[b * F4_TQ + qi] = 1;
+        col[b * (F4_TQ / 4)] |= (uint16_t)(1u << (4 * qi));
       }
     }
   } else if (q0 < P) {
@@ -115,49 +131,33 @@ k_f4_rows_main(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ 
     uint32_t sp[5];
 #pragma unroll
     for (int qi = 0; qi < 5; ++qi) sp[qi] = __ldg(ip + min(q0 + qi, (int64_t)P));
+    bool sat = false;
     for (uint32_t s = sp[0]; s < sp[4]; ++s) {
       uint32_t wd = __ldg(Aw + __ldg(invsrc + s));
-      const int qi = (s >= sp[1]) + (s >= sp[2]) + (s >= sp[3]);
+      const int sh = 4 * ((s >= sp[1]) + (s >= sp[2]) + (s >= sp[3]));
       while (wd) {
         const int b = __ffs(wd) - 1;
         wd &= wd - 1;
-        col[b * F4_TQ + qi] += 1;
+        const uint32_t old = col[b * (F4_TQ / 4)];
+        sat |= ((old >> sh) & 0xFu) == 0xFu;
+        col[b * (F4_TQ / 4)] = (uint16_t)(old + (1u << sh));
       }
     }
+    if (sat) atomicOr(dflags + 5, F4_FAIL_NIBBLE);
   }
   __syncthreads();
-  // rows out: 32 peaks -> 16 bytes per store, 512 bytes per row
+  // rows out: 16 bytes = 32 peaks per store, 512 bytes per row
   for (int i = threadIdx.x; i < 32 * (F4_TQ / 32); i += 256) {
     const int r = i / (F4_TQ / 32), c = i % (F4_TQ / 32);
     const long long ro = s_row[r];
     const int64_t q = (int64_t)blockIdx.x * F4_TQ + c * 32;
     if (ro < 0 || q >= Ppad4) continue;
-    const uint4 lo = *reinterpret_cast<const uint4*>(tile + r * F4_TQ + c * 32);
-    const uint4 hi = *reinterpret_cast<const uint4*>(tile + r * F4_TQ + c * 32 + 16);
-    const uint32_t in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    uint32_t out[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int wv = 0; wv < 8; ++wv) {
-      const uint32_t x = in[wv];
-      if (x == 0u) continue;                        // annotations are a few percent dense
-      uint32_t packed;
-      if ((x & 0xFCFCFCFCu) == 0u) {
-        // every byte is 0..3: code = 2v for v <= 2, 5 for v = 3  ->  2v - (v == 3), per byte, no carries
-        const uint32_t three = x & (x >> 1) & 0x01010101u;
-        const uint32_t c = (x << 1) - three;        // bytes 0, 2, 4, 5
-        packed = (c & 0xFu) | ((c >> 4) & 0xF0u) | ((c >> 8) & 0xF00u) | ((c >> 12) & 0xF000u);
-      } else {
-        packed = 0u;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t v = (x >> (8 * e)) & 0xFFu;
-          if (v > 4u && v != 6u) atomicMax(Tq + q + wv * 4 + e, f4_nterms(v));
-          packed |= f4_code0(v) << (4 * e);
-        }
-      }
-      out[wv >> 1] |= (wv & 1) ? packed << 16 : packed;
-    }
-    *reinterpret_cast<uint4*>(M4 + ro + (q >> 1)) = make_uint4(out[0], out[1], out[2], out[3]);
+    uint4 x = *reinterpret_cast<const uint4*>(tile + r * (F4_TQ / 4) + c * 8);
+    x.x = f4_codes_of_counts(x.x, q, Tq);
+    x.y = f4_codes_of_counts(x.y, q + 8, Tq);
+    x.z = f4_codes_of_counts(x.z, q + 16, Tq);
+    x.w = f4_codes_of_counts(x.w, q + 24, Tq);
+    *reinterpret_cast<uint4*>(M4 + ro + (q >> 1)) = x;
   }
 }
 
@@ -206,18 +206,19 @@ __global__ void __launch_bounds__(256)
 k_f4_rows_ov(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ invptr, const int32_t* __restrict__ invsrc,
              const int32_t* __restrict__ colq, const uint32_t* __restrict__ colt, const uint32_t* __restrict__ info,
              int K, int P, int B, int Ga, int Gb, int64_t rowb, int64_t Pb, uint8_t* __restrict__ M4) {
-  __shared__ uint8_t tile[32 * 256];
+  __shared__ __align__(16) uint8_t tile[32 * 256];
   __shared__ uint8_t s_t[256];
   __shared__ long long s_row[32];
   const uint32_t h = info[1];
-  const uint32_t x0 = blockIdx.x * 256u;
-  if (x0 >= h) return;                                // columns past the last used k-block are never read
   const int j = blockIdx.y, w = blockIdx.z;
   const int I = B + 1;
   if (threadIdx.x < 32) {
     const int k = w * 32 + threadIdx.x;
     s_row[threadIdx.x] = k < K ? f4_row(k, j, Ga, Gb, I) * rowb : -1ll;
   }
+  // columns past the last used k-block are never read
+  for (uint32_t x0 = blockIdx.x * 256u; x0 < h; x0 += gridDim.x * 256u) {
+  __syncthreads();
   for (int i = threadIdx.x; i < 32 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
   __syncthreads();
   const uint32_t x = x0 + threadIdx.x;
@@ -249,14 +250,22 @@ k_f4_rows_ov(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ in
   }
   s_t[threadIdx.x] = (uint8_t)min(tt, 255u);
   __syncthreads();
-  // 256 columns = 128 bytes per row (columns at or past h in this block read as zero)
-  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
-    const int r = i >> 7, cb = i & 127;
+  // 256 columns = 128 bytes per row (columns at or past h in this block read as zero); 8 columns per item
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int r = i >> 5, cw = i & 31;
     const long long ro = s_row[r];
     if (ro < 0) continue;
-    const uint32_t v0 = tile[r * 256 + 2 * cb], v1 = tile[r * 256 + 2 * cb + 1];
-    const uint32_t byte = f4_code(f4_term(v0, s_t[2 * cb])) | (f4_code(f4_term(v1, s_t[2 * cb + 1])) << 4);
-    M4[ro + Pb + (x0 >> 1) + cb] = (uint8_t)byte;
+    const uint2 v8 = *reinterpret_cast<const uint2*>(tile + r * 256 + 8 * cw);
+    uint32_t out = 0u;
+    if (v8.x | v8.y) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t v = ((e < 4 ? v8.x : v8.y) >> (8 * (e & 3))) & 0xFFu;
+        if (v) out |= f4_code(f4_term(v, s_t[8 * cw + e])) << (4 * e);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(M4 + ro + Pb + (x0 >> 1) + 4 * cw) = out;
+  }
   }
 }
 
@@ -547,7 +556,7 @@ int cv_f4_build_rows(cv_handle* h, const DensePlan& pl) {
   dim3 grid((unsigned)((pl.Ppad4 + F4_TQ - 1) / F4_TQ), (unsigned)I, (unsigned)Kw);
   CV_LAUNCH(h, k_f4_rows_main, grid, 256, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
             h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, pl.Ga, pl.Gb, pl.rowb, pl.Ppad4, h->dn_M.as<uint8_t>(),
-            h->f4_Tq.as<uint32_t>());
+            h->f4_Tq.as<uint32_t>(), h->flags.as<uint32_t>() + CV_DFLAGS);
   return CV_OK;
 }
 
@@ -573,7 +582,7 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   CV_LAUNCH(h, k_f4_collist, (unsigned)((P + 255) / 256), 256, 0, h->f4_off.as<uint32_t>(), h->f4_Tq.as<uint32_t>(), info,
             (int)P, h->f4_colq.as<int32_t>(), h->f4_colt.as<uint32_t>());
   {
-    dim3 grid((unsigned)(pl.Hcap / 256), (unsigned)I, (unsigned)Kw);
+    dim3 grid((unsigned)std::min<int64_t>(pl.Hcap / 256, 8), (unsigned)I, (unsigned)Kw);
     CV_LAUNCH(h, k_f4_rows_ov, grid, 256, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
               h->dn_invsrc.as<int32_t>(), h->f4_colq.as<int32_t>(), h->f4_colt.as<uint32_t>(), info, (int)K, (int)P, B,
               pl.Ga, pl.Gb, pl.rowb, Pb, h->dn_M.as<uint8_t>());

@@ -179,3 +179,25 @@ def test_fp4_duplicate_row_index_in_a_column_falls_back(fp4_engine):
     assert fp4_engine.stats()["operand_bits"] == 8
     ref = orc.compute_deviations_core(Cd, [np.asarray(s) for s in sets], bg, e2, intermediate=True)
     assert np.array_equal(got["observed"], ref["observed"])
+
+
+def test_fp4_falls_back_when_an_operand_entry_exceeds_a_nibble(fp4_engine):
+    """40 peaks of one set drawn to the same background peak: the operand entry 40 does not fit the
+    4-bit tile of the builder: flagged on the device, redone on u8"""
+    C, P, N, bg, e, ptr, idx, sets = _problem([1, 2, 3])
+    bg = bg.copy()
+    bg[:40, 3] = 17
+    sets = list(sets) + [np.arange(1, 61, dtype=np.int32)]
+    ptr, idx = sets_to_csr(sets)
+    fp4_engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    fp4_engine.set_option("dense_fp4", 1)
+    got = fp4_engine.deviations(ptr, idx, bg, e, sums=True)
+    assert fp4_engine.stats()["operand_bits"] == 8
+    ref = orc.compute_deviations_core(C, [np.asarray(s) for s in sets], bg, e, intermediate=True)
+    check_against_oracle(got, ref)
+    # 12 sources on one destination still fit (terms 6 + 6)
+    bg[:40, 3] = np.arange(40) % 4 + 17
+    got = fp4_engine.deviations(ptr, idx, bg, e, sums=True)
+    assert fp4_engine.stats()["operand_bits"] == 4 and fp4_engine.stats()["overflow_columns"] > 0
+    ref = orc.compute_deviations_core(C, [np.asarray(s) for s in sets], bg, e, intermediate=True)
+    check_against_oracle(got, ref)
