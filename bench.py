@@ -411,7 +411,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
                 "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
-                "gemm_kernel": "k_dense_contract_pair" if e2e_stats["cell_tile"] == 256 else
+                "gemm_kernel": ("k_dense_contract_fp4" if e2e_stats.get("operand_bits") == 4 else "k_dense_contract_pair") if e2e_stats["cell_tile"] == 256 else
                 ("k_dense_contract" if e2e_stats["path"] == 1 else "k_contract"),
                 "cell_chunks": int(e2e_stats["n_cell_tiles"]), "ms_each_step": [round(t, 2) for t in e2e_each],
                 "ms_inside_library": [round(t, 2) for t in e2e_lib],

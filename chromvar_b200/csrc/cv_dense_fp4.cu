@@ -202,12 +202,18 @@ k_f4_collist(const uint32_t* __restrict__ off, const uint32_t* __restrict__ Tq, 
 }
 
 // ---- operand M4: the overflow columns of this chunk (term t of the multiplicity of peak colq[x]) ----------------
+// Same construction as k_f4_rows_main: 32 annotations x 1024 overflow columns of iteration j per CTA
+// iteration, 4-bit counts, thread t owns columns 4t .. 4t+3.  Column x holds term colt[x] of the
+// count; terms past the first are zero unless the count is outside S.
+#define F4_OV_COLS 1024
 __global__ void __launch_bounds__(256)
 k_f4_rows_ov(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ invptr, const int32_t* __restrict__ invsrc,
              const int32_t* __restrict__ colq, const uint32_t* __restrict__ colt, const uint32_t* __restrict__ info,
-             int K, int P, int B, int Ga, int Gb, int64_t rowb, int64_t Pb, uint8_t* __restrict__ M4) {
-  __shared__ __align__(16) uint8_t tile[32 * 256];
-  __shared__ uint8_t s_t[256];
+             int K, int P, int B, int Ga, int Gb, int64_t rowb, int64_t Pb, uint8_t* __restrict__ M4,
+             uint32_t* __restrict__ dflags) {
+  __shared__ __align__(16) uint16_t tile[32 * (F4_OV_COLS / 4)];
+  __shared__ uint8_t s_t[F4_OV_COLS];
+  __shared__ uint32_t s_first[F4_OV_COLS / 8];      // nibble mask of the columns holding term 0
   __shared__ long long s_row[32];
   const uint32_t h = info[1];
   const int j = blockIdx.y, w = blockIdx.z;
@@ -216,56 +222,72 @@ k_f4_rows_ov(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ in
     const int k = w * 32 + threadIdx.x;
     s_row[threadIdx.x] = k < K ? f4_row(k, j, Ga, Gb, I) * rowb : -1ll;
   }
-  // columns past the last used k-block are never read
-  for (uint32_t x0 = blockIdx.x * 256u; x0 < h; x0 += gridDim.x * 256u) {
-  __syncthreads();
-  for (int i = threadIdx.x; i < 32 * 256 / 4; i += 256) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
-  __syncthreads();
-  const uint32_t x = x0 + threadIdx.x;
-  uint32_t tt = 0u;
-  if (x < h) {
-    const int q = colq[x];
-    tt = colt[x];
-    const uint32_t* __restrict__ Aw = Abits + (int64_t)w * P;
-    uint8_t* col = tile + threadIdx.x;
-    if (j == 0) {
-      uint32_t wd = __ldg(Aw + q);
-      while (wd) {
-        const int b = __ffs(wd) - 1;
-        wd &= wd - 1;
-        col[b * 256] = 1;
-      }
-    } else {
-      const uint32_t* __restrict__ ip = invptr + (int64_t)(j - 1) * P;
-      const uint32_t s1 = __ldg(ip + q + 1);
-      for (uint32_t s = __ldg(ip + q); s < s1; ++s) {
-        uint32_t wd = __ldg(Aw + __ldg(invsrc + s));
+  const uint32_t* __restrict__ Aw = Abits + (int64_t)w * P;
+  const uint32_t* __restrict__ ip = invptr + (int64_t)(j > 0 ? j - 1 : 0) * P;
+  const uint32_t hpad = (h + F4_KPEAKS - 1) / F4_KPEAKS * F4_KPEAKS;     // columns past the last used k-block are never read
+  for (uint32_t x0 = blockIdx.x * F4_OV_COLS; x0 < hpad; x0 += gridDim.x * F4_OV_COLS) {
+    __syncthreads();
+    {
+      uint4* t4 = reinterpret_cast<uint4*>(tile);
+#pragma unroll
+      for (int i = 0; i < (32 * (F4_OV_COLS / 4) * 2 / 16) / 256; ++i) t4[i * 256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    uint16_t* col = tile + threadIdx.x;
+    bool sat = false;
+    uint32_t tt4 = 0u, first = 0u;
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      const uint32_t x = x0 + 4 * threadIdx.x + qi;
+      if (x >= h) { first |= 0xFu << (4 * qi); continue; }          // zero columns: any map gives 0
+      const int q = colq[x];
+      const uint32_t tt = min(colt[x], 255u);
+      tt4 |= tt << (8 * qi);
+      if (tt == 0u) first |= 0xFu << (4 * qi);
+      const int sh = 4 * qi;
+      if (j == 0) {
+        uint32_t wd = __ldg(Aw + q);
         while (wd) {
           const int b = __ffs(wd) - 1;
           wd &= wd - 1;
-          col[b * 256] += 1;
+          col[b * (F4_OV_COLS / 4)] |= (uint16_t)(1u << sh);
+        }
+      } else {
+        const uint32_t s1 = __ldg(ip + q + 1);
+        for (uint32_t s = __ldg(ip + q); s < s1; ++s) {
+          uint32_t wd = __ldg(Aw + __ldg(invsrc + s));
+          while (wd) {
+            const int b = __ffs(wd) - 1;
+            wd &= wd - 1;
+            const uint32_t old = col[b * (F4_OV_COLS / 4)];
+            sat |= ((old >> sh) & 0xFu) == 0xFu;
+            col[b * (F4_OV_COLS / 4)] = (uint16_t)(old + (1u << sh));
+          }
         }
       }
     }
-  }
-  s_t[threadIdx.x] = (uint8_t)min(tt, 255u);
-  __syncthreads();
-  // 256 columns = 128 bytes per row (columns at or past h in this block read as zero); 8 columns per item
-  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-    const int r = i >> 5, cw = i & 31;
-    const long long ro = s_row[r];
-    if (ro < 0) continue;
-    const uint2 v8 = *reinterpret_cast<const uint2*>(tile + r * 256 + 8 * cw);
-    uint32_t out = 0u;
-    if (v8.x | v8.y) {
+    if (sat) atomicOr(dflags + 5, F4_FAIL_NIBBLE);
+    reinterpret_cast<uint32_t*>(s_t)[threadIdx.x] = tt4;
+    reinterpret_cast<uint16_t*>(s_first)[threadIdx.x] = (uint16_t)first;
+    __syncthreads();
+    // rows out: 8 columns = one 32-bit word per item, 512 bytes per row
+    for (int i = threadIdx.x; i < 32 * (F4_OV_COLS / 8); i += 256) {
+      const int r = i / (F4_OV_COLS / 8), cw = i % (F4_OV_COLS / 8);
+      const long long ro = s_row[r];
+      if (ro < 0 || x0 + 8u * cw >= hpad) continue;
+      const uint32_t x = reinterpret_cast<const uint32_t*>(tile + r * (F4_OV_COLS / 4))[cw];
+      uint32_t out = 0u;
+      if ((x & 0xCCCCCCCCu) == 0u) {
+        out = ((x << 1) - (x & (x >> 1) & 0x11111111u)) & s_first[cw];      // counts <= 3: term 0 only
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t v = ((e < 4 ? v8.x : v8.y) >> (8 * (e & 3))) & 0xFFu;
-        if (v) out |= f4_code(f4_term(v, s_t[8 * cw + e])) << (4 * e);
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t v = (x >> (4 * e)) & 0xFu;
+          if (v) out |= f4_code(f4_term(v, s_t[8 * cw + e])) << (4 * e);
+        }
       }
+      *reinterpret_cast<uint32_t*>(M4 + ro + Pb + (x0 >> 1) + 4 * cw) = out;
     }
-    *reinterpret_cast<uint32_t*>(M4 + ro + Pb + (x0 >> 1) + 4 * cw) = out;
-  }
   }
 }
 
@@ -582,10 +604,10 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   CV_LAUNCH(h, k_f4_collist, (unsigned)((P + 255) / 256), 256, 0, h->f4_off.as<uint32_t>(), h->f4_Tq.as<uint32_t>(), info,
             (int)P, h->f4_colq.as<int32_t>(), h->f4_colt.as<uint32_t>());
   {
-    dim3 grid((unsigned)std::min<int64_t>(pl.Hcap / 256, 8), (unsigned)I, (unsigned)Kw);
+    dim3 grid((unsigned)std::min<int64_t>((pl.Hcap + F4_OV_COLS - 1) / F4_OV_COLS, 8), (unsigned)I, (unsigned)Kw);
     CV_LAUNCH(h, k_f4_rows_ov, grid, 256, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
               h->dn_invsrc.as<int32_t>(), h->f4_colq.as<int32_t>(), h->f4_colt.as<uint32_t>(), info, (int)K, (int)P, B,
-              pl.Ga, pl.Gb, pl.rowb, Pb, h->dn_M.as<uint8_t>());
+              pl.Ga, pl.Gb, pl.rowb, Pb, h->dn_M.as<uint8_t>(), dflags);
   }
   {
     const int budget = h->max_smem_optin - 2048;

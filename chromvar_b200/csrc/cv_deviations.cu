@@ -571,10 +571,10 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   int use_dense = 0;
   DensePlan pl;
   {
-    // about four GEMM launches per call: host copies overlap them chunk by chunk, and four short
-    // launches of the CTA-pair kernel also finish sooner than one long one (22.3 vs 24.5 ms on
-    // config 2, profiles/r01h); none smaller than a few waves of tiles
-    const int64_t want_chunk = std::max<int64_t>((N + 3) / 4, 1024);
+    // about three GEMM launches per call: host copies overlap them chunk by chunk (config 2, e2m1
+    // kernel: e2e 20.2 / 19.6 / 22.4 ms with 4 / 3 / 2 chunks, kernels alone 17.5 / 17.0 / 16.6 ms;
+    // profiles/r01p); none smaller than a few waves of tiles
+    const int64_t want_chunk = std::max<int64_t>((N + 2) / 3, 1024);
     CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
   }
 
@@ -981,7 +981,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
       DensePlan pl;
       int use_dense = 0;
       const int opt = h->opt_path;
-      int rc = choose_path(h, 0u, std::max<int64_t>((N + 3) / 4, 1024), false, &pl, &use_dense);
+      int rc = choose_path(h, 0u, std::max<int64_t>((N + 2) / 3, 1024), false, &pl, &use_dense);
       ok = rc == CV_OK && use_dense && (opt == 2 || cv_dense_cost_ms(h, pl) > 2.0);   // tiny problems: plain sequence
     }
     try_stream = ok;
