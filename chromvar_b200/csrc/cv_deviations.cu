@@ -556,6 +556,39 @@ static int choose_path(cv_handle* h, uint32_t max_val, int64_t want_chunk, bool 
   return CV_OK;
 }
 
+// Cell-chunk boundaries of the dense path (multiples of 256 cells, each <= pl.chunk_cells).
+static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int64_t N) {
+  const int64_t chunk = pl.chunk_cells;
+  std::vector<int64_t> b;
+  const int64_t U = (N + 255) / 256, maxU = chunk / 256;
+  const int n_min = (int)((U + maxU - 1) / maxU);
+  const int n = std::max<int>(n_min, (int)std::min<int64_t>(3, U));
+  if (h->opt_chunk > 0 || !pl.pair || n != 3 || U < 6 || U > 4096) {
+    for (int64_t c = 0; c < N; c += chunk) b.push_back(c);
+    b.push_back(N);
+    return b;
+  }
+  const int64_t ipu = pl.fp4 ? pl.n_sg : pl.n_groups;            // work items per 256-cell unit
+  const int64_t pairs = std::max(1, h->num_sms / 2);
+  auto waves = [&](int64_t u) { return (u * ipu + pairs - 1) / pairs; };
+  const int64_t minU = std::max<int64_t>(1, U / 6);
+  int64_t best = -1, ba = 0, bb = 0;
+  for (int64_t a = minU; a <= maxU; ++a)
+    for (int64_t m = minU; m <= maxU; ++m) {
+      const int64_t c = U - a - m;
+      if (c < minU || c > maxU) continue;
+      const int64_t cost = (waves(a) + waves(m) + waves(c)) * 4096 + a * 8 + (m > c ? 1 : 0);   // fewest waves, then the smallest first chunk
+      if (best < 0 || cost < best) { best = cost; ba = a; bb = m; }
+    }
+  if (best < 0) {
+    for (int64_t c = 0; c < N; c += chunk) b.push_back(c);
+    b.push_back(N);
+    return b;
+  }
+  b = {0, ba * 256, (ba + bb) * 256, N};
+  return b;
+}
+
 // Every kernel of the path on resident (or arriving) inputs.
 static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums, DevIO* io) {
   const int64_t P = h->P, N = h->N, K = h->K;
@@ -568,13 +601,13 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   int64_t set_max = 0;
   for (int64_t k = 0; k < K; ++k) set_max = std::max(set_max, h->h_annoptr[k + 1] - h->h_annoptr[k]);
 
-  int use_dense = 0;
+  int use_dense = 0, dense_chunks_used = 0;
   DensePlan pl;
   {
     // about three GEMM launches per call: host copies overlap them chunk by chunk (config 2, e2m1
     // kernel: e2e 20.2 / 19.6 / 22.4 ms with 4 / 3 / 2 chunks, kernels alone 17.5 / 17.0 / 16.6 ms;
-    // profiles/r01p); none smaller than a few waves of tiles
-    const int64_t want_chunk = std::max<int64_t>((N + 2) / 3, 1024);
+    // profiles/r01p); buffers for up to half the cells, boundaries from chunk_bounds()
+    const int64_t want_chunk = std::max<int64_t>((N + 1) / 2, 1024);
     CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
   }
 
@@ -608,14 +641,19 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   bool wide = false;
   if (use_dense) {
     const int64_t chunk = pl.chunk_cells;
-    const int n_chunks = (int)((N + chunk - 1) / chunk);
+    // chunk boundaries: uniform when the caller fixed the chunk ("cell_chunk"); otherwise about three
+    // chunks whose work items fill whole waves of CTA pairs (config 2: 40 units of 256 cells x 97
+    // super-groups on 74 pairs: 8 + 16 + 16 units = 53 waves, 14 + 13 + 13 = 55), the small one first
+    std::vector<int64_t> bounds = chunk_bounds(h, pl, N);
+    const int n_chunks = (int)bounds.size() - 1;
+    dense_chunks_used = n_chunks;
     std::vector<cudaEvent_t> ev_up((size_t)n_chunks), ev_done((size_t)n_chunks), ev_dn((size_t)n_chunks);
     for (int i = 0; i < n_chunks; ++i) { ev_up[i] = pool_event(h); ev_done[i] = pool_event(h); ev_dn[i] = pool_event(h); }
     const bool trace = getenv("CV_TRACE") != nullptr;
     cudaEvent_t ev_t0 = pool_event(h), ev_prep = pool_event(h);
     CV_CUDA(h, cudaEventRecord(ev_t0, h->stream));         // origin of the timeline; orders the upload stream
-    auto lo = [&](int i) { return (int64_t)i * chunk; };
-    auto hi = [&](int i) { return std::min<int64_t>(N, (int64_t)(i + 1) * chunk); };
+    auto lo = [&](int i) { return bounds[(size_t)i]; };
+    auto hi = [&](int i) { return bounds[(size_t)i + 1]; };
     CV_TRY(cv_dense_prepare(h, pl, 0));                       // operand M + tables: cell independent
     if (trace) cudaEventRecord(ev_prep, h->stream);
     if (streaming) {
@@ -846,7 +884,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     h->st.path = 1;
     h->st.acc_bytes = 4;
     h->st.cell_tile = pl.pair ? 256 : 128;
-    h->st.n_cell_tiles = (int)((N + pl.chunk_cells - 1) / pl.chunk_cells);
+    h->st.n_cell_tiles = dense_chunks_used;
     h->st.planes = pl.planes;
     h->st.operand_bits = pl.fp4 ? 4 : 8;
     h->st.overflow_columns = pl.fp4 ? (int32_t)hf[CV_DFLAGS + 6] : 0;
@@ -981,7 +1019,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
       DensePlan pl;
       int use_dense = 0;
       const int opt = h->opt_path;
-      int rc = choose_path(h, 0u, std::max<int64_t>((N + 2) / 3, 1024), false, &pl, &use_dense);
+      int rc = choose_path(h, 0u, std::max<int64_t>((N + 1) / 2, 1024), false, &pl, &use_dense);
       ok = rc == CV_OK && use_dense && (opt == 2 || cv_dense_cost_ms(h, pl) > 2.0);   // tiny problems: plain sequence
     }
     try_stream = ok;
