@@ -58,15 +58,57 @@ def ncu_traffic(kernel, workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled every 100 ms during the timed region.  NVML in-process
+    (nvmlInit happens in the constructor, before any timed work: spawning nvidia-smi inside the timed
+    region takes driver locks for tens of milliseconds and shows up as slow steps); nvidia-smi -lms
+    only when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples = index, None, [], []
+        self.nv = self.dev = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES: `index` is the CUDA ordinal
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        masks = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                self.samples.append((sm, [n for n, m in masks if r & m]))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -82,6 +124,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            if not self.samples:
+                return None
+            reasons = set()
+            for _, rs in self.samples:
+                reasons.update(rs)
+            return {"sm_mhz": float(np.median([x for x, _ in self.samples])), "sm_max_mhz": self.max_sm,
+                    "samples": len(self.samples), "reasons": sorted(reasons), "source": "nvml"}
         if not self.proc:
             return None
         time.sleep(0.25)
@@ -107,7 +159,7 @@ class ClockSampler:
         if not sm:
             return None
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def make_workload(rank, cells, quick, workload=None):
@@ -302,9 +354,9 @@ def run_ours(args):
         upd, bytes_alg, path = st["contract_updates"], st["contract_bytes"], st["path"]
         tile_cells, gemm_launches, padded_flops = st["cell_tile"], st["n_cell_tiles"] * max(st["planes"], 1), st["contract_flops"]
     barrier()
-    clocks = sampler.stop()
     launches = eng.stats()["kernel_launches"] - launches0
     total_ms = float(np.sum(step_ms))
+    log("[bench] rank %d: ms of each timed step: %s" % (rank, [round(x, 2) for x in step_ms]))
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -344,6 +396,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     gc.enable()
+    clocks = sampler.stop()                              # sampled across both timed regions
     e2e_stats = eng.stats()
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if ws > 1:

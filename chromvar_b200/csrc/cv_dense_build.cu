@@ -562,6 +562,20 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   return CV_OK;
 }
 
+// The u8 operand rows again, from the bit columns / inverse background map a gather build left on
+// the device (the e2m1 attempt turned out not to fit): no tables, no auxiliary stream.
+int cv_dense_rebuild_rows_u8(cv_handle* h, const DensePlan& pl) {
+  const int64_t P = h->P, K = h->K;
+  const int B = h->B, I = B + 1, G = pl.G;
+  const int64_t Kw = (K + 31) / 32;
+  if (G * I < DB_BLOCK_N || K % G)
+    CV_LAUNCH(h, k_zero_pad_rows, pl.n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, pl.Ppad);
+  dim3 grid((unsigned)((pl.Ppad + GR_TQ - 1) / GR_TQ), (unsigned)I, (unsigned)Kw);
+  CV_LAUNCH(h, k_dense_rows_gather, grid, GR_THREADS, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
+            h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, G, pl.Ppad, h->dn_M.as<uint8_t>());
+  return CV_OK;
+}
+
 // Cd rows [0, rows) <- cells [c0, c0 + rows), digit plane `shift` / 8.  Asynchronous.
 int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift) {
   const int budget = h->max_smem_optin - 2048;

@@ -161,6 +161,17 @@ k_f4_rows_main(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ 
   }
 }
 
+// overflow columns the operand alone needs (sum of T_q - 1): when they already fill the reserve the
+// caller switches to the u8 kernel before any cell is touched (dense k-mer annotations: nearly every
+// peak meets a multiplicity of 5 in one of the K x B rows)
+__global__ void __launch_bounds__(256)
+k_f4_tq_total(const uint32_t* __restrict__ Tq, int P, uint32_t* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = (q < P && Tq[q] > 1u) ? Tq[q] - 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
 // ---- per cell chunk: which peaks need overflow columns ---------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_f4_terms(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx, const uint32_t* __restrict__ val,
@@ -550,7 +561,9 @@ int cv_f4_plan(cv_handle* h, DensePlan* pl) {
   pl->Gb = F4_NB / I;
   pl->n_sg = (int)((h->K + pl->Ga + pl->Gb - 1) / (pl->Ga + pl->Gb));
   pl->Ppad4 = f4_round_up(h->P, F4_KPEAKS);
-  pl->Hcap = std::max<int64_t>(1024, f4_round_up(h->P / 4, F4_KPEAKS));
+  // reserve of overflow columns: as many as there are peaks (the operand rows are then as long as
+  // the u8 rows); unused k-blocks of the reserve are never read, a chunk that needs more goes to u8
+  pl->Hcap = std::max<int64_t>(1024, pl->Ppad4);
   pl->rowb = (pl->Ppad4 + pl->Hcap) / 2;
   pl->rowsM4 = (int64_t)pl->n_sg * F4_SG_ROWS;
   pl->fp4 = 1;
@@ -579,13 +592,15 @@ int cv_f4_build_rows(cv_handle* h, const DensePlan& pl) {
   CV_LAUNCH(h, k_f4_rows_main, grid, 256, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
             h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, pl.Ga, pl.Gb, pl.rowb, pl.Ppad4, h->dn_M.as<uint8_t>(),
             h->f4_Tq.as<uint32_t>(), h->flags.as<uint32_t>() + CV_DFLAGS);
+  CV_LAUNCH(h, k_f4_tq_total, (unsigned)((P + 255) / 256), 256, 0, h->f4_Tq.as<uint32_t>(), (int)P,
+            h->flags.as<uint32_t>() + CV_DFLAGS + 7);
   return CV_OK;
 }
 
 // Cells [c0, c0 + rows) (c1 = first cell past the chunk's real cells): overflow columns of the chunk, both
 // operands' overflow parts, Cd4, GEMM + fused epilogue.  prm: the launch parameters cv_dense_chunk filled.
 int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, int64_t c0, int64_t c1, int64_t rows,
-                int fixed_point_epilogue) {
+                int fixed_point_epilogue, int check_now) {
   const int64_t P = h->P, K = h->K;
   const int B = h->B, I = B + 1;
   const int64_t Kw = (K + 31) / 32;
@@ -620,6 +635,17 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
               h->dn_C.as<uint8_t>(), h->work_ctr.as<uint32_t>() + 1, dflags);
   }
   cv_span_end(h);
+  if (check_now) {
+    // first chunk of a call: does it fit the reserve?  (one short sync before the first GEMM; later
+    // chunks are only checked at the end of the call)
+    uint32_t flag = 0;
+    CV_CUDA(h, cudaMemcpyAsync(&flag, dflags + 5, 4, cudaMemcpyDeviceToHost, h->stream));
+    CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+      h->f4_veto = true;
+      CV_FAIL(h, CV_ERR_UNSUPPORTED, "counts not representable on the e2m1 path (flags %u)", flag);
+    }
+  }
   cv_span_begin(h, CV_SPAN_CONTRACT);
   CUtensorMap map_c, map_ma, map_mb;
   CV_TRY(cv_make_map_u8(h, &map_c, h->dn_C.p, (uint64_t)rows, (uint64_t)pl.rowb, (uint64_t)pl.rowb, DN_BLOCK_M));

@@ -685,18 +685,20 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       if (soft && h->opt_path != 2 && !streaming) use_dense = 0;     // exact fallback below
       else { if (io) io->soft_fail = soft; return rc; }
     }
-    if (use_dense && pl.fp4 && !streaming &&
-        !((double)h->max_cell_tot * (double)h->dn_maxmult < 16777216.0)) {
-      // sums may not fit a float exactly: u8 operands / s32 accumulators instead
-      CV_CUDA(h, cudaStreamSynchronize(h->s_aux));
-      h->aux_pending = false;
-      CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));
+    if (use_dense && pl.fp4 &&
+        ((!streaming && !((double)h->max_cell_tot * (double)h->dn_maxmult < 16777216.0)) ||
+         (double)hf[CV_DFLAGS + 7] > 0.7 * (double)pl.Hcap || (hf[CV_DFLAGS + 5] & 4u))) {
+      // sums may not fit a float exactly, or the operand alone (multiplicities outside the e2m1
+      // alphabet on most peaks: dense k-mer annotations) already fills the overflow reserve, or an
+      // entry passed 15: u8 operands / s32 accumulators instead.  Only the operand rows are redone
+      // (bit columns, inverse background map and the per-annotation tables do not depend on the format).
+      CV_CUDA(h, cudaMemsetAsync(dflags + 5, 0, 12, h->stream));
       cv_dense_plan_set_fp4(&pl, 0);
-      CV_TRY(cv_dense_prepare(h, pl, 0));
-      CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
-      CV_CUDA(h, cudaStreamSynchronize(h->stream));
-      int soft2 = 0;
-      CV_TRY(cv_dense_check(h, pl, hf, 1, &soft2));
+      CV_TRY(cv_ensure(h, h->dn_M, (size_t)pl.m_bytes));
+      CV_TRY(cv_ensure(h, h->dn_C, (size_t)pl.c_bytes));
+      cv_span_begin(h, CV_SPAN_LAYOUT);
+      CV_TRY(cv_dense_rebuild_rows_u8(h, pl));
+      cv_span_end(h);
     }
     if (use_dense) {
       const bool dl = io && (io->out_dev || io->out_z);
@@ -719,7 +721,12 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
         {
           const int rcc = cv_dense_chunk(h, pli, lo(i), hi(i), keep_sums);
           if (rcc != CV_OK) {
-            if (h->f4_veto && io) io->soft_fail = 1;         // not exact on the e2m1 path: the caller retries with u8
+            if (h->f4_veto && !streaming && i == 0) {         // the first chunk does not fit the e2m1 operands: u8 from the start
+              const int rc2 = deviations_run(h, rebuild_counts_layout, keep_sums, io);
+              h->f4_veto = false;
+              return rc2;
+            }
+            if (h->f4_veto && io) io->soft_fail = 1;         // the caller retries with u8
             return rcc;
           }
         }

@@ -214,7 +214,7 @@ void cv_dense_plan_set_fp4(DensePlan* pl, int on);
 int cv_f4_build_rows(cv_handle* h, const DensePlan& pl);
 struct DenseParams;
 int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm, int64_t c0, int64_t c1, int64_t rows,
-                int fixed_point_epilogue);
+                int fixed_point_epilogue, int check_now);
 int cv_dense_plan(cv_handle* h, uint32_t max_val, int64_t want_chunk, DensePlan* pl, std::string* why);
 double cv_dense_cost_ms(cv_handle* h, const DensePlan& pl);
 int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows);
@@ -222,6 +222,7 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
 int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, int with_counts, int* soft_fail);
 // cv_dense_build.cu
 int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter);
+int cv_dense_rebuild_rows_u8(cv_handle* h, const DensePlan& pl);
 int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift);
 int cv_exclusive_scan_u32_async(cv_handle* h, const uint32_t* in, uint32_t* out, int64_t n);
 // cv_counts.cu: K1 in pieces so the streamed call can run it per uploaded cell chunk

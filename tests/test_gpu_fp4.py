@@ -102,9 +102,9 @@ def test_fp4_overflow_columns_for_multiplicities(fp4_engine):
 
 
 def test_fp4_falls_back_when_the_overflow_reserve_is_exceeded(fp4_engine):
-    """every nonzero is a 5: every peak needs an overflow column, four times the reserve (P / 4):
-    detected on the device, the call redoes itself with u8 operands"""
-    C, P, N, bg, e, ptr, idx, sets = _problem([5])
+    """every nonzero is an 11 = 6 + 4 + 1: every peak needs two overflow columns, twice the reserve
+    (one column per peak): detected on the device, the call redoes itself with u8 operands"""
+    C, P, N, bg, e, ptr, idx, sets = _problem([11])
     fp4_engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
     fp4_engine.set_option("dense_fp4", 1)
     got = fp4_engine.deviations(ptr, idx, bg, e, sums=True)
