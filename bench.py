@@ -261,7 +261,7 @@ def run_reference(args):
                                  "MulticoreParam); not a chromVAR R timing: R is not installed here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -481,10 +481,30 @@ def run_ours(args):
                         "sampled_indices_per_s": P * NITER / max(t_bg, 1e-9),
                         "computeExpectations_ms_wall": 1e3 * t_exp},
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL's
+    version banner, for one) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    sys.stdout.flush()
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
