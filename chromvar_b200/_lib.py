@@ -27,7 +27,7 @@ EXPORTS = [
     "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_deviations", "cv_deviations_csc",
     "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
-    "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats",
+    "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms",
 ]
 
 

@@ -550,6 +550,20 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
+// The term decomposition the e2m1 operands use, for inspection and tests (no device needed): writes the
+// terms of v (each in {1,2,3,4,6}, summing to v) and their 4-bit e2m1 codes; returns the number of terms
+// (1 for v = 0, whose single term is 0), or -1 when max_terms is too small.
+extern "C" int cv_e2m1_terms(uint32_t v, uint32_t* terms, uint32_t* codes, int max_terms) {
+  const int n = (int)f4_nterms(v);
+  if (n > max_terms) return -1;
+  for (int t = 0; t < n; ++t) {
+    const uint32_t x = f4_term(v, (uint32_t)t);
+    if (terms) terms[t] = x;
+    if (codes) codes[t] = t == 0 ? f4_code0(v) : f4_code(x);
+  }
+  return n;
+}
+
 static inline int64_t f4_round_up(int64_t v, int64_t m) { return ((v + m - 1) / m) * m; }
 
 // Shape of the e2m1 path for the current problem (fills the fp4 members of the plan); 0 = not applicable.

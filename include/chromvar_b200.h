@@ -73,6 +73,8 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *                      of u8) whenever the problem can be represented exactly that way -- values
  *                      outside {0,1,2,3,4,6} are split into terms in extra "overflow" columns -- and
  *                      falls back to u8 otherwise; 0: never
+ *   "dense_lockstep"   1 (default): in the e2m1 kernel the TMA producers of all CTAs start each sub-tile
+ *                      together (L2 then serves all but the first request for an operand block); 0: free running
  *   "dense_rows_scatter" 1 builds the operand rows with the per-annotation scatter kernel only
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
@@ -204,6 +206,11 @@ typedef struct cv_stage_stats {
   int32_t overflow_columns;  /* e2m1 operands: extra columns holding the terms of values outside {0,1,2,3,4,6}, all chunks */
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
+
+/* Diagnostic (no device needed): how the e2m1 variant of the dense path writes the integer v -- its
+ * terms (each in {1,2,3,4,6}, summing to v; 5 = 4+1, 13 = 6+6+1) and their 4-bit e2m1 codes.  Returns
+ * the number of terms (1 for v = 0), or -1 when max_terms is too small.  terms / codes may be NULL. */
+int cv_e2m1_terms(uint32_t v, uint32_t* terms, uint32_t* codes, int max_terms);
 
 #ifdef __cplusplus
 }

@@ -68,3 +68,29 @@ def test_bh_adjust_matches_oracle():
     p = rng.random(50)
     p[[3, 9]] = np.nan
     assert np.allclose(api._p_adjust_bh(p), orc.p_adjust_bh(p), equal_nan=True)
+
+
+def test_e2m1_term_decomposition():
+    """The e2m1 operands hold {0,1,2,3,4,6} only: every other count / multiplicity is a sum of such
+    terms (cv_dense_fp4.cu).  The decomposition must be exact for every value a u8 count or a
+    4-bit tile can hold, use the documented number of terms, and encode each term correctly."""
+    import ctypes as C
+    from chromvar_b200 import _lib
+    lib = _lib.load()
+    lib.cv_e2m1_terms.restype = C.c_int
+    lib.cv_e2m1_terms.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
+    value_of_code = {0: 0.0, 1: 0.5, 2: 1.0, 3: 1.5, 4: 2.0, 5: 3.0, 6: 4.0, 7: 6.0}
+    terms = (C.c_uint32 * 64)()
+    codes = (C.c_uint32 * 64)()
+    for v in list(range(0, 300)) + [1000, 4095, 65535]:
+        n = lib.cv_e2m1_terms(v, terms, codes, 64) if v < 300 else lib.cv_e2m1_terms(v, None, None, 1 << 20)
+        if v >= 300:
+            assert n == v // 6 + (0 if v % 6 == 0 else 2 if v % 6 == 5 else 1)
+            continue
+        assert n >= 1
+        t = [terms[i] for i in range(n)]
+        assert sum(t) == v, (v, t)
+        assert all(x in (1, 2, 3, 4, 6) for x in t) or v == 0
+        assert [value_of_code[codes[i]] for i in range(n)] == [float(x) for x in t]
+        assert n == (1 if v in (0, 1, 2, 3, 4, 6) else v // 6 + (0 if v % 6 == 0 else 2 if v % 6 == 5 else 1))
+    assert lib.cv_e2m1_terms(65, terms, codes, 4) == -1
