@@ -201,3 +201,42 @@ def test_fp4_falls_back_when_an_operand_entry_exceeds_a_nibble(fp4_engine):
     assert fp4_engine.stats()["operand_bits"] == 4 and fp4_engine.stats()["overflow_columns"] > 0
     ref = orc.compute_deviations_core(C, [np.asarray(s) for s in sets], bg, e, intermediate=True)
     check_against_oracle(got, ref)
+
+
+def test_fp4_equals_u8_at_config2_size(engine):
+    """BASELINE config 2 at full size (100 000 peaks x 10 000 cells x 870 annotations, 50 iterations):
+    the e2m1 kernel (overflow columns for 0.4 % of the nonzeros, three cell chunks) and the u8 kernel
+    give bit-identical deviations, z-scores and variabilities; integer sums of a slab of annotations are
+    compared too (the full K x B x N int64 array would be 3.5 GB)."""
+    from chromvar_b200 import synthetic
+    d = synthetic.make_config("cfg2_scatac_motifs")
+    C = d["counts"]
+    P, N = C.shape
+    bg = synthetic.random_background(P, 50, np.random.default_rng(1))
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    try:
+        engine.set_option("path", 2)
+        engine.set_option("dense_fp4", 0)
+        u8 = engine.deviations(d["annoptr"], d["annoidx"], bg, e)
+        assert engine.stats()["operand_bits"] == 8
+        engine.set_option("dense_fp4", 1)
+        f4 = engine.deviations(d["annoptr"], d["annoidx"], bg, e)
+        st = engine.stats()
+        assert st["operand_bits"] == 4 and st["overflow_columns"] > 0 and st["n_cell_tiles"] == 3
+        for key in ("dev", "z", "variability", "matches", "overlap"):
+            assert np.array_equal(f4[key], u8[key], equal_nan=True), key
+        # integer sums of the first 24 annotations, both kernels
+        ptr = d["annoptr"][:25]
+        idx = d["annoidx"][:ptr[-1]]
+        f4s = engine.deviations(ptr, idx, bg, e, sums=True)
+        assert engine.stats()["operand_bits"] == 4
+        engine.set_option("dense_fp4", 0)
+        u8s = engine.deviations(ptr, idx, bg, e, sums=True)
+        assert np.array_equal(f4s["observed"], u8s["observed"]) and np.array_equal(f4s["sampled"], u8s["sampled"])
+        # observed sums against scipy for those annotations
+        A = sp.csr_matrix((np.ones(len(idx)), idx - 1, ptr), shape=(24, P))
+        assert np.array_equal(f4s["observed"], np.asarray((A @ C).todense()).astype(np.int64))
+    finally:
+        for key, v in (("path", 0), ("dense_fp4", -1)):
+            engine.set_option(key, v)
