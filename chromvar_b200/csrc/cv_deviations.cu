@@ -557,7 +557,7 @@ static int choose_path(cv_handle* h, uint32_t max_val, int64_t want_chunk, bool 
 }
 
 // Cell-chunk boundaries of the dense path (multiples of 256 cells, each <= pl.chunk_cells).
-static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int64_t N) {
+static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int64_t N, bool streaming) {
   const int64_t chunk = pl.chunk_cells;
   std::vector<int64_t> b;
   const int64_t U = (N + 255) / 256, maxU = chunk / 256;
@@ -577,6 +577,9 @@ static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int6
     for (int64_t m = minU; m <= maxU; ++m) {
       const int64_t c = U - a - m;
       if (c < minU || c > maxU) continue;
+      // counts arriving from the host: a chunk's upload has to fit behind the previous chunk's GEMM
+      // (PCIe moves a unit in about two thirds of the time the GEMM needs for it)
+      if (streaming && (2 * m > 3 * a + 4 || 2 * c > 3 * m + 4)) continue;
       const int64_t cost = (waves(a) + waves(m) + waves(c)) * 4096 + a * 8 + (m > c ? 1 : 0);   // fewest waves, then the smallest first chunk
       if (best < 0 || cost < best) { best = cost; ba = a; bb = m; }
     }
@@ -644,7 +647,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     // chunk boundaries: uniform when the caller fixed the chunk ("cell_chunk"); otherwise about three
     // chunks whose work items fill whole waves of CTA pairs (config 2: 40 units of 256 cells x 97
     // super-groups on 74 pairs: 8 + 16 + 16 units = 53 waves, 14 + 13 + 13 = 55), the small one first
-    std::vector<int64_t> bounds = chunk_bounds(h, pl, N);
+    std::vector<int64_t> bounds = chunk_bounds(h, pl, N, streaming);
     const int n_chunks = (int)bounds.size() - 1;
     dense_chunks_used = n_chunks;
     std::vector<cudaEvent_t> ev_up((size_t)n_chunks), ev_done((size_t)n_chunks), ev_dn((size_t)n_chunks);
