@@ -1,0 +1,157 @@
+"""The oracle's restatements of the reference's native routines, pinned against the reference's
+own code: src/utils.cpp compiled unmodified into oracle/_ref/libchromvar_ref.so (oracle/Makefile).
+
+R's unif_rand() is R's Mersenne-Twister, restated in oracle/refbuild/ref_capi.cpp and pinned here
+to the first runif() values after set.seed(42 / 1 / 123) (the values every R session prints).
+With the SAME uniform stream the restatement and the compiled reference must agree draw for draw.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import chromvar_oracle as orc
+from oracle import ref_native as rn
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _ref_lib():
+    if not rn.available() and rn.build() is None:
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    rn.load()
+
+
+def test_r_mersenne_twister_known_values():
+    # as printed by R (7 significant digits): set.seed(s); runif(5)
+    known = {
+        42: [0.9148060, 0.9370754, 0.2861395, 0.8304476, 0.6417455],
+        1: [0.2655087, 0.3721239, 0.5728534, 0.9082078, 0.2016819],
+        123: [0.2875775, 0.7883051, 0.4089769, 0.8830174, 0.9404673],
+    }
+    for seed, vals in known.items():
+        rn.set_seed(seed)
+        assert np.allclose(rn.unif_rand(5), vals, rtol=0, atol=5e-8), seed
+    rn.set_seed(42)
+    assert abs(rn.unif_rand(1)[0] - 0.914806043496355) < 1e-15      # print(runif(1), digits = 15)
+    rn.set_seed(42)
+    a = rn.unif_rand(2000)          # crosses three regenerations of the 624-word block
+    rn.set_seed(42)
+    assert np.array_equal(a, np.concatenate([rn.unif_rand(700), rn.unif_rand(1300)]))
+    assert a.min() > 0 and a.max() < 1 and abs(a.mean() - 0.5) < 0.02
+
+
+def test_euc_dist_pinned():
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(200, 2))
+    ref = rn.euc_dist(x)
+    got = orc.euc_dist(x)
+    assert np.array_equal(ref, ref.T) and np.all(np.diag(ref) == 0)
+    assert np.max(np.abs(got - ref)) <= 4e-16 * np.max(ref)
+    # the 2500-bin grid of the sampler (R/background_peaks.R:139-144)
+    g = np.array([(a, b) for b in np.linspace(0, 4.3, 50) for a in np.linspace(1.9, 7.6, 50)])
+    assert np.max(np.abs(orc.euc_dist(g) - rn.euc_dist(g))) < 1e-14
+
+
+def test_row_sds_pinned():
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(23, 301)) * rng.lognormal(size=(23, 1)) + 5
+    assert np.allclose(orc.row_sds(x, False), rn.row_sds(x, False), rtol=1e-13, atol=0)
+    assert np.allclose(orc.row_sds(x, True), rn.row_sds(x, True), rtol=1e-13, atol=0)
+    x[2, 7] = np.nan
+    x[4, :] = np.nan                 # nothing finite -> NaN
+    x[5, 1:] = np.inf                # one finite value -> NaN
+    x[6, ::2] = -np.inf
+    for na_rm in (True, False):
+        ref, got = rn.row_sds(x, na_rm), orc.row_sds(x, na_rm)
+        assert np.array_equal(np.isnan(ref), np.isnan(got)), na_rm
+        m = ~np.isnan(ref)
+        assert np.allclose(got[m], ref[m], rtol=1e-13, atol=0)
+    assert np.isnan(rn.row_sds(x, True)[[4, 5]]).all() and not np.isnan(rn.row_sds(x, True)[[2, 6]]).any()
+    assert np.isnan(rn.row_sds(x, False)[[2, 4, 5, 6]]).all()
+    # one column: stddev of a single value is 0 without na_rm, NaN with it (keep.size() > 1 fails)
+    one = rng.normal(size=(4, 1))
+    assert np.array_equal(rn.row_sds(one, False), np.zeros(4)) and np.array_equal(orc.row_sds(one, False), np.zeros(4))
+    assert np.isnan(rn.row_sds(one, True)).all() and np.isnan(orc.row_sds(one, True)).all()
+
+
+def test_row_sds_perm_pinned():
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(11, 97))
+    x[3, 4] = np.nan
+    for seed in (7, 8):
+        rn.set_seed(seed)
+        ref = rn.row_sds_perm(x, True)
+        assert rn.draws() == 97
+        rn.set_seed(seed)
+        got = orc.row_sds_perm(x, True, unif=rn.unif_rand)
+        assert np.allclose(got, ref, rtol=1e-13, atol=0, equal_nan=True)
+
+
+def test_prob_sample_replace_pinned():
+    rng = np.random.default_rng(3)
+    cases = [rng.random(500) ** 3, np.full(64, 1.0), np.r_[np.zeros(40), rng.random(60)], np.array([1.0]),
+             np.r_[1e-12, rng.random(9)]]
+    for k, prob in enumerate(cases):
+        prob = prob / prob.sum()
+        size = 20000
+        rn.set_seed(100 + k)
+        ref = rn.prob_sample_replace(size, prob)
+        assert rn.draws() == size
+        rn.set_seed(100 + k)
+        got = orc.prob_sample_replace(size, prob, rn.unif_rand)
+        assert np.array_equal(got, ref), k
+        assert ref.min() >= 1 and ref.max() <= prob.size
+        assert np.all(prob[ref - 1] > 0)
+        # and the alias table samples the distribution it was given
+        exp = prob * size
+        keep = exp >= 5
+        if keep.sum() > 1:
+            from scipy.stats import chi2
+            obs = np.bincount(ref - 1, minlength=prob.size).astype(float)
+            stat = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+            assert stat < chi2.ppf(1 - 1e-5, int(keep.sum()))
+
+
+def test_bg_sample_helper_pinned_random_bins():
+    rng = np.random.default_rng(4)
+    nb, P, B = 30, 400, 20
+    bm0 = rng.integers(0, nb - 4, P)                     # the last four bins stay empty
+    bin_p = rng.random((nb, nb)) ** 2
+    dens = np.bincount(bm0, minlength=nb).astype(float)
+    rn.set_seed(5)
+    ref = rn.bg_sample_helper(bm0, bin_p, dens, B)
+    assert rn.draws() == P * B
+    rn.set_seed(5)
+    got = orc.bg_sample_helper(bm0, bin_p, dens, B, rn.unif_rand)
+    assert np.array_equal(got, ref)
+    assert ref.min() >= 1 and ref.max() <= P
+
+
+def test_bg_sample_helper_pinned_mini_counts(golden_mini):
+    """The sampler half of getBackgroundPeaks on the bundled mini_counts (config 1): bins and
+    weights from the restated front half, draws by the reference's own code."""
+    g = golden_mini
+    Cm = sp.csc_matrix((g["counts_x"], g["counts_i"], g["counts_p"]), shape=tuple(g["counts_dim"]))
+    fh = orc.background_front_half(orc.get_fragments_per_peak(Cm), g["bias"], 50)
+    bin_p = orc.bin_weight_matrix(fh["bin_data"], 0.1)
+    assert np.max(np.abs(orc.euc_dist(fh["bin_data"]) - rn.euc_dist(fh["bin_data"]))) < 1e-14
+    bm0 = fh["bin_membership"] - 1
+    rn.set_seed(2017)
+    ref = rn.bg_sample_helper(bm0, bin_p, fh["bin_density"], 50)
+    rn.set_seed(2017)
+    got = orc.bg_sample_helper(bm0, bin_p, fh["bin_density"], 50, rn.unif_rand)
+    assert ref.shape == (1000, 50)
+    assert np.array_equal(got, ref)
+    # the generative statement the GPU sampler implements has the same destination-bin law:
+    # expected occupancy of bin j under Pbin against the reference's draws (chi-square)
+    from scipy.stats import chi2
+    rn.set_seed(11)
+    big = rn.bg_sample_helper(bm0, bin_p, fh["bin_density"], 400)
+    Pbin = orc.bin_probability_matrix(bin_p, fh["bin_density"])
+    exp = 400 * (fh["bin_density"][:, None] * Pbin).sum(axis=0)
+    obs = np.bincount(bm0[big.ravel() - 1], minlength=2500).astype(float)
+    keep = exp >= 5
+    o = np.append(obs[keep], obs[~keep].sum())
+    x = np.append(exp[keep], exp[~keep].sum())
+    nz = x > 0
+    assert o[~nz].sum() == 0
+    assert ((o[nz] - x[nz]) ** 2 / x[nz]).sum() < chi2.ppf(1 - 1e-4, int(nz.sum()) - 1)
