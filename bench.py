@@ -162,7 +162,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
-def make_workload(rank, cells, quick, workload=None):
+def make_workload(rank, cells, quick, workload=None, gen="host", device=None):
+    """gen: "host" (numpy generator), "device" (same model, draws and duplicate merging on the GPU:
+    make_counts_device), "auto" = device for configurations of >= 5e8 expected nonzeros (the atlas
+    shard takes minutes on the host)."""
     from chromvar_b200 import synthetic
     t0 = time.time()
     if quick:
@@ -171,7 +174,14 @@ def make_workload(rank, cells, quick, workload=None):
     else:
         over = {"N": cells} if cells else {}
         name = workload or WORKLOAD
-        d = synthetic.make_config(name, seed_offset=rank, **over)
+        cfg = dict(synthetic.CONFIGS[name])
+        cfg.update(over)
+        big = cfg["density"] < 1.0 and cfg["P"] * cfg["N"] * cfg["density"] >= 5e8
+        use_dev = device is not None and (gen == "device" or (gen == "auto" and big))
+        d = synthetic.make_config(name, seed_offset=rank, device=device if use_dev else None, **over)
+        if use_dev:
+            import torch
+            torch.cuda.empty_cache()
     if not hasattr(d["counts"], "indptr"):
         import scipy.sparse as sp
         d["dense"] = d["counts"]                       # bulk (config 4): dense column-major counts
@@ -288,20 +298,24 @@ def run_ours(args):
         eng.set_option("dense_band", args.band)
     if args.debug_no_tma:
         eng.set_option("debug_no_tma", args.debug_no_tma)
-    d, name = make_workload(rank, args.cells, args.quick, args.workload)
+    d, name = make_workload(rank, args.cells, args.quick, args.workload, gen=args.gen, device="cuda:%d" % local)
     C = d["counts"]
     P, N = C.shape
     K = len(d["annoptr"]) - 1
     nnz = int(C.nnz)
 
     def pin(a):
-        """Pinned copy of a (memory order kept: the background matrix stays column-major)."""
+        """Pinned copy of a (memory order kept: the background matrix stays column-major); arrays
+        the device generator already left in pinned memory are used as they are."""
         a = np.asarray(a)
+        if a.ndim == 1 and a.flags.c_contiguous and a.size and torch.from_numpy(a).is_pinned():
+            return a
         if a.ndim == 2 and a.flags.f_contiguous and not a.flags.c_contiguous:
             return torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory().numpy().T
         return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
-    h_colptr, h_rowidx, h_x = pin(C.indptr.astype(np.int64)), pin(C.indices.astype(np.int32)), pin(C.data.astype(np.float64))
+    h_colptr, h_rowidx, h_x = (pin(C.indptr.astype(np.int64)), pin(C.indices.astype(np.int32, copy=False)),
+                               pin(C.data.astype(np.float64, copy=False)))
     h_ptr, h_idx = pin(d["annoptr"]), pin(d["annoidx"].astype(np.int32))
 
     # ---- setup (untimed): counts -> HBM, global per-peak totals, expectation, background -------
@@ -458,6 +472,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
                    "niterations": NITER, "nnz_per_gpu": nnz, "nnz_annotations": int(d["annoptr"][-1]),
+                   "cells_total": int(N) * ws, "generator": d["cfg"].get("generator", "numpy (make_counts)"),
                    "l2": "256 MB flush write between timed steps", "cell_tile": int(tile_cells),
                    "path": ("dense_tcgen05_cta_pair" if tile_cells == 256 else "dense_tcgen05") if path == 1
                    else "row_gather_spmm"},
@@ -514,6 +529,8 @@ def main():
     ap.add_argument("--workload", default=None, help="synthetic configuration (default cfg2_scatac_motifs; "
                     "cfg3_kmers, cfg4_bulk, cfg5_atlas_shard are parity / scale cases, not the bench line)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="number of timed e2e steps (default min(steps, 10))")
+    ap.add_argument("--gen", default="auto", choices=["auto", "host", "device"],
+                    help="synthetic counts on the host (numpy) or on the GPU (same model, torch); auto: GPU for >= 5e8 nonzeros")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
