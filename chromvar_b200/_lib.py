@@ -24,7 +24,8 @@ _DTYPE_TAG = {np.dtype(np.int32): CV_I32, np.dtype(np.int64): CV_I64,
 EXPORTS = [
     "cv_create", "cv_destroy", "cv_last_error", "cv_version", "cv_set_seed", "cv_set_option", "cv_stream",
     "cv_set_counts_csc", "cv_set_counts_dense", "cv_fragments", "cv_peak_totals_device",
-    "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_deviations", "cv_deviations_csc",
+    "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_background_peaks_knn", "cv_deviations",
+    "cv_deviations_csc",
     "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
     "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms",
@@ -85,6 +86,7 @@ def load(build_if_missing=True):
         "cv_peak_totals_commit": (i32, [vp]),
         "cv_expectations": (i32, [vp, i32, vp, i32, vp]),
         "cv_background_peaks": (i32, [vp, vp, i32, dbl, i32, vp, vp, vp, vp, vp]),
+        "cv_background_peaks_knn": (i32, [vp, vp, i32, i32, vp, vp, vp]),
         "cv_deviations": (i32, [vp, i64, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "cv_deviations_csc": (i32, [vp, i64, i64, vp, i32, vp, vp, i32, i64, vp, vp, i32, vp, i32, vp,
                                     vp, vp, vp, vp, vp]),
@@ -224,6 +226,22 @@ class Handle:
         self._check(self.lib.cv_background_peaks(self._h, _ptr(bias), niterations, w, bs, _ptr(bg),
                                                  _ptr(trans), _ptr(memb), _ptr(dens), _ptr(binprob)))
         return bg, dict(trans_norm_mat=trans, bin_membership=memb, bin_density=dens, bin_prob=binprob)
+
+    def background_peaks_knn(self, bias, niterations=50, window=500, debug=False):
+        """get_background_peaks_alternative (R/test_sets.R:291-330): uniform draws among the `window`
+        nearest other peaks in the whitened (fragments per peak, bias) plane."""
+        bias = _carr(bias, np.float64)
+        if bias.shape[0] != self.P:
+            raise ChromVARError(CV_ERR_INVALID, "length(bias) must equal nrow(counts)")
+        bg = np.empty((self.P, niterations), np.int32, order="F")
+        if not debug:
+            self._check(self.lib.cv_background_peaks_knn(self._h, _ptr(bias), niterations, window, _ptr(bg), None, None))
+            return bg
+        trans = np.empty((self.P, 2), np.float64, order="F")
+        nn = np.empty((self.P, window), np.int32)
+        self._check(self.lib.cv_background_peaks_knn(self._h, _ptr(bias), niterations, window, _ptr(bg),
+                                                     _ptr(trans), _ptr(nn)))
+        return bg, dict(tmp_vals=trans, nn_idx=nn)
 
     # ---- deviations -----------------------------------------------------------------------
     @staticmethod

@@ -48,27 +48,34 @@ __device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double* sh /*[
   for (int i = 0; i < NV; ++i) v[i] = sh[i * RED_THREADS];
 }
 
-// partial[b][0..1] = sum log10(fpp), sum bias over block b's strided elements
+// intensity axis: log10(fragments per peak) for getBackgroundPeaks (R/background_peaks.R:128), the raw
+// total for get_background_peaks_alternative (:188)
+template <bool LOG>
+__device__ __forceinline__ double intensity(unsigned long long f) { return LOG ? log10((double)f) : (double)f; }
+
+// partial[b][0..1] = sum intensity, sum bias over block b's strided elements
+template <bool LOG>
 __global__ void __launch_bounds__(RED_THREADS)
 k_front_sums(const unsigned long long* __restrict__ fpp, const double* __restrict__ bias, int P,
              double* __restrict__ partial) {
   __shared__ double sh[2 * RED_THREADS];
   double v[2] = {0.0, 0.0};
   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < P; i += gridDim.x * RED_THREADS) {
-    v[0] += log10((double)fpp[i]);
+    v[0] += intensity<LOG>(fpp[i]);
     v[1] += bias[i];
   }
   block_reduce_sum<2>(v, sh);
   if (threadIdx.x == 0) { partial[blockIdx.x * 2] = v[0]; partial[blockIdx.x * 2 + 1] = v[1]; }
 }
 
+template <bool LOG>
 __global__ void __launch_bounds__(RED_THREADS)
 k_front_cov(const unsigned long long* __restrict__ fpp, const double* __restrict__ bias, int P,
             double mx, double my, double* __restrict__ partial) {
   __shared__ double sh[3 * RED_THREADS];
   double v[3] = {0.0, 0.0, 0.0};
   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < P; i += gridDim.x * RED_THREADS) {
-    double dx = log10((double)fpp[i]) - mx, dy = bias[i] - my;
+    double dx = intensity<LOG>(fpp[i]) - mx, dy = bias[i] - my;
     v[0] += dx * dx; v[1] += dx * dy; v[2] += dy * dy;
   }
   block_reduce_sum<3>(v, sh);
@@ -78,6 +85,7 @@ k_front_cov(const unsigned long long* __restrict__ fpp, const double* __restrict
 
 // trans = t(forwardsolve(t(R), t(norm_mat)))  (:131): y1 = x / r11, y2 = (b - r12*y1) / r22
 // T is P x 2 column-major.  partial[b] = (min1, max1, min2, max2)
+template <bool LOG>
 __global__ void __launch_bounds__(RED_THREADS)
 k_front_transform(const unsigned long long* __restrict__ fpp, const double* __restrict__ bias,
                   int P, double r11, double r12, double r22, double* __restrict__ T,
@@ -85,7 +93,7 @@ k_front_transform(const unsigned long long* __restrict__ fpp, const double* __re
   __shared__ double sh[4 * RED_THREADS];
   double mn1 = INFINITY, mx1 = -INFINITY, mn2 = INFINITY, mx2 = -INFINITY;
   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < P; i += gridDim.x * RED_THREADS) {
-    double y1 = log10((double)fpp[i]) / r11;
+    double y1 = intensity<LOG>(fpp[i]) / r11;
     double y2 = __ddiv_rn(__dsub_rn(bias[i], __dmul_rn(r12, y1)), r22);
     T[i] = y1; T[(int64_t)P + i] = y2;
     mn1 = fmin(mn1, y1); mx1 = fmax(mx1, y1); mn2 = fmin(mn2, y2); mx2 = fmax(mx2, y2);
@@ -359,23 +367,19 @@ static double sum_partials(const std::vector<double>& v, int stride, int off, in
   return s;
 }
 
-extern "C" int cv_background_peaks(cv_handle* h, const double* bias, int niter, double w, int bs,
-                                   int32_t* out_bg, double* out_trans, int32_t* out_membership,
-                                   double* out_density, double* out_binprob) {
-  if (!h) return CV_ERR_INVALID;
-  cudaSetDevice(h->device);
+// Whitening shared by cv_background_peaks (log10 intensity) and cv_background_peaks_knn (raw totals):
+// state / input checks, bias -> h->bk[0], T = t(forwardsolve(t(chol(cov(norm_mat))), t(norm_mat))) -> h->bk[1]
+// (P x 2 column-major), mm = (min1, max1, min2, max2).  Records h->ev[6] after the bias upload.
+int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm) {
   if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
   if (!h->totals_committed)
     CV_FAIL(h, CV_ERR_STATE, "per-peak totals handed out for a cross-shard reduction; call cv_peak_totals_commit first");
   if (!bias) CV_FAIL(h, CV_ERR_INVALID, "bias is NULL");
-  if (niter < 1 || bs < 2 || !(w > 0.0)) CV_FAIL(h, CV_ERR_INVALID, "niterations >= 1, bs >= 2 and w > 0 required");
-  if (bs > 200) CV_FAIL(h, CV_ERR_UNSUPPORTED, "bs > 200 is not supported");
   const int64_t P = h->P;
   if (P < 2) CV_FAIL(h, CV_ERR_INVALID, "need at least two peaks");
-  const int64_t nb = (int64_t)bs * bs;
   const unsigned long long* fpp = h->peak_tot.as<unsigned long long>();
 
-  // (:122-125) every peak needs a fragment
+  // (:122-125, :183-184) every peak needs a fragment
   {
     std::vector<unsigned long long> tot((size_t)P);
     CV_CUDA(h, cudaMemcpyAsync(tot.data(), fpp, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -388,23 +392,23 @@ extern "C" int cv_background_peaks(cv_handle* h, const double* bias, int niter, 
 
   CV_TRY(cv_ensure(h, h->bk[0], (size_t)P * 8));
   CV_TRY(cv_ensure(h, h->bk[1], (size_t)P * 2 * 8));
-  CV_TRY(cv_ensure(h, h->bk[2], (size_t)P * 4));
   CV_TRY(cv_ensure(h, h->bk[3], (size_t)RED_BLOCKS * 4 * 8));
   double* d_bias = h->bk[0].as<double>();
   double* d_T = h->bk[1].as<double>();
-  int32_t* d_memb = h->bk[2].as<int32_t>();
   double* d_part = h->bk[3].as<double>();
   CV_CUDA(h, cudaMemcpyAsync(d_bias, bias, (size_t)P * 8, cudaMemcpyHostToDevice, h->stream));
   CV_CUDA(h, cudaEventRecord(h->ev[6], h->stream));
   const int G = (int)std::min<int64_t>(RED_BLOCKS, (P + RED_THREADS - 1) / RED_THREADS);
   std::vector<double> part((size_t)RED_BLOCKS * 4);
 
-  CV_LAUNCH(h, k_front_sums, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part);
+  if (log_intensity) CV_LAUNCH(h, k_front_sums<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part);
+  else CV_LAUNCH(h, k_front_sums<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part);
   CV_CUDA(h, cudaMemcpyAsync(part.data(), d_part, (size_t)G * 2 * 8, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   const double mx = sum_partials(part, 2, 0, G) / (double)P, my = sum_partials(part, 2, 1, G) / (double)P;
 
-  CV_LAUNCH(h, k_front_cov, G, RED_THREADS, 0, fpp, d_bias, (int)P, mx, my, d_part);
+  if (log_intensity) CV_LAUNCH(h, k_front_cov<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, mx, my, d_part);
+  else CV_LAUNCH(h, k_front_cov<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, mx, my, d_part);
   CV_CUDA(h, cudaMemcpyAsync(part.data(), d_part, (size_t)G * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   const double c11 = sum_partials(part, 3, 0, G) / (double)(P - 1);   // stats::cov, n-1 (:130)
@@ -415,18 +419,38 @@ extern "C" int cv_background_peaks(cv_handle* h, const double* bias, int niter, 
   const double r12 = c12 / r11;
   const double r22 = sqrt(c22 - r12 * r12);
   if (!(r11 > 0.0) || !(r22 > 0.0))
-    CV_FAIL(h, CV_ERR_INVALID, "covariance of (log10 fragments, bias) is not positive definite (chol would fail)");
+    CV_FAIL(h, CV_ERR_INVALID, "covariance of (%sfragments, bias) is not positive definite (chol would fail)",
+            log_intensity ? "log10 " : "");
 
-  CV_LAUNCH(h, k_front_transform, G, RED_THREADS, 0, fpp, d_bias, (int)P, r11, r12, r22, d_T, d_part);
+  if (log_intensity) CV_LAUNCH(h, k_front_transform<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, r11, r12, r22, d_T, d_part);
+  else CV_LAUNCH(h, k_front_transform<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, r11, r12, r22, d_T, d_part);
   CV_CUDA(h, cudaMemcpyAsync(part.data(), d_part, (size_t)G * 4 * 8, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  mm[0] = part[0]; mm[1] = part[1]; mm[2] = part[2]; mm[3] = part[3];
+  for (int b = 1; b < G; ++b) {
+    mm[0] = fmin(mm[0], part[(size_t)b * 4 + 0]); mm[1] = fmax(mm[1], part[(size_t)b * 4 + 1]);
+    mm[2] = fmin(mm[2], part[(size_t)b * 4 + 2]); mm[3] = fmax(mm[3], part[(size_t)b * 4 + 3]);
+  }
+  return CV_OK;
+}
+
+extern "C" int cv_background_peaks(cv_handle* h, const double* bias, int niter, double w, int bs,
+                                   int32_t* out_bg, double* out_trans, int32_t* out_membership,
+                                   double* out_density, double* out_binprob) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (niter < 1 || bs < 2 || !(w > 0.0)) CV_FAIL(h, CV_ERR_INVALID, "niterations >= 1, bs >= 2 and w > 0 required");
+  if (bs > 200) CV_FAIL(h, CV_ERR_UNSUPPORTED, "bs > 200 is not supported");
+  const int64_t P = h->P;
+  const int64_t nb = (int64_t)bs * bs;
+  double mm[4];
+  CV_TRY(cv_whiten(h, bias, 1, mm));
+  CV_TRY(cv_ensure(h, h->bk[2], (size_t)P * 4));
+  double* d_T = h->bk[1].as<double>();
+  int32_t* d_memb = h->bk[2].as<int32_t>();
   GridParams g;
   g.bs = bs;
-  g.min1 = part[0]; g.max1 = part[1]; g.min2 = part[2]; g.max2 = part[3];
-  for (int b = 1; b < G; ++b) {
-    g.min1 = fmin(g.min1, part[(size_t)b * 4 + 0]); g.max1 = fmax(g.max1, part[(size_t)b * 4 + 1]);
-    g.min2 = fmin(g.min2, part[(size_t)b * 4 + 2]); g.max2 = fmax(g.max2, part[(size_t)b * 4 + 3]);
-  }
+  g.min1 = mm[0]; g.max1 = mm[1]; g.min2 = mm[2]; g.max2 = mm[3];
   g.by1 = (g.max1 - g.min1) / (double)(bs - 1);   // seq(min, max, length.out = bs) (:134-137)
   g.by2 = (g.max2 - g.min2) / (double)(bs - 1);
 

@@ -182,6 +182,7 @@ int cv_sync_check(cv_handle* h);
 // cv_counts.cu
 int cv_build_layout(cv_handle* h, int W);
 // cv_background.cu: shared sampler back half (bin CDF rows + Philox draws)
+int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm);
 int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
                          const double* d_binp_colmajor, const double* d_bin_xy, double w,
                          int niter, int32_t* host_out, double* host_binprob, double* host_density);

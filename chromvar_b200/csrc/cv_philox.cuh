@@ -6,7 +6,7 @@
 #pragma once
 #include <stdint.h>
 
-enum { CV_STREAM_BACKGROUND = 0, CV_STREAM_PROBSAMPLE = 1, CV_STREAM_BOOTSTRAP = 2 };
+enum { CV_STREAM_BACKGROUND = 0, CV_STREAM_PROBSAMPLE = 1, CV_STREAM_BOOTSTRAP = 2, CV_STREAM_KNN = 3 };
 
 struct Philox4 {
   uint32_t v[4];

@@ -201,3 +201,76 @@ def getPermutedData(object, niterations=10, w=0.1, bs=50):
         assays["perm_%d" % (it + 1)] = sp.hstack(cols).tocsc()
     return api.SummarizedExperiment(assays, rowData=object.rowData, colData=object.colData,
                                     rownames=object.rownames, colnames=object.colnames)
+
+
+# --------------------------------------------------------------------------------------------
+# makePermutedSets (R/test_sets.R:150-289) on get_background_peaks_alternative (:291-330)
+# --------------------------------------------------------------------------------------------
+def getBackgroundPeaksAlternative(object, bias=None, niterations=50, window=500):
+    """get_background_peaks_alternative (R/test_sets.R:291-330; internal in the reference): P x
+    niterations 1-based peaks, each drawn uniformly among the `window` nearest other peaks in the
+    whitened (fragments per peak, bias) plane.  One kernel on the GPU instead of the bplapply over
+    groups of 2000 peaks around nabor::knn."""
+    if isinstance(object, api.SummarizedExperiment) and bias is None:
+        bias = object.rowData.get("bias")
+    mat = api._counts_matrix(object)
+    if bias is None:
+        raise ValueError("bias is missing (rowData(object)$bias)")
+    bias = np.asarray(bias, np.float64)
+    if bias.shape[0] != mat.shape[0]:
+        raise ValueError("length(bias) must equal nrow(object)")
+    eng = api._load_counts(mat)
+    seed = api._next_sampler_seed()
+    if seed is not None:
+        eng.set_seed(seed)
+    try:
+        return eng.background_peaks_knn(bias, int(niterations), int(window))
+    except ChromVARError as e:
+        raise ValueError(str(e)) from e
+
+
+def makePermutedSets(object, annotations, bias=None, window=10):
+    """R/test_sets.R:150-289: every annotation's peaks replaced by a draw among their `window`
+    nearest neighbours in (fragments per peak, bias); returns a SummarizedExperiment with the
+    assay `matches` (P x K boolean sparse, convert_from_ix_list: a peak hit twice counts once) and
+    colData$name = "permuted.<name>".  All eight method signatures: object = SummarizedExperiment /
+    matrix, annotations = SummarizedExperiment / matrix / list (dict keeps the names)."""
+    is_se = isinstance(object, api.SummarizedExperiment)
+    if not is_se and not api._is_matrix(object):
+        raise TypeError("object must be a SummarizedExperiment, a sparse matrix or an ndarray")
+    if is_se:
+        object = api.counts_check(object)
+    col_data = None
+    if isinstance(annotations, api.SummarizedExperiment):
+        annotations = api.matches_check(annotations)
+        ptr, idx = api.convert_to_ix_list(api.annotationMatches(annotations))
+        sets = [idx[ptr[k]:ptr[k + 1]] for k in range(len(ptr) - 1)]
+        names = annotations.colnames
+        col_data = dict(annotations.colData)
+    elif api._is_matrix(annotations):
+        ptr, idx = api.convert_to_ix_list(annotations)
+        sets = [idx[ptr[k]:ptr[k + 1]] for k in range(len(ptr) - 1)]
+        names = None
+    elif isinstance(annotations, dict):
+        names = list(annotations.keys())
+        sets = [np.asarray(v) for v in annotations.values()]
+    elif isinstance(annotations, (list, tuple)):
+        sets, names = [np.asarray(v) for v in annotations], None
+    else:
+        raise TypeError("unsupported annotations type")
+    P = api._counts_matrix(object).shape[0]
+    bg = getBackgroundPeaksAlternative(object, bias, niterations=1, window=window)[:, 0]     # :275-276
+    perm = [bg[np.asarray(s).astype(np.int64) - 1].astype(np.int64) for s in sets]            # :277
+    # names(sets) <- paste("permuted.", name): unnamed lists give "permuted." for every set (:278-281)
+    pnames = ["permuted.%s" % (n if n is not None else "") for n in (names if names is not None else [None] * len(sets))]
+    rows = np.concatenate(perm) - 1 if perm else np.zeros(0, np.int64)
+    cols = np.concatenate([np.full(len(v), k, np.int64) for k, v in enumerate(perm)]) if perm else np.zeros(0, np.int64)
+    M = sp.csc_matrix((np.ones(rows.size, bool), (rows, cols)), shape=(P, len(perm)), dtype=bool)
+    M.data[:] = True                                                                          # duplicates: TRUE
+    if col_data is None:
+        col_data = {"name": np.asarray(pnames)}                                               # :283-284
+    elif "name" in col_data:
+        col_data["name"] = np.asarray(["permuted.%s" % n for n in col_data["name"]])          # :286-290
+    else:
+        col_data["name"] = np.asarray(pnames)
+    return api.SummarizedExperiment({"matches": M}, colData=col_data, colnames=pnames)

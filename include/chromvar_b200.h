@@ -118,6 +118,16 @@ int cv_background_peaks(cv_handle* h, const double* bias, int niter, double w, i
                         int32_t* out_bg, double* out_trans, int32_t* out_membership,
                         double* out_density, double* out_binprob);
 
+/* ---- get_background_peaks_alternative (R/test_sets.R:291-330), the sampler of makePermutedSets
+ * (R/test_sets.R:246-289): each background peak is drawn uniformly (with replacement) among the
+ * `window` nearest OTHER peaks in the whitened (fragments per peak, bias) plane -- exact k nearest
+ * neighbours (nabor::knn(k = window + 1, eps = 0) minus the query, :308-312); distance ties are
+ * broken by the peak index (the reference leaves them to the kd-tree).
+ * out_bg: P x niter column-major, 1-based.  Optional (NULL to skip): out_trans P x 2 col-major
+ * (tmp_vals, :301); out_nn [P][window] row-major, 1-based neighbours in (distance, index) order. */
+int cv_background_peaks_knn(cv_handle* h, const double* bias, int niter, int window,
+                            int32_t* out_bg, double* out_trans, int32_t* out_nn);
+
 /* ---- computeDeviations -> compute_deviations_core (R/compute_deviations.R:355-408), the whole
  * bplapply fan-out over compute_deviations_single (:451-537) in one call -------------------- */
 /* annoptr: K+1 offsets into annoidx; annoidx: peak indices (index_base 0 or 1; duplicates keep

@@ -3,7 +3,7 @@ counter mapping -- test infrastructure, used to reproduce the GPU samplers draw 
 import numpy as np
 
 M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
-STREAM_BACKGROUND, STREAM_PROBSAMPLE, STREAM_BOOTSTRAP = 0, 1, 2
+STREAM_BACKGROUND, STREAM_PROBSAMPLE, STREAM_BOOTSTRAP, STREAM_KNN = 0, 1, 2, 3
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

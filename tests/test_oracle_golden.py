@@ -130,3 +130,31 @@ def test_single_peak_and_empty_sets(golden_deviations_test):
     assert one["matches"] == 1 / 3 and many["matches"] == 2 / 3
     emp = orc.compute_deviations_single([], C, g["bg"], e)
     assert np.all(np.isnan(emp["z"])) and emp["matches"] == 0 and np.isnan(emp["overlap"])
+
+
+def test_alternative_background_restatement(golden_mini):
+    """get_background_peaks_alternative (R/test_sets.R:291-330), parity unpinned (no golden values in
+    the reference): the whitening leaves an identity covariance (what chol + forwardsolve does), the
+    brute-force neighbour lists agree with an independent exact kd-tree (scipy cKDTree) on every
+    k-th distance, the query is never its own neighbour, draws stay inside the neighbour lists."""
+    from scipy.spatial import cKDTree
+    g = golden_mini
+    C = sp.csc_matrix((g["counts_x"], g["counts_i"], g["counts_p"]), shape=tuple(g["counts_dim"]))
+    tv = orc.alternative_whitening(orc.get_fragments_per_peak(C), g["bias"])
+    assert np.allclose(np.cov(tv, rowvar=False), np.eye(2), atol=1e-12)
+    for window in (1, 10, 200):
+        nn = orc.knn_other(tv, window)
+        assert not np.any(nn == np.arange(tv.shape[0])[:, None])
+        d_ref, _ = cKDTree(tv).query(tv, k=window + 1)
+        d = np.sqrt(((tv[nn] - tv[:, None, :]) ** 2).sum(-1))
+        assert np.all(np.diff(d, axis=1) >= -1e-15)
+        # with duplicates of the query point the kd-tree may list a twin instead of the query itself;
+        # the multiset of the window + 1 smallest distances is the same either way
+        mine = np.sort(np.concatenate([np.zeros((tv.shape[0], 1)), d], axis=1), axis=1)
+        assert np.max(np.abs(mine - d_ref)) < 1e-12
+    bg = orc.get_background_peaks_alternative(C, g["bias"], 7, 10, rng=np.random.default_rng(1))
+    nn = orc.knn_other(tv, 10)
+    assert bg.shape == (1000, 7)
+    assert all(set(bg[p] - 1) <= set(nn[p]) for p in range(1000))
+    sets = orc.make_permuted_sets(C, [[1, 2, 3], [5]], g["bias"], window=10, rng=np.random.default_rng(2))
+    assert [len(s) for s in sets] == [3, 1]
