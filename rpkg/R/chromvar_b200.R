@@ -47,6 +47,18 @@ get_background_peaks_core <- function(object, bias, niterations = 50, w = 0.1, b
         as.integer(bs), PACKAGE = "chromVARb200")
 }
 
+# replaces R/test_sets.R:291-330 (the bplapply over groups of 2000 peaks around nabor::knn);
+# makePermutedSets_core (R/test_sets.R:270-289) calls it unchanged
+get_background_peaks_alternative <- function(object, bias, niterations = 50, window = 500) {
+  fragments_per_peak <- getFragmentsPerPeak(object)
+  if (min(fragments_per_peak) <= 0)
+    stop("All peaks must have at least one fragment in one sample")
+  .cvb_load_counts(if (is(object, "SummarizedExperiment")) counts(object) else object)
+  .Call("cvb_set_seed", as.numeric(sample.int(.Machine$integer.max, 1)), PACKAGE = "chromVARb200")
+  .Call("cvb_background_peaks_knn", as.numeric(bias), as.integer(niterations), as.integer(window),
+        PACKAGE = "chromVARb200")
+}
+
 compute_deviations_core <- function(counts_mat, peak_indices, background_peaks, expectation,
                                     rowData = NULL, colData = NULL) {
   stopifnot(nrow(counts_mat) == nrow(background_peaks))

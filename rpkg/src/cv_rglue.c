@@ -85,6 +85,20 @@ SEXP cvb_background_peaks(SEXP bias, SEXP niter, SEXP w, SEXP bs) {
   return out;
 }
 
+/* get_background_peaks_alternative (R/test_sets.R:291-330): P x niterations matrix (double, like the
+ * do.call(rbind, ...) of sample() results the reference returns) */
+SEXP cvb_background_peaks_knn(SEXP bias, SEXP niter, SEXP window) {
+  R_xlen_t P = XLENGTH(bias);
+  int B = Rf_asInteger(niter);
+  int32_t *tmp = (int32_t *) R_alloc((size_t) P * B, sizeof(int32_t));
+  check(cv_background_peaks_knn(H, REAL(bias), B, Rf_asInteger(window), tmp, NULL, NULL));
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int) P, B));
+  double *o = REAL(out);
+  for (R_xlen_t k = 0; k < P * (R_xlen_t) B; ++k) o[k] = (double) tmp[k];
+  UNPROTECT(1);
+  return out;
+}
+
 /* compute_deviations_core: annoptr (double, K+1 offsets), annoidx (integer, 1-based),
  * bg (integer matrix P x B, 1-based), expectation (double P).
  * Returns list(deviations K x N, z K x N, matches K, overlap K, variability K). */
@@ -164,6 +178,7 @@ static const R_CallMethodDef CallEntries[] = {
   {"cvb_fragments", (DL_FUNC) &cvb_fragments, 2},
   {"cvb_expectations", (DL_FUNC) &cvb_expectations, 4},
   {"cvb_background_peaks", (DL_FUNC) &cvb_background_peaks, 4},
+  {"cvb_background_peaks_knn", (DL_FUNC) &cvb_background_peaks_knn, 3},
   {"cvb_deviations", (DL_FUNC) &cvb_deviations, 5},
   {"cvb_deviations_csc", (DL_FUNC) &cvb_deviations_csc, 8},
   {"cvb_row_sds", (DL_FUNC) &cvb_row_sds, 2},
