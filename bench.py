@@ -292,6 +292,7 @@ def run_ours(args):
     eng.set_option("dense_cta_pair", args.pair)
     eng.set_option("dense_fp4", args.fp4)
     eng.set_option("dense_lockstep", args.lockstep)
+    eng.set_option("host_narrow", args.host_narrow)
     if args.chunk:
         eng.set_option("cell_chunk", args.chunk)
     if args.band:
@@ -416,7 +417,10 @@ def run_ours(args):
     if ws > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = K * N * ws * n_e2e / float(te.item())
-    h2d = h_colptr.nbytes + h_rowidx.nbytes + h_x.nbytes + h_ptr.nbytes + h_idx.nbytes + h_bg.nbytes + h_e.nbytes
+    host_in = h_colptr.nbytes + h_rowidx.nbytes + h_x.nbytes + h_ptr.nbytes + h_idx.nbytes + h_bg.nbytes + h_e.nbytes
+    # bytes that crossed PCIe: the library narrows the fp64 values to bytes on host threads before the
+    # copy (cv_hostnarrow.cpp), so fewer bytes travel than the host buffers hold
+    h2d = int(e2e_stats.get("h2d_bytes", 0)) or host_in
     d2h = 2 * K * N * 8 + 3 * K * 8
 
     if rank != 0:
@@ -477,6 +481,7 @@ def run_ours(args):
                    "path": ("dense_tcgen05_cta_pair" if tile_cells == 256 else "dense_tcgen05") if path == 1
                    else "row_gather_spmm"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "host_input_bytes_per_step": int(host_in),
                 "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
                 "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
                 "gemm_kernel": ("k_dense_contract_fp4" if e2e_stats.get("operand_bits") == 4 else "k_dense_contract_pair") if e2e_stats["cell_tile"] == 256 else
@@ -531,6 +536,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="number of timed e2e steps (default min(steps, 10))")
     ap.add_argument("--gen", default="auto", choices=["auto", "host", "device"],
                     help="synthetic counts on the host (numpy) or on the GPU (same model, torch); auto: GPU for >= 5e8 nonzeros")
+    ap.add_argument("--host-narrow", type=int, default=1, help="e2e call: 0 sends the fp64 values as they are, 1 narrows them to bytes on host threads (default), n > 1: with n threads")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")

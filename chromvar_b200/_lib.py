@@ -28,7 +28,7 @@ EXPORTS = [
     "cv_deviations_csc",
     "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
-    "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms",
+    "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms", "cv_host_narrow",
 ]
 
 
@@ -101,6 +101,7 @@ def load(build_if_missing=True):
         "cv_bg_sample_helper": (i32, [vp, i64, vp, i64, vp, vp, i32, vp]),
         "cv_euc_dist": (i32, [vp, i64, i64, vp, vp]),
         "cv_stats": (i32, [vp, C.POINTER(StageStats)]),
+        "cv_host_narrow": (i32, [vp, i32, i64, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError if the export is missing: loud on purpose
@@ -112,6 +113,18 @@ def load(build_if_missing=True):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def host_narrow(x, threads=4):
+    """cv_host_narrow: (ok, bytes) -- the host-side conversion of wide count values to bytes that
+    cv_deviations_csc applies before the upload.  Host only, needs no GPU."""
+    x = np.ascontiguousarray(x)
+    t = {np.dtype(np.float64): CV_F64, np.dtype(np.float32): CV_F32, np.dtype(np.int32): CV_I32}[x.dtype]
+    out = np.empty(x.size, np.uint8)
+    rc = load().cv_host_narrow(_ptr(x), t, x.size, _ptr(out), int(threads))
+    if rc < 0:
+        raise ChromVARError(-rc, "cv_host_narrow: bad arguments")
+    return bool(rc), out
 
 
 def _carr(a, dtype):

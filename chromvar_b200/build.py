@@ -18,7 +18,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libchromvar_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["cv_counts.cu", "cv_deviations.cu", "cv_dense.cu", "cv_dense_fp4.cu", "cv_dense_build.cu", "cv_background.cu", "cv_knn.cu", "cv_compat.cu"]
+SOURCES = ["cv_counts.cu", "cv_deviations.cu", "cv_dense.cu", "cv_dense_fp4.cu", "cv_dense_build.cu", "cv_background.cu", "cv_knn.cu", "cv_compat.cu", "cv_hostnarrow.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
     relink = force or not os.path.exists(LIB)
     for src in sources:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
         stamp = obj + ".sha"
         dig = _digest([path] + headers, " ".join(NVCC_FLAGS))
         old = open(stamp).read() if os.path.exists(stamp) else ""

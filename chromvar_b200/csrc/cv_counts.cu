@@ -131,6 +131,8 @@ extern "C" void cv_destroy(cv_handle* h) {
   for (int i = 0; i < 4; ++i)
     if (h->ev_aux[i]) cudaEventDestroy(h->ev_aux[i]);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->narrower) cv_narrower_destroy(h->narrower);
+  if (h->stage8) cudaFreeHost(h->stage8);
   if (h->s_up) cudaStreamDestroy(h->s_up);
   if (h->s_dn) cudaStreamDestroy(h->s_dn);
   if (h->s_aux) cudaStreamDestroy(h->s_aux);
@@ -172,6 +174,16 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
+  if (!strcmp(key, "host_narrow")) {
+    // 0: the counts' values cross PCIe in the caller's type; n >= 1: narrowed to bytes on the host
+    // first (cv_hostnarrow.cpp), n = 1 with the default number of threads, n > 1 with n threads
+    h->opt_host_narrow = (int)(value < 0 ? 1 : value);
+    if (h->narrower && value > 1 && cv_narrower_threads(h->narrower) != (int)value) {
+      cv_narrower_destroy(h->narrower);
+      h->narrower = nullptr;
+    }
+    return CV_OK;
+  }
   CV_FAIL(h, CV_ERR_INVALID, "unknown option %s", key);
 }
 

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 #include <numeric>
 
 #include "cv_internal.cuh"
@@ -476,6 +477,8 @@ struct DevIO {
   const char* h_x = nullptr;
   int x_type = 0;
   size_t xb = 0;
+  bool narrow = false;               // values are being narrowed to bytes on host threads (h->narrower -> h->stage8)
+  int64_t x_bytes_sent = 0;          // bytes of values that actually crossed PCIe
   // results leaving chunk by chunk (K x N column-major: a cell chunk is a contiguous slab)
   double* out_dev = nullptr;
   double* out_z = nullptr;
@@ -486,18 +489,30 @@ struct DevIO {
 // Chunk [c0, c1) of the counts: H2D of its row indices and values, K1 on what arrived (validation,
 // u32 values, per-peak / per-cell totals, fragments per sample), and a snapshot of the K1 flag
 // words into pinned host memory -- all on the upload stream, so it runs ahead of the GEMMs.
-static int enqueue_counts_upload(cv_handle* h, const DevIO& io, int64_t c0, int64_t c1, int chunk_index,
+static int enqueue_counts_upload(cv_handle* h, DevIO& io, int64_t c0, int64_t c1, int chunk_index,
                                  cudaEvent_t done) {
   const int64_t e0 = io.h_colptr[c0], e1 = io.h_colptr[c1];
+  int x_type = io.x_type;
   if (e1 > e0) {
     CV_CUDA(h, cudaMemcpyAsync(h->rowidx.as<int32_t>() + e0, io.h_rowidx + e0, (size_t)(e1 - e0) * 4,
                                cudaMemcpyHostToDevice, h->s_up));
-    CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0 * io.xb, io.h_x + (size_t)e0 * io.xb,
-                               (size_t)(e1 - e0) * io.xb, cudaMemcpyHostToDevice, h->s_up));
+    // the row indices are on their way while the last slices of this chunk finish narrowing.
+    // xraw is staging only (K1 of this chunk reads it on the same stream before the next chunk's
+    // copy lands), so a byte chunk and a chunk in the caller's type may share it.
+    if (io.narrow && cv_narrower_wait(h->narrower, e0, e1)) {
+      CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0, h->stage8 + e0, (size_t)(e1 - e0),
+                                 cudaMemcpyHostToDevice, h->s_up));
+      x_type = CV_U8;
+      io.x_bytes_sent += e1 - e0;
+    } else {
+      CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0 * io.xb, io.h_x + (size_t)e0 * io.xb,
+                                 (size_t)(e1 - e0) * io.xb, cudaMemcpyHostToDevice, h->s_up));
+      io.x_bytes_sent += (e1 - e0) * (int64_t)io.xb;
+    }
   }
   cudaStream_t compute = h->stream;
   h->stream = h->s_up;                                   // CV_LAUNCH targets h->stream
-  int rc = cv_counts_range(h, io.x_type, e0, e1, c0, c1);
+  int rc = cv_counts_range(h, x_type, e0, e1, c0, c1);
   h->stream = compute;
   CV_TRY(rc);
   CV_CUDA(h, cudaMemcpyAsync(h->pinned + 4 * chunk_index, h->flags.p, 16, cudaMemcpyDeviceToHost, h->s_up));
@@ -1049,7 +1064,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
       CV_CUDA(h, cudaMemcpyAsync(h->colptr.p, cp64.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
       int rc = upload_annotations(h, K, annoptr, annoidx, index_base, bg, B, expectation, h->stream);
       if (rc != CV_OK) return rc;
-      int64_t h2d_b = h->st.h2d_bytes + (N + 1) * 8 + nnz * (int64_t)(4 + xb);
+      int64_t h2d_b = h->st.h2d_bytes + (N + 1) * 8 + nnz * 4;
       h->have_anno = true;
       DevIO io;
       io.stream_counts = true;
@@ -1060,12 +1075,39 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
       io.xb = xb;
       io.out_dev = out_dev;
       io.out_z = out_z;
+      // wide value types (R: double) are narrowed to bytes by host threads while the annotations
+      // travel and the operand is built; each chunk's upload waits for its own slices only
+      struct NarrowGuard {                      // the caller's x must not be read after the call returns
+        cv_handle* h;
+        ~NarrowGuard() { if (h->narrower) cv_narrower_finish(h->narrower); }
+      } narrow_guard{h};
+      if (h->opt_host_narrow && xb > 1) {
+        if (!h->narrower) {
+          int ndev = 1;
+          cudaGetDeviceCount(&ndev);
+          const int hw = (int)std::thread::hardware_concurrency();
+          const int t = h->opt_host_narrow > 1 ? h->opt_host_narrow : std::max(1, std::min(8, hw / std::max(ndev, 1) - 1));
+          h->narrower = cv_narrower_create(t);
+        }
+        if (h->stage8_cap < (size_t)nnz) {
+          if (h->stage8) cudaFreeHost(h->stage8);
+          h->stage8 = nullptr;
+          h->stage8_cap = 0;
+          if (cudaHostAlloc((void**)&h->stage8, (size_t)nnz, cudaHostAllocDefault) == cudaSuccess) h->stage8_cap = (size_t)nnz;
+          else cudaGetLastError();              // no page-locked memory to spare: the values travel as they are
+        }
+        if (h->stage8_cap >= (size_t)nnz) {
+          cv_narrower_start(h->narrower, x, x_type, nnz, h->stage8);
+          io.narrow = true;
+        }
+      }
       rc = deviations_run(h, 0, 0, &io);
+      if (h->narrower) cv_narrower_finish(h->narrower);
       if (rc == CV_OK) {
         CV_TRY(download_results(h, io.results_streamed ? nullptr : out_dev, io.results_streamed ? nullptr : out_z,
                                 out_matches, out_overlap, out_variability, nullptr, nullptr));
         h->st.ms_h2d = wall_ms() - t0;          // whole call: copies and kernels overlap
-        h->st.h2d_bytes = h2d_b;
+        h->st.h2d_bytes = h2d_b + io.x_bytes_sent;
         h->st.d2h_bytes += 2 * K * N * 8;
         return CV_OK;
       }

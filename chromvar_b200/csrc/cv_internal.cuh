@@ -69,6 +69,10 @@ struct cv_handle {
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_aux[4] = {};         // operand build: inputs ready, bit columns, table, overlap
   uint32_t* pinned = nullptr;         // CV_PINNED_WORDS of page-locked host memory (flag snapshots)
+  struct cv_narrower* narrower = nullptr;   // host threads converting x to bytes ahead of the uploads (cv_hostnarrow.cpp)
+  uint8_t* stage8 = nullptr;          // page-locked staging of the narrowed values
+  size_t stage8_cap = 0;
+  int opt_host_narrow = 1;            // "host_narrow": 0 keeps the caller's value type on the wire
   // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -182,6 +186,14 @@ int cv_sync_check(cv_handle* h);
 // cv_counts.cu
 int cv_build_layout(cv_handle* h, int W);
 // cv_background.cu: shared sampler back half (bin CDF rows + Philox draws)
+// cv_hostnarrow.cpp
+struct cv_narrower;
+cv_narrower* cv_narrower_create(int threads);
+int cv_narrower_threads(const cv_narrower* nw);
+void cv_narrower_destroy(cv_narrower* nw);
+void cv_narrower_start(cv_narrower* nw, const void* x, int x_type, int64_t n, uint8_t* out);
+int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1);
+void cv_narrower_finish(cv_narrower* nw);
 int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm);
 int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
                          const double* d_binp_colmajor, const double* d_bin_xy, double w,

@@ -217,6 +217,12 @@ typedef struct cv_stage_stats {
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
 
+/* Host-only: the conversion cv_deviations_csc applies to wide value types before the upload
+ * ("host_narrow" option; a dgCMatrix's x slot is double, R/helper_functions.R:50-88).  x_type CV_F64 /
+ * CV_F32 / CV_I32.  Returns 1 when every value is an integer in 0..255 and out[0, n) holds them,
+ * 0 when some value is not (out is then unspecified), < 0 on bad arguments.  No GPU involved. */
+int cv_host_narrow(const void* x, int x_type, int64_t n, uint8_t* out, int threads);
+
 /* Diagnostic (no device needed): how the e2m1 variant of the dense path writes the integer v -- its
  * terms (each in {1,2,3,4,6}, summing to v; 5 = 4+1, 13 = 6+6+1) and their 4-bit e2m1 codes.  Returns
  * the number of terms (1 for v = 0), or -1 when max_terms is too small.  terms / codes may be NULL. */

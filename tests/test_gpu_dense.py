@@ -327,3 +327,43 @@ def test_dense_many_peaks(dense_engine, maxcount):
     assert st["path"] == 1 and st["planes"] == (1 if maxcount < 256 else 2)
     ref = orc.compute_deviations_core(C, sets, bg, e, intermediate=True)
     check_against_oracle(got, ref)
+
+
+def test_streamed_call_host_narrowing(engine):
+    """Wide value types are narrowed to bytes on host threads before the upload ("host_narrow"):
+    same results bit for bit, fewer bytes on the wire; a chunk holding a count above 255 travels in
+    the caller's type while the other chunks still travel as bytes."""
+    C, P, N, bg, e, ptr, idx = _small_problem()
+    engine.set_option("path", 2)
+    try:
+        engine.set_option("cell_chunk", 512)
+        x64 = C.data.astype(np.float64)
+        engine.set_option("host_narrow", 0)
+        base = engine.deviations_csc(P, N, C.indptr, C.indices, x64, ptr, idx, bg, e)
+        wide = engine.stats()["h2d_bytes"]
+        for threads in (1, 3):
+            engine.set_option("host_narrow", threads)
+            got = engine.deviations_csc(P, N, C.indptr, C.indices, x64, ptr, idx, bg, e)
+            st = engine.stats()
+            assert st["n_cell_tiles"] >= 2
+            assert wide - st["h2d_bytes"] == 7 * C.nnz                   # 1 byte instead of 8 per nonzero
+            for key in ("dev", "z", "variability", "matches", "overlap"):
+                assert np.array_equal(got[key], base[key], equal_nan=True), key
+            fpp, fps, tot = engine.fragments()
+            assert np.array_equal(fpp, np.asarray(C.sum(axis=1)).ravel()) and tot == C.sum()
+        # one large count in the last cell: only the chunks whose slices hold it keep 8 bytes per value
+        x = x64.copy()
+        x[-3] = 700.0
+        C2 = sp.csc_matrix((x, C.indices, C.indptr), shape=C.shape)
+        e2 = np.asarray(C2.sum(axis=1)).ravel() / C2.sum()
+        engine.set_option("host_narrow", 0)
+        ref = engine.deviations_csc(P, N, C.indptr, C.indices, x, ptr, idx, bg, e2)
+        engine.set_option("host_narrow", 1)
+        got = engine.deviations_csc(P, N, C.indptr, C.indices, x, ptr, idx, bg, e2)
+        assert engine.stats()["planes"] == 2
+        for key in ("dev", "z", "variability"):
+            assert np.array_equal(got[key], ref[key], equal_nan=True), key
+    finally:
+        engine.set_option("path", 0)
+        engine.set_option("cell_chunk", 0)
+        engine.set_option("host_narrow", 1)

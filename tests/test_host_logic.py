@@ -94,3 +94,30 @@ def test_e2m1_term_decomposition():
         assert [value_of_code[codes[i]] for i in range(n)] == [float(x) for x in t]
         assert n == (1 if v in (0, 1, 2, 3, 4, 6) else v // 6 + (0 if v % 6 == 0 else 2 if v % 6 == 5 else 1))
     assert lib.cv_e2m1_terms(65, terms, codes, 4) == -1
+
+
+def test_host_narrow():
+    """The host-side conversion of a dgCMatrix's double x slot to bytes (cv_hostnarrow.cpp): exact for
+    integers 0..255, and anything else -- a large count, a fraction, a negative, NaN, Inf -- is reported
+    so that chunk travels in its original type.  Slices of 2^18 elements on several threads."""
+    from chromvar_b200 import _lib
+    rng = np.random.default_rng(0)
+    n = (1 << 20) + 12345                         # several slices and a ragged tail
+    v = rng.integers(0, 256, n)
+    for dt in (np.float64, np.float32, np.int32):
+        for threads in (1, 3):
+            ok, out = _lib.host_narrow(v.astype(dt), threads)
+            assert ok and np.array_equal(out, v.astype(np.uint8)), (dt, threads)
+    ok, out = _lib.host_narrow(np.zeros(0), 2)
+    assert ok and out.size == 0
+    for bad, where in ((256.0, 5), (0.5, n - 1), (-1.0, 300000), (np.nan, 7), (np.inf, n // 2), (1e300, 11), (-0.5, 1 << 18)):
+        x = v.astype(np.float64)
+        x[where] = bad
+        ok, _ = _lib.host_narrow(x, 3)
+        assert not ok, (bad, where)
+    x = v.astype(np.float64)
+    x[123] = -0.0                                 # negative zero is the integer 0
+    ok, out = _lib.host_narrow(x, 2)
+    assert ok and out[123] == 0
+    ok, _ = _lib.host_narrow(np.array([7, 300, 2], np.int32), 1)
+    assert not ok
