@@ -536,7 +536,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="number of timed e2e steps (default min(steps, 10))")
     ap.add_argument("--gen", default="auto", choices=["auto", "host", "device"],
                     help="synthetic counts on the host (numpy) or on the GPU (same model, torch); auto: GPU for >= 5e8 nonzeros")
-    ap.add_argument("--host-narrow", type=int, default=1, help="e2e call: 0 sends the fp64 values as they are, 1 narrows them to bytes on host threads (default), n > 1: with n threads")
+    ap.add_argument("--host-narrow", type=int, default=0, help="e2e call: 0 sends the fp64 values as they are (default), 1 narrows them to bytes on host threads, n > 1: with n threads")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")
@@ -546,7 +546,18 @@ def main():
     ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
     ap.add_argument("--pair", type=int, default=-1, help="dense GEMM kernel: 1 CTA pair (cta_group::2), 0 single CTA, -1 library default (by context)")
+    ap.add_argument("--pin-cores", type=int, default=0,
+                    help="multi-GPU experiment: 1 keeps each rank on its own block of host cores (cores / ranks, by "
+                         "local rank); measured on 8x B200 / 32 cores: no gain for the e2e call, device-timed step slower")
     args = ap.parse_args()
+    ws_env, local_env = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "ours" and ws_env > 1 and args.pin_cores != 0 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // ws_env)
+            os.sched_setaffinity(0, cores[local_env * per:(local_env + 1) * per] or cores)
+        except OSError:
+            pass
     if args.warmup < 3 and not args.quick and args.impl == "ours":
         log("[bench] warning: fewer than 3 warm-up steps")
     if args.impl == "reference":

@@ -175,9 +175,11 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
   if (!strcmp(key, "host_narrow")) {
-    // 0: the counts' values cross PCIe in the caller's type; n >= 1: narrowed to bytes on the host
-    // first (cv_hostnarrow.cpp), n = 1 with the default number of threads, n > 1 with n threads
-    h->opt_host_narrow = (int)(value < 0 ? 1 : value);
+    // 0 (default): the counts' values cross PCIe in the caller's type; n >= 1: narrowed to bytes on the
+    // host first (cv_hostnarrow.cpp), n = 1 with the default number of threads, n > 1 with n threads.
+    // Measured (profiles/r01u_summary.md): neutral on one GPU with page-locked buffers (the call is
+    // compute-bound), a loss on an 8-GPU host with 4 cores per GPU (the conversion competes for cores)
+    h->opt_host_narrow = (int)(value < 0 ? 0 : value);
     if (h->narrower && value > 1 && cv_narrower_threads(h->narrower) != (int)value) {
       cv_narrower_destroy(h->narrower);
       h->narrower = nullptr;

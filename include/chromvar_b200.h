@@ -78,7 +78,11 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *   "dense_rows_scatter" 1 builds the operand rows with the per-annotation scatter kernel only
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
- *                      0 for a shard of a larger matrix (the caller checks the reduced totals) */
+ *                      0 for a shard of a larger matrix (the caller checks the reduced totals)
+ *   "host_narrow"      cv_deviations_csc: 0 (default) the counts' values cross PCIe in the caller's type;
+ *                      1: host threads convert wide types (a dgCMatrix's double x) to bytes ahead of the
+ *                      uploads, chunks holding anything but integers 0..255 still travel as they are;
+ *                      n > 1: with n threads.  Same results bit for bit. */
 int cv_set_option(cv_handle* h, const char* key, int64_t value);
 /* the CUDA stream all of this handle's kernels run on (a cudaStream_t), for event timing */
 void* cv_stream(cv_handle* h);

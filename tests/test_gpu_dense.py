@@ -366,4 +366,4 @@ def test_streamed_call_host_narrowing(engine):
     finally:
         engine.set_option("path", 0)
         engine.set_option("cell_chunk", 0)
-        engine.set_option("host_narrow", 1)
+        engine.set_option("host_narrow", 0)
