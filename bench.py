@@ -330,6 +330,13 @@ def run_ours(args):
     bg = eng.background_peaks(d["bias"], NITER, 0.1, 50)
     t_bg = time.perf_counter() - t0
     bg_ms_dev = eng.stats()["ms_background"]
+    # the sampler of makePermutedSets (get_background_peaks_alternative, R/test_sets.R:291-330): exact
+    # 10 nearest neighbours of every peak in the whitened (fragments, bias) plane + the draws
+    eng.background_peaks_knn(d["bias"], NITER, 10)
+    t0 = time.perf_counter()
+    eng.background_peaks_knn(d["bias"], NITER, 10)
+    t_knn = time.perf_counter() - t0
+    knn_ms_dev = eng.stats()["ms_background"]
     h_bg, h_e = pin(bg), pin(e)
     eng.deviations_upload(h_ptr, h_idx, h_bg, h_e, index_base=1)
 
@@ -499,7 +506,9 @@ def run_ours(args):
                               (stage_acc / args.steps).round(4).tolist())),
         "other_paths": {"getBackgroundPeaks_ms_device": bg_ms_dev, "getBackgroundPeaks_ms_wall": 1e3 * t_bg,
                         "sampled_indices_per_s": P * NITER / max(t_bg, 1e-9),
-                        "computeExpectations_ms_wall": 1e3 * t_exp},
+                        "computeExpectations_ms_wall": 1e3 * t_exp,
+                        "backgroundPeaksAlternative_window10_ms_device": knn_ms_dev,
+                        "backgroundPeaksAlternative_window10_ms_wall": 1e3 * t_knn},
     }
     emit_json(line)
 
