@@ -105,7 +105,10 @@ def test_make_permuted_sets(golden_mini):
     names = [str(n) for n in g["ix_names"]]
     ix = api.SummarizedExperiment({"matches": A}, colData={"name": np.asarray(names)}, colnames=names)
     api.set_seed(5)
-    out = synergy.makePermutedSets(counts, ix, window=10)
+    try:
+        out = synergy.makePermutedSets(counts, ix, window=10)
+    finally:
+        api._seed_rng = None                      # like leaving set.seed() behind: later tests fix the engine seed themselves
     M = out.assays["matches"]
     assert M.shape == A.shape and M.dtype == bool
     assert list(out.colData["name"]) == ["permuted.%s" % n for n in names]
