@@ -171,7 +171,17 @@ int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1) {
     uint8_t f;
     int spins = 0;
     while ((f = nw->flag[(size_t)s].load(std::memory_order_acquire)) == 0) {
-      if (nw->next.load(std::memory_order_relaxed) >= nw->n_slices && s >= nw->n_slices) return 0;
+      if (nw->next.load(std::memory_order_relaxed) >= nw->n_slices) {
+        // every slice has been handed out or dropped (cv_narrower_finish): when no worker is busy
+        // nobody will ever set this flag, so the waiting thread converts the slice itself
+        std::unique_lock<std::mutex> lk(nw->mu);
+        if (nw->active == 0 && nw->flag[(size_t)s].load(std::memory_order_acquire) == 0) {
+          const int64_t a = s * SLICE, b = std::min(nw->n, a + SLICE);
+          const bool ok1 = narrow_any(nw->x, nw->x_type, a, nw->out + a, b - a);
+          nw->flag[(size_t)s].store(ok1 ? 1 : 2, std::memory_order_release);
+          continue;
+        }
+      }
       if (++spins > 64) std::this_thread::yield();
     }
     if (f != 1) ok = 0;
