@@ -293,6 +293,7 @@ def run_ours(args):
     eng.set_option("dense_fp4", args.fp4)
     eng.set_option("dense_lockstep", args.lockstep)
     eng.set_option("host_narrow", args.host_narrow)
+    eng.set_option("tail_chunk", args.tail_chunk)
     if args.chunk:
         eng.set_option("cell_chunk", args.chunk)
     if args.band:
@@ -490,6 +491,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "host_input_bytes_per_step": int(host_in),
                 "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
+                "ms_per_step_median": float(np.median(e2e_each)),
                 "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
                 "gemm_kernel": ("k_dense_contract_fp4" if e2e_stats.get("operand_bits") == 4 else "k_dense_contract_pair") if e2e_stats["cell_tile"] == 256 else
                 ("k_dense_contract" if e2e_stats["path"] == 1 else "k_contract"),
@@ -555,6 +557,7 @@ def main():
     ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
     ap.add_argument("--pair", type=int, default=-1, help="dense GEMM kernel: 1 CTA pair (cta_group::2), 0 single CTA, -1 library default (by context)")
+    ap.add_argument("--tail-chunk", type=int, default=1, help="e2e call: 1 (default) ends with a short fourth cell chunk, 0: three chunks")
     ap.add_argument("--pin-cores", type=int, default=0,
                     help="multi-GPU experiment: 1 keeps each rank on its own block of host cores (cores / ranks, by "
                          "local rank); measured on 8x B200 / 32 cores: no gain for the e2e call, device-timed step slower")

@@ -174,6 +174,7 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
+  if (!strcmp(key, "tail_chunk")) { h->opt_tail_chunk = value != 0; return CV_OK; }
   if (!strcmp(key, "host_narrow")) {
     // 0 (default): the counts' values cross PCIe in the caller's type; n >= 1: narrowed to bytes on the
     // host first (cv_hostnarrow.cpp), n = 1 with the default number of threads, n > 1 with n threads.

@@ -604,6 +604,18 @@ static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int6
     return b;
   }
   b = {0, ba * 256, (ba + bb) * 256, N};
+  if (streaming && h->opt_tail_chunk && U >= 24) {
+    // results leave for the host one chunk behind the GEMMs, so the copy of the LAST chunk's results
+    // is exposed at the end of the call: a short fourth chunk (an eighth of the third, whole waves
+    // kept where possible) shortens that tail by more than one more round of per-chunk launches costs
+    const int64_t c3 = U - ba - bb;
+    int64_t best_d = 0, best_cost = -1;
+    for (int64_t d = std::max<int64_t>(1, c3 / 12); d <= std::max<int64_t>(1, c3 / 3); ++d) {
+      const int64_t cost = (waves(c3 - d) + waves(d)) * 4096 + d * 1160;   // a wave ~ 0.23 ms, a unit of results ~ 0.065 ms on the wire
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_d = d; }
+    }
+    if (best_d > 0 && c3 - best_d >= 1) b = {0, ba * 256, (ba + bb) * 256, (U - best_d) * 256, N};
+  }
   return b;
 }
 

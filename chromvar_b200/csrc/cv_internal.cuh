@@ -72,6 +72,7 @@ struct cv_handle {
   struct cv_narrower* narrower = nullptr;   // host threads converting x to bytes ahead of the uploads (cv_hostnarrow.cpp)
   uint8_t* stage8 = nullptr;          // page-locked staging of the narrowed values
   size_t stage8_cap = 0;
+  int opt_tail_chunk = 1;             // "tail_chunk": streamed call ends with a short fourth cell chunk
   int opt_host_narrow = 0;            // "host_narrow": 0 (default) keeps the caller's value type on the wire
   // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
   std::vector<cudaEvent_t> ev_pool;

@@ -79,6 +79,8 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
  *                      0 for a shard of a larger matrix (the caller checks the reduced totals)
+ *   "tail_chunk"       cv_deviations_csc: 1 (default) a short fourth cell chunk ends the call so that little
+ *                      of the results is still on its way to the host when the last GEMM finishes; 0: three chunks
  *   "host_narrow"      cv_deviations_csc: 0 (default) the counts' values cross PCIe in the caller's type;
  *                      1: host threads convert wide types (a dgCMatrix's double x) to bytes ahead of the
  *                      uploads, chunks holding anything but integers 0..255 still travel as they are;
