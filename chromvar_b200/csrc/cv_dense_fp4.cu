@@ -305,7 +305,7 @@ k_f4_rows_ov(const uint32_t* __restrict__ Abits, const uint32_t* __restrict__ in
 // ---- operand Cd4: one cell per CTA iteration, nibbles set with shared-memory atomicOr ---------------------------
 // Row r of Cd4 = cell c0 + r (zero row past the last cell).  The row (peak columns + used overflow
 // columns) is built in pieces of `piece` bytes.
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, 3)
 k_f4_cells(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx, const uint32_t* __restrict__ val,
            int N, int c0, int n_rows_padded, const uint32_t* __restrict__ Tq, const uint32_t* __restrict__ Sq,
            const uint32_t* __restrict__ off, const uint32_t* __restrict__ info, int64_t Pb, int64_t rowb, int piece,
@@ -639,11 +639,20 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
               pl.Ga, pl.Gb, pl.rowb, Pb, h->dn_M.as<uint8_t>(), dflags);
   }
   {
+    // a cell is latency-bound (zero the row, a few dependent loads per thread, write the row), so up
+    // to three CTAs share an SM when a row's peak columns plus 8 KB of overflow columns fit a third of
+    // its shared memory (config 2: 50 KB of peak columns -> 3 CTAs of 74.75 KB; ncu capture X: one CTA
+    // per SM kept 25 % of the warp slots busy); longer rows are built in pieces by one CTA per SM
     const int budget = h->max_smem_optin - 2048;
-    const int piece = (int)std::min<int64_t>(pl.rowb, (budget / 128) * 128);
+    const int64_t sm_total = (int64_t)h->max_smem_optin + 1024;            // per SM: the opt-in maximum plus one CTA's reserve
+    int nc = 1;
+    for (int c = 3; c >= 2; --c)
+      if (sm_total / c - 1280 >= Pb + 8192) { nc = c; break; }
+    const int piece = nc == 1 ? (int)std::min<int64_t>(pl.rowb, (budget / 128) * 128)
+                              : (int)std::min<int64_t>(pl.rowb, ((sm_total / nc - 1280) / 128) * 128);
     CV_CUDA(h, cudaMemsetAsync(h->work_ctr.as<uint32_t>() + 1, 0, 4, h->stream));
     CV_CUDA(h, cudaFuncSetAttribute(k_f4_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, piece));
-    CV_LAUNCH(h, k_f4_cells, (unsigned)std::min<int64_t>(rows, (int64_t)h->num_sms), 512, (size_t)piece,
+    CV_LAUNCH(h, k_f4_cells, (unsigned)std::min<int64_t>(rows, (int64_t)h->num_sms * nc), 512, (size_t)piece,
               h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), (int)h->N, (int)c0, (int)rows,
               h->f4_Tq.as<uint32_t>(), h->f4_Sq.as<uint32_t>(), h->f4_off.as<uint32_t>(), info, Pb, pl.rowb, piece,
               h->dn_C.as<uint8_t>(), h->work_ctr.as<uint32_t>() + 1, dflags);
