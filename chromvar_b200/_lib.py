@@ -26,7 +26,8 @@ EXPORTS = [
     "cv_set_counts_csc", "cv_set_counts_dense", "cv_fragments", "cv_peak_totals_device",
     "cv_peak_totals_commit", "cv_expectations", "cv_background_peaks", "cv_background_peaks_knn", "cv_deviations",
     "cv_deviations_csc",
-    "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_download",
+    "cv_deviations_upload", "cv_deviations_compute", "cv_deviations_compute_async", "cv_deviations_wait",
+    "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
     "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms", "cv_host_narrow",
 ]
@@ -92,6 +93,8 @@ def load(build_if_missing=True):
                                     vp, vp, vp, vp, vp]),
         "cv_deviations_upload": (i32, [vp, i64, vp, vp, i32, vp, i32, vp]),
         "cv_deviations_compute": (i32, [vp, i32, i32]),
+        "cv_deviations_compute_async": (i32, [vp, i32]),
+        "cv_deviations_wait": (i32, [vp]),
         "cv_deviations_download": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "cv_variability_partials_device": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "cv_merge_variability": (i32, [vp, i32, i64, i32, vp]),
@@ -280,6 +283,14 @@ class Handle:
 
     def deviations_compute(self, rebuild_counts_layout=False, keep_sums=False):
         self._check(self.lib.cv_deviations_compute(self._h, int(rebuild_counts_layout), int(keep_sums)))
+
+    def deviations_compute_async(self, rebuild_counts_layout=False):
+        """cv_deviations_compute without host synchronisation (a replay of the last checked call on
+        the same resident inputs); deviations_wait() or any reading call settles it."""
+        self._check(self.lib.cv_deviations_compute_async(self._h, int(rebuild_counts_layout)))
+
+    def deviations_wait(self):
+        self._check(self.lib.cv_deviations_wait(self._h))
 
     def deviations_download(self, sums=False, out=None, vectors_only=False):
         K, N, B = self.K, self.N, self.B

@@ -114,6 +114,7 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
 extern "C" void cv_destroy(cv_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  h->async_pending = false;
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->colptr, &h->rowidx, &h->val, &h->xraw, &h->peak_tot, &h->peak_loc,
                     &h->cell_tot, &h->fps, &h->flags, &h->tcnt, &h->rowptr, &h->entries,
@@ -152,6 +153,8 @@ extern "C" int cv_set_seed(cv_handle* h, uint64_t seed) {
 
 extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!h || !key) return CV_ERR_INVALID;
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;                    // options change which kernels run
   if (!strcmp(key, "path")) {
     if (value < 0 || value > 2) CV_FAIL(h, CV_ERR_INVALID, "path must be 0 (auto), 1 (row-gather SpMM) or 2 (dense tcgen05)");
     h->opt_path = (int)value;
@@ -225,6 +228,7 @@ extern "C" void* cv_stream(cv_handle* h) { return h ? (void*)h->stream : nullptr
 
 extern "C" int cv_stats(cv_handle* h, cv_stage_stats* out) {
   if (!h || !out) return CV_ERR_INVALID;
+  CV_TRY(cv_settle(h));
   h->st.kernel_launches = h->launches;
   *out = h->st;
   return CV_OK;
@@ -756,6 +760,8 @@ extern "C" int cv_set_counts_csc(cv_handle* h, int64_t P, int64_t N, const void*
                                  int x_type) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;
   h->have_counts = false;
   if (P <= 0 || N <= 0 || !colptr) CV_FAIL(h, CV_ERR_INVALID, "counts: empty matrix");
   if (P > 0x7fffffff || N > 0x7fffffff) CV_FAIL(h, CV_ERR_UNSUPPORTED, "P, N must be < 2^31");
@@ -840,6 +846,8 @@ static int dense_to_csc(cv_handle* h, const XT* xd, int64_t P, int64_t N) {
 extern "C" int cv_set_counts_dense(cv_handle* h, int64_t P, int64_t N, const void* x, int x_type) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;
   h->have_counts = false;
   if (P <= 0 || N <= 0 || !x) CV_FAIL(h, CV_ERR_INVALID, "counts: empty matrix");
   if (P > 0x7fffffff || N > 0x7fffffff) CV_FAIL(h, CV_ERR_UNSUPPORTED, "P, N must be < 2^31");
@@ -893,6 +901,8 @@ extern "C" int cv_fragments(cv_handle* h, double* out_per_peak, double* out_per_
 
 extern "C" int cv_peak_totals_device(cv_handle* h, void** dptr, int64_t* n_elems) {
   if (!h || !dptr) return CV_ERR_INVALID;
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;                    // the totals are about to be rewritten by the caller
   if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
   // keep the shard-local totals: the norm/group expectation variants are per-shard quantities
   CV_TRY(cv_ensure(h, h->peak_loc, (size_t)(h->P + 1) * 8));

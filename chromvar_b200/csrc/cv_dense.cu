@@ -593,7 +593,7 @@ int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, in
     const bool want32 = h->opt_epilogue == 1 ||
                         (h->opt_epilogue == 0 && pl.Ppad4 / 256 < 1100 && tiles >= 4 * (int64_t)h->num_sms);
     const int fx = want32 && h->dn_fixed_ok;
-    CV_TRY(cv_f4_chunk(h, pl, prm, c0, std::min<int64_t>(c1, N), rows, fx, c0 == 0));
+    CV_TRY(cv_f4_chunk(h, pl, prm, c0, std::min<int64_t>(c1, N), rows, fx, c0 == 0 && !h->replaying));
     h->st.epilogue = fx ? 32 : 64;
     h->dn_flops += 2.0 * (double)pl.rowsM4 * (double)rows * (double)pl.Ppad4;
     return CV_OK;

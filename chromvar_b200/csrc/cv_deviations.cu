@@ -450,6 +450,8 @@ extern "C" int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* anno
                                     int B, const double* expectation) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;
   if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
   if (!expectation) CV_FAIL(h, CV_ERR_INVALID, "expectation is NULL");
   double t0 = wall_ms();
@@ -625,6 +627,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   const int B = h->B, I = B + 1;
   const bool streaming = io && io->stream_counts;
   h->have_results = false;
+  if (!h->replaying) h->replay_valid = false;            // re-established at the end of a clean checked run
   cv_spans_reset(h);
 
   // accumulator width of the row-gather path: |sum| <= (largest set) * (largest count)
@@ -632,6 +635,8 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   for (int64_t k = 0; k < K; ++k) set_max = std::max(set_max, h->h_annoptr[k + 1] - h->h_annoptr[k]);
 
   int use_dense = 0, dense_chunks_used = 0;
+  bool verdict_clean = false;
+  uint32_t verdict_hf[16] = {};
   DensePlan pl;
   {
     // about three GEMM launches per call: host copies overlap them chunk by chunk (config 2, e2m1
@@ -695,8 +700,14 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     // multiplicity bounds of the u8 operand before any GEMM runs (one short host sync; the first
     // counts chunk is already in flight)
     uint32_t hf[16];
-    CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
-    CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->replaying) {
+      memcpy(hf, h->replay_hf, 64);                          // same inputs, same kernels: same words
+    } else {
+      CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
+      CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    bool clean = !streaming && !keep_sums && hf[CV_DFLAGS + 3] == 0;   // may this call's verdict be replayed?
+    memcpy(verdict_hf, hf, 64);
     if (hf[CV_DFLAGS] & FLAG_BADIDX)
       CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
     if (hf[CV_DFLAGS + 3]) {
@@ -722,6 +733,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       // alphabet on most peaks: dense k-mer annotations) already fills the overflow reserve, or an
       // entry passed 15: u8 operands / s32 accumulators instead.  Only the operand rows are redone
       // (bit columns, inverse background map and the per-annotation tables do not depend on the format).
+      clean = false;
       CV_CUDA(h, cudaMemsetAsync(dflags + 5, 0, 12, h->stream));
       cv_dense_plan_set_fp4(&pl, 0);
       CV_TRY(cv_ensure(h, h->dn_M, (size_t)pl.m_bytes));
@@ -730,6 +742,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       CV_TRY(cv_dense_rebuild_rows_u8(h, pl));
       cv_span_end(h);
     }
+    verdict_clean = clean && use_dense;
     if (use_dense) {
       const bool dl = io && (io->out_dev || io->out_z);
       int planes_max = pl.planes;
@@ -879,6 +892,16 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   cv_span_end(h);
   uint32_t hf[16];
   unsigned long long upd = 0;
+  if (h->replaying) {
+    // no host in the loop: the flag words travel to page-locked memory behind the kernels and
+    // cv_settle() looks at them (and at the timed spans) once somebody needs the outcome
+    CV_CUDA(h, cudaMemcpyAsync(h->pinned + CV_PINNED_WORDS - 32, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
+    h->st.path = 1;
+    h->st.n_cell_tiles = dense_chunks_used;
+    h->have_results = true;
+    h->async_pending = true;
+    return CV_OK;
+  }
   CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaMemcpyAsync(&upd, h->work_ctr.as<uint32_t>() + 2, 8, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -939,12 +962,61 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     h->st.overflow_columns = 0;
   }
   h->have_results = true;
+  // a clean dense run on resident inputs (no fallback taken, nothing flagged): its verdict can be replayed
+  h->replay_valid = verdict_clean && use_dense && !hf[CV_DFLAGS + 5] && !(hf[CV_DFLAGS] & (FLAG_ZEROPEAK | FLAG_BADIDX));
+  if (h->replay_valid) memcpy(h->replay_hf, verdict_hf, 64);
   return CV_OK;
+}
+
+// Waits for a pending replay (cv_deviations_compute_async) and collects what the checked call
+// collects inline: the flag words and the timed spans.
+int cv_settle(cv_handle* h) {
+  if (!h->async_pending) return CV_OK;
+  h->async_pending = false;
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  const uint32_t* hf = h->pinned + CV_PINNED_WORDS - 32;
+  if ((hf[CV_DFLAGS] & (FLAG_ZEROPEAK | FLAG_BADIDX)) || hf[CV_DFLAGS + 5] || hf[CV_DFLAGS + 3]) {
+    h->have_results = false;
+    h->replay_valid = false;
+    CV_FAIL(h, CV_ERR_STATE, "replayed call raised flags the checked call did not (resident inputs changed?)");
+  }
+  double ms[CV_SPAN_N];
+  cv_spans_collect(h, ms);
+  h->st.ms_counts_layout = ms[CV_SPAN_LAYOUT] + ms[CV_SPAN_K1];
+  h->st.ms_anno_prep = ms[CV_SPAN_ANNO];
+  h->st.ms_contract = ms[CV_SPAN_CONTRACT];
+  h->st.ms_finalize = ms[CV_SPAN_FINALIZE];
+  return CV_OK;
+}
+
+extern "C" int cv_deviations_wait(cv_handle* h) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  return cv_settle(h);
+}
+
+// cv_deviations_compute with the host out of the loop.  When the last fully checked call ran on the
+// same resident inputs and options and took no fallback, every kernel of the path is enqueued again
+// -- same work, same results -- but the host neither waits for the flag words between the stages
+// (their values are known) nor for the end of the call, so consecutive calls queue up behind each
+// other and a descheduled host thread no longer leaves the GPU idle.  Otherwise it is the checked
+// call itself.  cv_deviations_wait (or any call that reads results or changes inputs) settles it.
+extern "C" int cv_deviations_compute_async(cv_handle* h, int rebuild_counts_layout) {
+  if (!h) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (!h->replay_valid || h->opt_path == 1) return cv_deviations_compute(h, rebuild_counts_layout, 0);
+  if (!h->have_counts || !h->have_anno) CV_FAIL(h, CV_ERR_STATE, "counts / annotations not set");
+  h->replaying = true;
+  const int rc = deviations_run(h, rebuild_counts_layout, 0, nullptr);
+  h->replaying = false;
+  if (rc != CV_OK) { h->replay_valid = false; h->async_pending = false; }
+  return rc;
 }
 
 extern "C" int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, int keep_sums) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
   if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
   if (!h->have_anno) CV_FAIL(h, CV_ERR_STATE, "annotations / background not uploaded");
   if (!h->totals_committed)
@@ -992,6 +1064,7 @@ extern "C" int cv_deviations_download(cv_handle* h, double* out_dev, double* out
                                       int64_t* out_sampled) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
   return download_results(h, out_dev, out_z, out_matches, out_overlap, out_variability, out_observed, out_sampled);
 }
 
@@ -1033,6 +1106,8 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
                                  double* out_variability) {
   if (!h) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;
   // the streamed pipeline needs the expectation up front and the dense path; otherwise (or when
   // the dense path turns out not to be exact for these inputs) the call is the plain sequence
   bool try_stream = expectation != nullptr && h->opt_path != 1 && P > 0 && N > 0 && P <= 0x7fffffff &&
@@ -1145,6 +1220,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
 
 extern "C" int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t* n_elems) {
   if (!h || !dptr) return CV_ERR_INVALID;
+  CV_TRY(cv_settle(h));
   if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no results");
   *dptr = h->varfinal.p;
   if (n_elems) *n_elems = h->K * 4;

@@ -72,6 +72,13 @@ struct cv_handle {
   struct cv_narrower* narrower = nullptr;   // host threads converting x to bytes ahead of the uploads (cv_hostnarrow.cpp)
   uint8_t* stage8 = nullptr;          // page-locked staging of the narrowed values
   size_t stage8_cap = 0;
+  // cv_deviations_compute_async: a resident call whose host-side verdicts (index checks, exactness
+  // bounds, e2m1 feasibility) are known from the last fully checked call on the SAME resident inputs
+  // is enqueued without any host synchronisation; cv_deviations_wait settles it
+  bool replay_valid = false;          // verdict below belongs to the current resident inputs and options
+  uint32_t replay_hf[16] = {};        // flag words the checked call read after the operand build
+  bool replaying = false;             // deviations_run is enqueueing a replay
+  bool async_pending = false;         // a replay is in flight: flags / timings not collected yet
   int opt_tail_chunk = 1;             // "tail_chunk": streamed call ends with a short fourth cell chunk
   int opt_host_narrow = 0;            // "host_narrow": 0 (default) keeps the caller's value type on the wire
   // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
@@ -195,6 +202,7 @@ void cv_narrower_destroy(cv_narrower* nw);
 void cv_narrower_start(cv_narrower* nw, const void* x, int x_type, int64_t n, uint8_t* out);
 int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1);
 void cv_narrower_finish(cv_narrower* nw);
+int cv_settle(cv_handle* h);            // cv_deviations.cu: waits for a pending replay and collects its verdict
 int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm);
 int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
                          const double* d_binp_colmajor, const double* d_bin_xy, double w,

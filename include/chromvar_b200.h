@@ -172,6 +172,16 @@ int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr, in
 int cv_deviations_upload(cv_handle* h, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
                          int index_base, const int32_t* bg, int B, const double* expectation);
 int cv_deviations_compute(cv_handle* h, int rebuild_counts_layout, int keep_sums);
+/* cv_deviations_compute(h, rebuild, 0) with the host out of the loop.  When the last fully checked
+ * call (cv_deviations / cv_deviations_compute) ran on the SAME resident inputs and options without
+ * taking a fallback, every kernel of the path is enqueued again -- same work, bit-identical results --
+ * but the host waits neither for the flag words between the stages (their values are known from the
+ * checked call) nor for the end of the call: consecutive calls queue up on the device and a
+ * descheduled host thread no longer leaves the GPU idle.  Without such a verdict it IS the checked
+ * call.  cv_deviations_wait -- or any entry point that reads results, reports statistics or changes
+ * inputs / options -- waits for the queued calls and verifies their flag words. */
+int cv_deviations_compute_async(cv_handle* h, int rebuild_counts_layout);
+int cv_deviations_wait(cv_handle* h);
 int cv_deviations_download(cv_handle* h, double* out_dev, double* out_z, double* out_matches,
                            double* out_overlap, double* out_variability, int64_t* out_observed,
                            int64_t* out_sampled);
