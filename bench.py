@@ -376,16 +376,26 @@ def run_ours(args):
     # so a descheduled host thread -- these shared boxes stall the host for 10-100 ms at a time -- no
     # longer shows up as GPU idle time inside a step.  Several ranks: the variability reduction needs
     # each step's partials on the host, so the checked call and its synchronisation stay.
-    use_async = ws == 1 and args.async_steps != 0
+    use_async = args.async_steps == 1 if ws == 1 else args.async_steps == 2
+    gathered = mine = None
 
     def step():
         if use_async:
             eng.deviations_compute_async(rebuild_counts_layout=True)
+            if ws > 1:
+                # reduction 2 stays in every step, on the device: NCCL all-gather of the K x 4 partials
+                # behind the step's kernels (stream-ordered, no host wait); Chan merge after the loop
+                with torch.cuda.stream(ext):
+                    dist.all_gather_into_tensor(gathered, mine)
             return
         eng.deviations_compute(rebuild_counts_layout=True, keep_sums=False)
         if ws > 1:
             cvd.gather_variability(eng)                  # reduction 2 (K x 4 doubles)
 
+    if use_async and ws > 1:
+        eng.deviations_compute(rebuild_counts_layout=True, keep_sums=False)      # the checked call: verdicts, buffers
+        mine = torch.as_tensor(eng.variability_partials_device(), device=dev)    # the engine's own buffer (grow-only)
+        gathered = torch.empty(ws * mine.numel(), dtype=mine.dtype, device=dev)
     for _ in range(args.warmup):
         step()
     if use_async:
@@ -419,6 +429,9 @@ def run_ours(args):
     if use_async:
         eng.deviations_wait()                            # flag words of the queued calls verified here
         torch.cuda.synchronize(dev)
+        if ws > 1:
+            sd_all = _lib.merge_variability(gathered.view(ws, -1, 4).cpu().numpy(), na_rm=True)
+            assert sd_all.shape[0] == K and np.isfinite(sd_all).any()
         step_ms = [a.elapsed_time(b) for a, b in pending]
         st = eng.stats()                                 # timed spans of the last queued step
         contract_ms = [st["ms_contract"]]
@@ -611,7 +624,7 @@ def main():
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
     ap.add_argument("--pair", type=int, default=-1, help="dense GEMM kernel: 1 CTA pair (cta_group::2), 0 single CTA, -1 library default (by context)")
     ap.add_argument("--async-steps", type=int, default=1,
-                    help="one rank: 1 (default) enqueues the timed steps back to back (cv_deviations_compute_async), 0 one checked call per step")
+                    help="1 (default): one rank enqueues the timed steps back to back (cv_deviations_compute_async), several ranks run one checked call + host-side variability merge per step; 2: several ranks queue their steps too (all-gather on the device); 0: one checked call per step")
     ap.add_argument("--clock-sampler", default="thread", choices=["thread", "inline", "off"],
                     help="SM clock / throttle reasons through NVML: polled by a thread every 100 ms, or by the main thread between steps")
     ap.add_argument("--tail-chunk", type=int, default=1, help="e2e call: 1 (default) ends with a short fourth cell chunk, 0: three chunks")
