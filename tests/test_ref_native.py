@@ -155,3 +155,57 @@ def test_bg_sample_helper_pinned_mini_counts(golden_mini):
     nz = x > 0
     assert o[~nz].sum() == 0
     assert ((o[nz] - x[nz]) ** 2 / x[nz]).sum() < chi2.ppf(1 - 1e-4, int(nz.sum()) - 1)
+
+
+# ---- randomised agreement (hypothesis): restatement vs the reference's compiled code ----------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 400), st.integers(0, 3000), st.integers(0, 2 ** 31 - 1), st.floats(0.2, 6.0))
+def test_prob_sample_replace_random_cases(n, size, seed, power):
+    rng = np.random.default_rng(seed)
+    prob = rng.random(n) ** power
+    prob[rng.random(n) < 0.2] = 0.0                  # zero-probability entries never drawn
+    if prob.sum() == 0:
+        prob[rng.integers(n)] = 1.0
+    prob = prob / prob.sum()
+    rn.set_seed(seed)
+    ref = rn.prob_sample_replace(size, prob)
+    rn.set_seed(seed)
+    got = orc.prob_sample_replace(size, prob, rn.unif_rand)
+    assert np.array_equal(got, ref)
+    if size:
+        assert ref.min() >= 1 and ref.max() <= n and np.all(prob[ref - 1] > 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 12), st.integers(1, 90), st.integers(0, 2 ** 31 - 1), st.booleans())
+def test_row_sds_random_cases(k, n, seed, na_rm):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(k, n)) * rng.lognormal(0, 2, size=(k, 1)) + rng.normal(0, 50, size=(k, 1))
+    mask = rng.random((k, n)) < 0.1
+    x[mask] = rng.choice([np.nan, np.inf, -np.inf], size=int(mask.sum()))
+    ref, got = rn.row_sds(x, na_rm), orc.row_sds(x, na_rm)
+    # a row holding +-Inf without na_rm has no finite SD anywhere; whether it comes out as NaN or Inf
+    # depends on where the Inf sits in Armadillo's running-variance fallback (a lone Inf at the end of a
+    # row gives Inf, anywhere else NaN), so only finiteness is compared there
+    assert np.array_equal(np.isfinite(ref), np.isfinite(got))
+    if na_rm:
+        assert np.array_equal(np.isnan(ref), np.isnan(got))
+    m = np.isfinite(ref)
+    assert np.allclose(got[m], ref[m], rtol=1e-11, atol=0)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(2, 25), st.integers(1, 120), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
+def test_bg_sample_helper_random_cases(nb, P, B, seed):
+    rng = np.random.default_rng(seed)
+    bm0 = rng.integers(0, nb, P)
+    bin_p = rng.random((nb, nb)) ** 2
+    dens = np.bincount(bm0, minlength=nb).astype(float)
+    rn.set_seed(seed)
+    ref = rn.bg_sample_helper(bm0, bin_p, dens, B)
+    rn.set_seed(seed)
+    got = orc.bg_sample_helper(bm0, bin_p, dens, B, rn.unif_rand)
+    assert np.array_equal(got, ref)
