@@ -121,3 +121,26 @@ def test_host_narrow():
     assert ok and out[123] == 0
     ok, _ = _lib.host_narrow(np.array([7, 300, 2], np.int32), 1)
     assert not ok
+
+
+def test_device_generator_of_synthetic_counts_on_cpu():
+    """synthetic.make_counts_device (the atlas shard's generator, torch) on the CPU device: a valid CSC
+    matrix of the requested density with the same value distribution as the numpy generator."""
+    from chromvar_b200 import synthetic
+    d = synthetic.make_config("small", device="cpu")
+    C = d["counts"]
+    P, N = C.shape
+    assert (P, N) == (20_000, 2_000) and C.indptr[0] == 0 and C.indptr[-1] == C.nnz
+    assert np.all(np.diff(C.indptr) >= 0) and C.indices.min() >= 0 and C.indices.max() < P
+    for c in range(0, N, 101):                                   # rows strictly increasing inside a column
+        r = C.indices[C.indptr[c]:C.indptr[c + 1]]
+        assert np.all(np.diff(r) > 0)
+    assert np.all(C.data >= 1) and np.all(C.data == np.round(C.data)) and C.data.max() <= 127
+    assert np.all(np.asarray(C.sum(axis=1)).ravel() > 0)          # every peak has a fragment (R/compute_deviations.R:362)
+    dens = C.nnz / (P * N)
+    assert 0.02 < dens < 0.04
+    ref = synthetic.make_config("small")["counts"]
+    h1 = np.bincount(C.data.astype(int), minlength=6)[:6] / C.nnz
+    h0 = np.bincount(ref.data.astype(int), minlength=6)[:6] / ref.nnz
+    assert np.max(np.abs(h1 - h0)) < 0.03
+    assert d["cfg"]["generator"].startswith("torch")
