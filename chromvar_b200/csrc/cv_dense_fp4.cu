@@ -640,14 +640,16 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   }
   {
     // a cell is latency-bound (zero the row, a few dependent loads per thread, write the row), so up
-    // to three CTAs share an SM when a row's peak columns plus 8 KB of overflow columns fit a third of
+    // to three CTAs share an SM when a row's peak columns plus their overflow columns fit a third of
     // its shared memory (config 2: 50 KB of peak columns -> 3 CTAs of 74.75 KB; ncu capture X: one CTA
     // per SM kept 25 % of the warp slots busy); longer rows are built in pieces by one CTA per SM
     const int budget = h->max_smem_optin - 2048;
     const int64_t sm_total = (int64_t)h->max_smem_optin + 1024;            // per SM: the opt-in maximum plus one CTA's reserve
     int nc = 1;
+    // (room for overflow columns worth a quarter of the peak columns: dense k-mer annotations need
+    // that much, and a row that does not fit its piece costs a second pass over the cell's column)
     for (int c = 3; c >= 2; --c)
-      if (sm_total / c - 1280 >= Pb + 8192) { nc = c; break; }
+      if (sm_total / c - 1280 >= Pb + Pb / 4 + 8192) { nc = c; break; }
     const int piece = nc == 1 ? (int)std::min<int64_t>(pl.rowb, (budget / 128) * 128)
                               : (int)std::min<int64_t>(pl.rowb, ((sm_total / nc - 1280) / 128) * 128);
     CV_CUDA(h, cudaMemsetAsync(h->work_ctr.as<uint32_t>() + 1, 0, 4, h->stream));
