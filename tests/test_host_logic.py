@@ -1,5 +1,7 @@
 """Host-side logic of the R-API mirror that needs no GPU: input marshalling, validation order
 and messages (R/compute_deviations.R:362-379, R/utils.R:3-27,289-300), BH adjustment."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -144,3 +146,27 @@ def test_device_generator_of_synthetic_counts_on_cpu():
     h0 = np.bincount(ref.data.astype(int), minlength=6)[:6] / ref.nnz
     assert np.max(np.abs(h1 - h0)) < 0.03
     assert d["cfg"]["generator"].startswith("torch")
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` (the CPU restatement timed on the host's cores): one JSON line with
+    the contract's keys; other ranks of a torchrun launch exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--quick",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "annotation_x_cell_zscores_per_sec_50bg" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["higher_is_better"] is True and d["config"]["workload"] == "small"
+    env.update(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--quick",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
