@@ -963,7 +963,9 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   }
   h->have_results = true;
   // a clean dense run on resident inputs (no fallback taken, nothing flagged): its verdict can be replayed
-  h->replay_valid = verdict_clean && use_dense && !hf[CV_DFLAGS + 5] && !(hf[CV_DFLAGS] & (FLAG_ZEROPEAK | FLAG_BADIDX));
+  // (not under an e2m1 veto either: the veto ends with this call, a replay would plan e2m1 operands again)
+  h->replay_valid = verdict_clean && use_dense && !h->f4_veto && !hf[CV_DFLAGS + 5] &&
+                    !(hf[CV_DFLAGS] & (FLAG_ZEROPEAK | FLAG_BADIDX));
   if (h->replay_valid) memcpy(h->replay_hf, verdict_hf, 64);
   return CV_OK;
 }
