@@ -108,3 +108,28 @@ def test_async_with_a_fallback_stays_on_the_checked_call(engine):
         assert not np.array_equal(a["z"], base["z"], equal_nan=True)
     finally:
         engine.set_option("path", 0)
+
+
+def test_async_after_an_e2m1_veto_stays_on_the_checked_call(engine):
+    """Every nonzero is 11 = 6 + 4 + 1: the overflow reserve of the e2m1 operands is exceeded, the
+    checked call redoes itself on u8 operands under a veto that ends with the call.  Such a call leaves
+    no verdict to replay, so the async entry point keeps going through the checked call."""
+    C, P, N, bg, e, ptr, idx = _problem()
+    C = sp.csc_matrix((np.full(C.nnz, 11.0), C.indices, C.indptr), shape=C.shape)
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    engine.set_option("path", 2)
+    engine.set_option("dense_fp4", 1)
+    try:
+        engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+        engine.deviations_upload(ptr, idx, bg, e, index_base=1)
+        engine.deviations_compute(True)
+        base = engine.deviations_download()
+        assert engine.stats()["operand_bits"] == 8
+        for _ in range(3):
+            engine.deviations_compute_async(True)
+        engine.deviations_wait()
+        assert engine.stats()["operand_bits"] == 8
+        _same(engine.deviations_download(), base)
+    finally:
+        engine.set_option("path", 0)
+        engine.set_option("dense_fp4", -1)
