@@ -197,9 +197,11 @@ def test_row_sds_random_cases(k, n, seed, na_rm):
     assert np.allclose(got[m], ref[m], rtol=1e-11, atol=0)
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=60, deadline=None)
 @given(st.integers(2, 25), st.integers(1, 120), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
 def test_bg_sample_helper_random_cases(nb, P, B, seed):
+    """Probability vectors full of ties (every peak of a bin has the same value): draw-for-draw
+    agreement needs the normalising sum in Armadillo's order (found by this test: nb=2, P=72, seed=138)."""
     rng = np.random.default_rng(seed)
     bm0 = rng.integers(0, nb, P)
     bin_p = rng.random((nb, nb)) ** 2
