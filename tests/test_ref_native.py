@@ -5,6 +5,8 @@ R's unif_rand() is R's Mersenne-Twister, restated in oracle/refbuild/ref_capi.cp
 to the first runif() values after set.seed(42 / 1 / 123) (the values every R session prints).
 With the SAME uniform stream the restatement and the compiled reference must agree draw for draw.
 """
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -161,7 +163,7 @@ def test_bg_sample_helper_pinned_mini_counts(golden_mini):
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=int(os.environ.get("CV_HYPOTHESIS_EXAMPLES", "60")), deadline=None, derandomize="CV_HYPOTHESIS_EXAMPLES" not in os.environ)
 @given(st.integers(1, 400), st.integers(0, 3000), st.integers(0, 2 ** 31 - 1), st.floats(0.2, 6.0))
 def test_prob_sample_replace_random_cases(n, size, seed, power):
     rng = np.random.default_rng(seed)
@@ -179,7 +181,7 @@ def test_prob_sample_replace_random_cases(n, size, seed, power):
         assert ref.min() >= 1 and ref.max() <= n and np.all(prob[ref - 1] > 0)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=int(os.environ.get("CV_HYPOTHESIS_EXAMPLES", "60")), deadline=None, derandomize="CV_HYPOTHESIS_EXAMPLES" not in os.environ)
 @given(st.integers(1, 12), st.integers(1, 90), st.integers(0, 2 ** 31 - 1), st.booleans())
 def test_row_sds_random_cases(k, n, seed, na_rm):
     rng = np.random.default_rng(seed)
@@ -197,7 +199,7 @@ def test_row_sds_random_cases(k, n, seed, na_rm):
     assert np.allclose(got[m], ref[m], rtol=1e-11, atol=0)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=int(os.environ.get("CV_HYPOTHESIS_EXAMPLES", "60")), deadline=None, derandomize="CV_HYPOTHESIS_EXAMPLES" not in os.environ)
 @given(st.integers(2, 25), st.integers(1, 120), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
 def test_bg_sample_helper_random_cases(nb, P, B, seed):
     """Probability vectors full of ties (every peak of a bin has the same value): draw-for-draw
