@@ -30,6 +30,11 @@ EXPORTS = [
     "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
     "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms", "cv_host_narrow",
+    "cv_variability_merge_device",
+    "cv_create_multi", "cv_destroy_multi", "cv_multi_last_error", "cv_multi_n_devices", "cv_multi_peer_access",
+    "cv_multi_handle", "cv_multi_set_seed", "cv_multi_set_option", "cv_multi_stats", "cv_multi_set_counts",
+    "cv_multi_shards", "cv_multi_fragments", "cv_multi_expectations", "cv_multi_background_peaks",
+    "cv_multi_deviations", "cv_multi_deviations_csc",
 ]
 
 
@@ -48,6 +53,12 @@ class StageStats(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class CscBlock(C.Structure):
+    """cv_csc_block: one column block of the counts (a dgCMatrix's @p / @i / @x)."""
+    _fields_ = [("n_cols", C.c_int64), ("colptr", C.c_void_p), ("colptr_type", C.c_int),
+                ("rowidx", C.c_void_p), ("x", C.c_void_p), ("x_type", C.c_int)]
 
 
 class ChromVARError(RuntimeError):
@@ -105,6 +116,24 @@ def load(build_if_missing=True):
         "cv_euc_dist": (i32, [vp, i64, i64, vp, vp]),
         "cv_stats": (i32, [vp, C.POINTER(StageStats)]),
         "cv_host_narrow": (i32, [vp, i32, i64, vp, i32]),
+        "cv_variability_merge_device": (i32, [vp, vp, i32]),
+        "cv_create_multi": (i32, [vp, i32, u64, C.POINTER(vp)]),
+        "cv_destroy_multi": (None, [vp]),
+        "cv_multi_last_error": (C.c_char_p, [vp]),
+        "cv_multi_n_devices": (i32, [vp]),
+        "cv_multi_peer_access": (i32, [vp]),
+        "cv_multi_handle": (vp, [vp, i32]),
+        "cv_multi_set_seed": (i32, [vp, u64]),
+        "cv_multi_set_option": (i32, [vp, C.c_char_p, i64]),
+        "cv_multi_stats": (i32, [vp, i32, C.POINTER(StageStats)]),
+        "cv_multi_set_counts": (i32, [vp, i64, C.POINTER(CscBlock), i32]),
+        "cv_multi_shards": (i32, [vp, vp]),
+        "cv_multi_fragments": (i32, [vp, vp, vp, vp]),
+        "cv_multi_expectations": (i32, [vp, vp]),
+        "cv_multi_background_peaks": (i32, [vp, vp, i32, dbl, i32, vp]),
+        "cv_multi_deviations": (i32, [vp, i64, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "cv_multi_deviations_csc": (i32, [vp, i64, C.POINTER(CscBlock), i32, i64, vp, vp, i32, vp, i32, vp,
+                                        vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError if the export is missing: loud on purpose
@@ -371,6 +400,11 @@ class Handle:
         self.P, self.N, self.K, self.B = int(P), int(N), K, B
         return out
 
+    def variability_merge_device(self, d_parts_ptr, n_parts):
+        """cv_variability_merge_device: merge an all-gathered device buffer of n_parts K x 4 tables into
+        this handle's variability vector, on the handle's stream (no host synchronisation)."""
+        self._check(self.lib.cv_variability_merge_device(self._h, C.c_void_p(int(d_parts_ptr)), int(n_parts)))
+
     def variability_partials_device(self):
         p, n = C.c_void_p(), C.c_int64()
         self._check(self.lib.cv_variability_partials_device(self._h, C.byref(p), C.byref(n)))
@@ -426,6 +460,155 @@ class Handle:
 
     def stream(self):
         return self.lib.cv_stream(self._h)
+
+
+class MultiHandle:
+    """cv_multi: one process driving several GPUs (the call the R shim binds).  Counts are given as
+    a list of column blocks -- scipy CSC matrices with the same number of rows, e.g. the pieces of an
+    atlas whose nonzeros exceed one dgCMatrix -- or a single matrix."""
+
+    def __init__(self, devices, seed=0):
+        self.lib = load()
+        devices = [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        m = C.c_void_p()
+        rc = self.lib.cv_create_multi(arr, len(devices), int(seed) & (2 ** 64 - 1), C.byref(m))
+        if rc != CV_OK:
+            raise ChromVARError(rc, self.lib.cv_multi_last_error(None).decode())
+        self._m = m
+        self.devices = devices
+        self.P = self.N = self.K = self.B = 0
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self.lib.cv_destroy_multi(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != CV_OK:
+            raise ChromVARError(rc, self.lib.cv_multi_last_error(self._m).decode())
+
+    @staticmethod
+    def _blocks(mats):
+        """(ctypes array of cv_csc_block, keep-alive list, P, N)."""
+        if not isinstance(mats, (list, tuple)):
+            mats = [mats]
+        keep, P, N = [], None, 0
+        arr = (CscBlock * len(mats))()
+        for b, M in enumerate(mats):
+            if P is None:
+                P = int(M.shape[0])
+            elif int(M.shape[0]) != P:
+                raise ChromVARError(CV_ERR_INVALID, "all column blocks must have the same number of rows")
+            cp = np.ascontiguousarray(M.indptr)
+            if cp.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+                cp = cp.astype(np.int64)
+            ri = _carr(M.indices, np.int32)
+            x = np.ascontiguousarray(M.data)
+            if x.dtype not in _DTYPE_TAG or x.dtype == np.dtype(np.int64):
+                x = x.astype(np.float64)
+            keep += [cp, ri, x]
+            arr[b].n_cols = int(M.shape[1])
+            arr[b].colptr = cp.ctypes.data
+            arr[b].colptr_type = _DTYPE_TAG[cp.dtype]
+            arr[b].rowidx = ri.ctypes.data
+            arr[b].x = x.ctypes.data
+            arr[b].x_type = _DTYPE_TAG[x.dtype]
+            N += int(M.shape[1])
+        return arr, keep, P, N
+
+    def n_devices(self):
+        return self.lib.cv_multi_n_devices(self._m)
+
+    def peer_access(self):
+        return bool(self.lib.cv_multi_peer_access(self._m))
+
+    def set_seed(self, seed):
+        self._check(self.lib.cv_multi_set_seed(self._m, int(seed) & (2 ** 64 - 1)))
+
+    def set_option(self, key, value):
+        self._check(self.lib.cv_multi_set_option(self._m, key.encode(), int(value)))
+
+    def stats(self, i=0):
+        s = StageStats()
+        self._check(self.lib.cv_multi_stats(self._m, int(i), C.byref(s)))
+        return s.as_dict()
+
+    def set_counts(self, mats):
+        arr, keep, P, N = self._blocks(mats)
+        self._check(self.lib.cv_multi_set_counts(self._m, P, arr, len(arr)))
+        self.P, self.N = P, N
+
+    def shards(self):
+        b = np.zeros(len(self.devices) + 1, np.int64)
+        self._check(self.lib.cv_multi_shards(self._m, _ptr(b)))
+        return b
+
+    def fragments(self):
+        fpp, fps, tot = np.empty(self.P), np.empty(self.N), np.empty(1)
+        self._check(self.lib.cv_multi_fragments(self._m, _ptr(fpp), _ptr(fps), _ptr(tot)))
+        return fpp, fps, float(tot[0])
+
+    def expectations(self):
+        e = np.empty(self.P)
+        self._check(self.lib.cv_multi_expectations(self._m, _ptr(e)))
+        return e
+
+    def background_peaks(self, bias, niterations=50, w=0.1, bs=50):
+        bias = _carr(bias, np.float64)
+        if bias.shape[0] != self.P:
+            raise ChromVARError(CV_ERR_INVALID, "length(bias) must equal nrow(counts)")
+        bg = np.empty((self.P, niterations), np.int32, order="F")
+        self._check(self.lib.cv_multi_background_peaks(self._m, _ptr(bias), niterations, w, bs, _ptr(bg)))
+        return bg
+
+    def _outputs(self, K, N, out):
+        if out is None:
+            out = dict(dev=np.empty((K, N), np.float64, order="F"), z=np.empty((K, N), np.float64, order="F"),
+                       matches=np.empty(K, np.float64), overlap=np.empty(K, np.float64),
+                       variability=np.empty(K, np.float64))
+        return out
+
+    def deviations(self, annoptr, annoidx, bg, expectation, index_base=1, out=None):
+        annoptr, annoidx, bg, expectation = Handle._prep_dev_inputs(annoptr, annoidx, bg, expectation)
+        K, B = annoptr.shape[0] - 1, bg.shape[1]
+        if bg.shape[0] != self.P or expectation.shape[0] != self.P:
+            raise ChromVARError(CV_ERR_INVALID, "nrow(background_peaks) / length(expectation) must equal nrow(counts)")
+        out = self._outputs(K, self.N, out)
+        self._check(self.lib.cv_multi_deviations(self._m, K, _ptr(annoptr), _ptr(annoidx), index_base, _ptr(bg), B,
+                                                 _ptr(expectation), _ptr(out["dev"]), _ptr(out["z"]),
+                                                 _ptr(out["matches"]), _ptr(out["overlap"]), _ptr(out["variability"])))
+        self.K, self.B = K, B
+        return out
+
+    def deviations_csc(self, mats, annoptr, annoidx, bg, expectation=None, index_base=1, out=None, blocks=None):
+        """cv_multi_deviations_csc: compute_deviations_core as ONE call on host data, all devices.
+        blocks: the tuple _blocks(mats) returned earlier (a caller timing the call prepares it once)."""
+        arr, keep, P, N = blocks if blocks is not None else self._blocks(mats)
+        annoptr = _carr(annoptr, np.int64)
+        annoidx = _carr(annoidx, np.int32)
+        bg = np.asarray(bg)
+        if bg.dtype != np.dtype(np.int32) or not bg.flags.f_contiguous:
+            bg = np.asfortranarray(bg.astype(np.int32, copy=False))
+        if expectation is not None:
+            expectation = _carr(expectation, np.float64)
+            if expectation.shape[0] != P:
+                raise ChromVARError(CV_ERR_INVALID, "length(expectation) must equal nrow(counts)")
+        if bg.shape[0] != P:
+            raise ChromVARError(CV_ERR_INVALID, "nrow(background_peaks) must equal nrow(counts)")
+        K, B = annoptr.shape[0] - 1, bg.shape[1]
+        out = self._outputs(K, N, out)
+        self._check(self.lib.cv_multi_deviations_csc(
+            self._m, P, arr, len(arr), K, _ptr(annoptr), _ptr(annoidx), index_base, _ptr(bg), B, _ptr(expectation),
+            _ptr(out["dev"]), _ptr(out["z"]), _ptr(out["matches"]), _ptr(out["overlap"]), _ptr(out["variability"])))
+        self.P, self.N, self.K, self.B = P, N, K, B
+        return out
 
 
 def merge_variability(parts, na_rm=True):

@@ -755,69 +755,94 @@ static int counts_sums(cv_handle* h, int x_type) {
   return cv_counts_verdict(h, flags);
 }
 
-extern "C" int cv_set_counts_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr,
-                                 int colptr_type, const int32_t* rowidx, const void* x,
-                                 int x_type) {
-  if (!h) return CV_ERR_INVALID;
-  cudaSetDevice(h->device);
-  CV_TRY(cv_settle(h));
-  h->replay_valid = false;
-  h->have_counts = false;
+// One shard's counts as the host holds them: colptr rebased to the shard (int64), nonzeros in one or
+// several segments (a shard may span several column blocks of the caller, cv_multi.cu).
+int cv_csc_view_init(cv_handle* h, CscView* v, int64_t P, int64_t N, const void* colptr, int colptr_type,
+                     const int32_t* rowidx, const void* x, int x_type) {
   if (P <= 0 || N <= 0 || !colptr) CV_FAIL(h, CV_ERR_INVALID, "counts: empty matrix");
   if (P > 0x7fffffff || N > 0x7fffffff) CV_FAIL(h, CV_ERR_UNSUPPORTED, "P, N must be < 2^31");
   if (colptr_type != CV_I32 && colptr_type != CV_I64)
     CV_FAIL(h, CV_ERR_INVALID, "colptr_type must be CV_I32 or CV_I64");
-  size_t xb = type_bytes(x_type);
+  const size_t xb = type_bytes(x_type);
   if (!xb || x_type == CV_I64) CV_FAIL(h, CV_ERR_INVALID, "unsupported x_type %d", x_type);
-  int64_t nnz, first;
-  if (colptr_type == CV_I32) {
-    nnz = ((const int32_t*)colptr)[N];
-    first = ((const int32_t*)colptr)[0];
-  } else {
-    nnz = ((const int64_t*)colptr)[N];
-    first = ((const int64_t*)colptr)[0];
-  }
-  if (first != 0 || nnz < 0) CV_FAIL(h, CV_ERR_INVALID, "colptr must start at 0 and be monotone");
-  if (nnz >= (1ll << 32)) CV_FAIL(h, CV_ERR_UNSUPPORTED, "nnz >= 2^32 on one handle: shard the cells");
+  v->P = P; v->N = N; v->x_type = x_type; v->xb = xb;
+  v->cp.resize((size_t)N + 1);
+  if (colptr_type == CV_I32) for (int64_t i = 0; i <= N; ++i) v->cp[(size_t)i] = ((const int32_t*)colptr)[i];
+  else memcpy(v->cp.data(), colptr, (size_t)(N + 1) * 8);
+  const int64_t nnz = v->cp[(size_t)N];
+  if (v->cp[0] != 0 || nnz < 0) CV_FAIL(h, CV_ERR_INVALID, "colptr must start at 0 and be monotone");
   if (nnz > 0 && (!rowidx || !x)) CV_FAIL(h, CV_ERR_INVALID, "rowidx / x are NULL");
-  // host-side monotonicity check of colptr (N+1 elements, cheap)
-  if (colptr_type == CV_I32) {
-    const int32_t* cp = (const int32_t*)colptr;
-    for (int64_t i = 0; i < N; ++i)
-      if (cp[i + 1] < cp[i]) CV_FAIL(h, CV_ERR_INVALID, "colptr is not monotone at column %lld", (long long)i);
-  } else {
-    const int64_t* cp = (const int64_t*)colptr;
-    for (int64_t i = 0; i < N; ++i)
-      if (cp[i + 1] < cp[i]) CV_FAIL(h, CV_ERR_INVALID, "colptr is not monotone at column %lld", (long long)i);
+  v->segs.clear();
+  if (nnz > 0) v->segs.push_back(CscSeg{0, nnz, rowidx, (const char*)x});
+  return CV_OK;
+}
+
+int cv_csc_view_check(cv_handle* h, const CscView& v) {
+  const int64_t N = v.N;
+  if ((int64_t)v.cp.size() != N + 1 || v.cp[0] != 0) CV_FAIL(h, CV_ERR_INVALID, "colptr must start at 0 and be monotone");
+  for (int64_t i = 0; i < N; ++i)
+    if (v.cp[(size_t)i + 1] < v.cp[(size_t)i]) CV_FAIL(h, CV_ERR_INVALID, "colptr is not monotone at column %lld", (long long)i);
+  if (v.cp[(size_t)N] >= (1ll << 32)) CV_FAIL(h, CV_ERR_UNSUPPORTED, "nnz >= 2^32 on one handle: shard the cells");
+  int64_t at = 0;
+  for (const CscSeg& sg : v.segs) {
+    if (sg.e0 != at || sg.e1 <= sg.e0 || !sg.rowidx || !sg.x) CV_FAIL(h, CV_ERR_INVALID, "counts: segments do not tile the nonzeros");
+    at = sg.e1;
   }
+  if (at != v.cp[(size_t)N]) CV_FAIL(h, CV_ERR_INVALID, "counts: segments do not tile the nonzeros");
+  return CV_OK;
+}
+
+// H2D of nonzeros [e0, e1) of the view (row indices and / or values) into the device arrays at the same
+// element offsets; one copy per segment touched
+int cv_csc_view_copy(cv_handle* h, const CscView& v, int64_t e0, int64_t e1, int32_t* d_rowidx, char* d_x,
+                     cudaStream_t st) {
+  for (const CscSeg& sg : v.segs) {
+    const int64_t a = std::max(e0, sg.e0), b = std::min(e1, sg.e1);
+    if (b <= a) continue;
+    if (d_rowidx)
+      CV_CUDA(h, cudaMemcpyAsync(d_rowidx + a, sg.rowidx + (a - sg.e0), (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
+    if (d_x)
+      CV_CUDA(h, cudaMemcpyAsync(d_x + (size_t)a * v.xb, sg.x + (size_t)(a - sg.e0) * v.xb, (size_t)(b - a) * v.xb,
+                                 cudaMemcpyHostToDevice, st));
+  }
+  return CV_OK;
+}
+
+int cv_set_counts_view(cv_handle* h, const CscView& v) {
+  cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  h->replay_valid = false;
+  h->have_counts = false;
+  CV_TRY(cv_csc_view_check(h, v));
+  const int64_t P = v.P, N = v.N, nnz = v.cp[(size_t)N];
   h->P = P; h->N = N; h->nnz = nnz;
   double t0 = wall_ms();
   CV_TRY(cv_ensure(h, h->colptr, (size_t)(N + 1) * 8));
   CV_TRY(cv_ensure(h, h->rowidx, (size_t)nnz * 4));
-  CV_TRY(cv_ensure(h, h->xraw, (size_t)nnz * xb));
-  if (colptr_type == CV_I64) {
-    CV_CUDA(h, cudaMemcpyAsync(h->colptr.p, colptr, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-  } else {
-    CV_TRY(cv_ensure(h, h->tmp0, (size_t)(N + 1) * 4));
-    CV_CUDA(h, cudaMemcpyAsync(h->tmp0.p, colptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-    CV_LAUNCH(h, k_widen_i32, (unsigned)((N + 1 + 255) / 256), 256, 0, h->tmp0.as<int32_t>(),
-              h->colptr.as<int64_t>(), N + 1);
-  }
-  if (nnz > 0) {
-    CV_CUDA(h, cudaMemcpyAsync(h->rowidx.p, rowidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
-    CV_CUDA(h, cudaMemcpyAsync(h->xraw.p, x, (size_t)nnz * xb, cudaMemcpyHostToDevice, h->stream));
-  }
+  CV_TRY(cv_ensure(h, h->xraw, (size_t)nnz * v.xb));
+  CV_CUDA(h, cudaMemcpyAsync(h->colptr.p, v.cp.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  CV_TRY(cv_csc_view_copy(h, v, 0, nnz, h->rowidx.as<int32_t>(), h->xraw.as<char>(), h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   h->st.ms_h2d = wall_ms() - t0;
-  h->st.h2d_bytes = (int64_t)((N + 1) * type_bytes(colptr_type) + nnz * (4 + xb));
+  h->st.h2d_bytes = (int64_t)((N + 1) * 8 + nnz * (4 + (int64_t)v.xb));
   CV_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-  CV_TRY(counts_sums(h, x_type));
+  CV_TRY(counts_sums(h, v.x_type));
   CV_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
   CV_CUDA(h, cudaEventSynchronize(h->ev[1]));
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
   h->st.ms_counts_layout = ms;
   return CV_OK;
+}
+
+extern "C" int cv_set_counts_csc(cv_handle* h, int64_t P, int64_t N, const void* colptr,
+                                 int colptr_type, const int32_t* rowidx, const void* x,
+                                 int x_type) {
+  if (!h) return CV_ERR_INVALID;
+  h->have_counts = false;
+  CscView v;
+  CV_TRY(cv_csc_view_init(h, &v, P, N, colptr, colptr_type, rowidx, x, x_type));
+  return cv_set_counts_view(h, v);
 }
 
 template <typename XT>

@@ -399,13 +399,22 @@ __global__ void k_winv_fixed(const double* __restrict__ etab, int K, int I, uint
   int ex = 0;
   if (!bad) frexp(wmax, &ex);                       // wmax = m * 2^ex, m in [0.5, 1)
   const int F = 32 - ex;
+  // The rounding of the table entries, delta_j = W_j - 2^F / E_j, shifts the mean over iterations by
+  // sum_j s_j delta_j / (B 2^F fps).  Where that matters -- sums s_j nearly equal, i.e. a small spread of
+  // the background deviations, which then divides it -- it is (mean + 1) * rho with
+  // rho = sum_j delta_j / sum_j W_j, a constant of the annotation: folded into the mean's scale below
+  // (the remainder is of relative size spread x 2^-32 / sqrt(B)).
+  double dsum = 0.0, wsum = 0.0;
   for (int j = 0; j < I; ++j) {
-    double v = bad ? 0.0 : rint(ldexp(1.0 / e[j], F));
+    const double exact = bad ? 0.0 : ldexp(1.0 / e[j], F);
+    double v = rint(exact);
     if (v > 4294967295.0) v = 4294967295.0;
     W[(int64_t)k * I + j] = (uint32_t)v;
+    if (j > 0) { dsum += v - exact; wsum += v; }
   }
+  const double rho = wsum > 0.0 ? dsum / wsum : 0.0;
   // per-annotation constants of the fixed-point epilogue: 2^-F / B (mean), 2^F (1 / sd), 1 / E_0, E_0
-  wscale[4 * k + 0] = bad ? 0.0 : ldexp(1.0, -F) / (double)(I - 1);
+  wscale[4 * k + 0] = bad ? 0.0 : ldexp(1.0, -F) / (double)(I - 1) * (1.0 - rho);
   wscale[4 * k + 1] = bad ? 0.0 : ldexp(1.0, F);
   wscale[4 * k + 2] = 1.0 / e[0];
   wscale[4 * k + 3] = e[0];

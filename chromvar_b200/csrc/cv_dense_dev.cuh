@@ -388,10 +388,12 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
   const double rf = 1.0 / fpsv;
   int a = 0, j = 0;
   DnCell cell = {0.0, 0.0, 0.0, 0.0};
-  unsigned long long f_piv = 0ull, f_sumi = 0ull;
-  float f_sumsq = 0.f;
+  // fixed-point form: per-annotation state between the two sweeps (indexed by the running annotation:
+  // thread-local memory, written / read once per annotation)
+  unsigned long long f_sumi = 0ull;
+  unsigned long long f_tot[MODE == DN_EPI_FUSED32 ? DN_MAX_G : 1];
+  int f_obs[MODE == DN_EPI_FUSED32 ? DN_MAX_G : 1];
   const double inv_b = 1.0 / (double)prm.B, inv_bm1 = 1.0 / (double)(prm.B - 1);
-  int f_obs = 0;
   const int ncols = nk * I;
   for (int col0 = 0; col0 < ncols; col0 += 32) {
     uint32_t r[32];
@@ -418,21 +420,9 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
             else if (prm.samp) prm.samp[((int64_t)k * prm.B + (j - 1)) * prm.N + c] = (long long)(int)r[u];
           }
           if (MODE == DN_EPI_FUSED32) {
-            // y_j = s_j * W_j (exact, < 2^56): their sum gives the mean over iterations exactly; the
-            // differences to the first iteration, exact integers, feed an fp32 sum of squares.  The
-            // cell's 1 / fps, the "- 1" and every cancellation happen once per annotation in fp64.
-            if (j == 0) {
-              f_obs = (int)r[u];
-              f_sumi = 0ull;
-              f_sumsq = 0.f;
-            } else {
-              const unsigned long long prod =
-                  (unsigned long long)r[u] * (unsigned long long)reinterpret_cast<const uint32_t*>(s_winv)[a * I + j];
-              if (j == 1) f_piv = prod;
-              f_sumi += prod;
-              const float df = (float)(long long)(prod - f_piv);
-              f_sumsq = fmaf(df, df, f_sumsq);
-            }
+            // first sweep: y_j = s_j * W_j (exact, < 2^56); their sum gives the mean over iterations exactly
+            if (j == 0) f_obs[a] = (int)r[u];
+            else f_sumi += (unsigned long long)r[u] * (unsigned long long)reinterpret_cast<const uint32_t*>(s_winv)[a * I + j];
           } else {
             dn_cell_add(cell, j, (double)(int)r[u], s_winv[a * I + j], rf);
           }
@@ -440,36 +430,136 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
             const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
             double devv, zv;
             if (MODE == DN_EPI_FUSED32) {
-              // FP64 issues ~25x slower while the tensor pipe runs, so this tail (once per annotation
-              // and cell) uses a dozen fp64 operations: reciprocals come from tables, the square
-              // root is an fp32 rsqrt + one Newton step (the variance is an fp32 sum anyway)
-              const double4 cst = *reinterpret_cast<const double4*>(prm.wscale + 4 * (int64_t)k);   // 2^-F / B, 2^F, 1 / E0, E0
-              const double expected = cst.w * fpsv;                                                 // :488
-              const double obs_dev = (double)f_obs * (rf * cst.z) - 1.0;                            // :489
-              const double mean = (double)f_sumi * (rf * cst.x) - 1.0;                              // :511
-              const double s1 = (double)(long long)(f_sumi - (unsigned long long)prm.B * f_piv);
-              float var = (float)(((double)f_sumsq - s1 * (s1 * inv_b)) * inv_bm1);                 // :512, scaled units
-              var = var > 0.f ? var : (var == var ? 0.f : var);
-              float rs = rsqrtf(var);
-              rs = rs * (1.5f - 0.5f * ((var * rs) * rs));                                          // inf / nan pass through
-              if (var == 0.f) rs = __int_as_float(0x7f800000);
-              devv = obs_dev - mean;                                                                // :514
-              zv = devv * ((fpsv * cst.y) * (double)rs);                                            // :515
-              if (empty || expected < 1.0) devv = zv = cv_na_real();
-            } else {
-              dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
+              f_tot[a] = f_sumi;                         // finished by the second sweep below
+              f_sumi = 0ull;
+              j = 0;
+              ++a;
+              continue;
             }
+            dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
             if (live) {
               prm.dev_rm[(int64_t)k * prm.N + c] = devv;
               prm.z_rm[(int64_t)k * prm.N + c] = zv;
             }
             // variability partial of (k, cell block): this warp's 32 cells, then the 4 epilogue warps
-            if (MODE == DN_EPI_FUSED32) dn_warp_variability_f32(zv, live, lane, s_wred + (a * 4 + q4) * 4);
-            else dn_warp_variability(zv, live, lane, s_wred + (a * 4 + q4) * 4);
+            dn_warp_variability(zv, live, lane, s_wred + (a * 4 + q4) * 4);
             j = 0;
             ++a;
           }
         }
+      }
+    }
+  }
+  if (MODE != DN_EPI_FUSED32) return;
+  // Second sweep of the fixed-point form (the accumulator is still in tensor memory): squared
+  // differences to a centre c within a few units of the integer mean sum_j y_j / B of this
+  // (annotation, cell), in fp32.  Every term is >= 0 and the residual s1 = sum_j (y_j - c), an exact
+  // integer of magnitude <= B, enters once -- nothing cancels whatever the background draws look like
+  // (a pivot on the first iteration loses digits when that iteration is an outlier: one fragment
+  // against 49 zeros amplified the fp32 rounding ~50x).  No fp64 inside the column loop: predicated-
+  // off fp64 instructions still issue, and fp64 issue is throttled while the tensor pipe runs.
+  const unsigned long long magic = ~0ull / (unsigned long long)prm.B;        // floor((2^64 - 1) / B)
+  a = 0;
+  j = 0;
+  unsigned long long ctr = __umul64hi(f_tot[0], magic);                      // floor(tot / B) or one less
+  float f_sumsq = 0.f;
+  unsigned redo = 0u, redo_mine = 0u;          // annotations for the fp64 sweep: any lane of the warp / this cell
+  for (int col0 = 0; col0 < ncols; col0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)col0, r);
+    tmem_ld_wait();
+    if (F32ACC) {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) r[u] = (uint32_t)__float2int_rn(__uint_as_float(r[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      if (col0 + u < ncols) {
+        if (j != 0) {
+          const unsigned long long prod =
+              (unsigned long long)r[u] * (unsigned long long)reinterpret_cast<const uint32_t*>(s_winv)[a * I + j];
+          const float df = (float)(long long)(prod - ctr);
+          f_sumsq = fmaf(df, df, f_sumsq);
+        }
+        if (++j == I) {
+          // FP64 issues ~25x slower while the tensor pipe runs, so this tail (once per annotation and
+          // cell) uses a dozen fp64 operations: reciprocals come from tables, the square root is an
+          // fp32 rsqrt + one Newton step (the variance is an fp32 sum anyway)
+          const int k = k0 + a;
+          const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
+          const unsigned long long tot = f_tot[a];
+          const double4 cst = *reinterpret_cast<const double4*>(prm.wscale + 4 * (int64_t)k);   // 2^-F / B, 2^F, 1 / E0, E0
+          const double expected = cst.w * fpsv;                                                 // :488
+          const double obs_dev = (double)f_obs[a] * (rf * cst.z) - 1.0;                         // :489
+          const double mean = (double)tot * (rf * cst.x) - 1.0;                                 // :511
+          const float s1 = (float)(long long)(tot - (unsigned long long)prm.B * ctr);           // 0 <= s1 < 2 B
+          float var = (f_sumsq - s1 * s1 * (float)inv_b) * (float)inv_bm1;                      // :512, scaled units
+          var = var > 0.f ? var : (var == var ? 0.f : var);
+          // The table entries W_j carry 32 bits, i.e. each y_j / c is off by up to ~2^-31: once the
+          // spread of the background deviations falls below ~5e-4 (only under-dispersed counts do that
+          // with sums < 2^24; Poisson spread there is >= 2.4e-4 ... 1) that shows in z.  Such
+          // (annotation, cell) pairs are redone in fp64 below.
+          const float fc = (float)ctr;
+          const bool thin = live && !empty && var < 2.5e-7f * fc * fc;
+          if (thin) redo_mine |= 1u << a;
+          if (__any_sync(0xffffffffu, thin)) redo |= 1u << a;
+          float rs = rsqrtf(var);
+          rs = rs * (1.5f - 0.5f * ((var * rs) * rs));                                          // inf / nan pass through
+          if (var == 0.f) rs = __int_as_float(0x7f800000);
+          double devv = obs_dev - mean;                                                         // :514
+          double zv = devv * ((fpsv * cst.y) * (double)rs);                                     // :515
+          if (empty || expected < 1.0) devv = zv = cv_na_real();
+          if (live) {
+            prm.dev_rm[(int64_t)k * prm.N + c] = devv;
+            prm.z_rm[(int64_t)k * prm.N + c] = zv;
+          }
+          dn_warp_variability_f32(zv, live, lane, s_wred + (a * 4 + q4) * 4);
+          j = 0;
+          ++a;
+          ctr = __umul64hi(f_tot[a < nk ? a : 0], magic);
+          f_sumsq = 0.f;
+        }
+      }
+    }
+  }
+  if (!redo) return;
+  // Third sweep, rare: the flagged (annotation, cell) pairs again, in the fp64 form of DN_EPI_FUSED
+  // (reciprocals of the expectation sums straight from the table in global memory).  The sweep is
+  // warp-wide (tensor-memory loads are), but only a flagged cell takes the fp64 value: what a cell
+  // gets never depends on which other cells share its warp, so sharding the cells differently
+  // leaves every result bit for bit the same.
+  a = 0;
+  j = 0;
+  for (int col0 = 0; col0 < ncols; col0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)col0, r);
+    tmem_ld_wait();
+    if (F32ACC) {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) r[u] = (uint32_t)__float2int_rn(__uint_as_float(r[u]));
+    }
+#pragma unroll 1
+    for (int u = 0; u < 32; ++u) {
+      if (col0 + u >= ncols) break;
+      const int k = k0 + a;
+      if ((redo >> a) & 1u) dn_cell_add(cell, j, (double)(int)r[u], 1.0 / prm.etab[(int64_t)k * I + j], rf);
+      if (++j == I) {
+        if ((redo >> a) & 1u) {
+          const bool empty = prm.annoptr[k + 1] == prm.annoptr[k];
+          double devv, zv;
+          dn_cell_finish(cell, prm.etab[(int64_t)k * I], fpsv, prm.B, empty, devv, zv);
+          if (live) {
+            if ((redo_mine >> a) & 1u) {
+              prm.dev_rm[(int64_t)k * prm.N + c] = devv;
+              prm.z_rm[(int64_t)k * prm.N + c] = zv;
+            } else {
+              zv = prm.z_rm[(int64_t)k * prm.N + c];           // this thread's own value of the second sweep
+            }
+          }
+          dn_warp_variability(zv, live, lane, s_wred + (a * 4 + q4) * 4);
+        }
+        j = 0;
+        ++a;
       }
     }
   }

@@ -474,9 +474,8 @@ static int launch_contract(cv_handle* h, const ContractParams& prm, size_t smem)
 struct DevIO {
   // counts arriving chunk by chunk (cv_deviations_csc): host CSC arrays, colptr as int64
   bool stream_counts = false;
+  const CscView* view = nullptr;
   const int64_t* h_colptr = nullptr;
-  const int32_t* h_rowidx = nullptr;
-  const char* h_x = nullptr;
   int x_type = 0;
   size_t xb = 0;
   bool narrow = false;               // values are being narrowed to bytes on host threads (h->narrower -> h->stage8)
@@ -496,8 +495,7 @@ static int enqueue_counts_upload(cv_handle* h, DevIO& io, int64_t c0, int64_t c1
   const int64_t e0 = io.h_colptr[c0], e1 = io.h_colptr[c1];
   int x_type = io.x_type;
   if (e1 > e0) {
-    CV_CUDA(h, cudaMemcpyAsync(h->rowidx.as<int32_t>() + e0, io.h_rowidx + e0, (size_t)(e1 - e0) * 4,
-                               cudaMemcpyHostToDevice, h->s_up));
+    CV_TRY(cv_csc_view_copy(h, *io.view, e0, e1, h->rowidx.as<int32_t>(), nullptr, h->s_up));
     // the row indices are on their way while the last slices of this chunk finish narrowing.
     // xraw is staging only (K1 of this chunk reads it on the same stream before the next chunk's
     // copy lands), so a byte chunk and a chunk in the caller's type may share it.
@@ -507,8 +505,7 @@ static int enqueue_counts_upload(cv_handle* h, DevIO& io, int64_t c0, int64_t c1
       x_type = CV_U8;
       io.x_bytes_sent += e1 - e0;
     } else {
-      CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0 * io.xb, io.h_x + (size_t)e0 * io.xb,
-                                 (size_t)(e1 - e0) * io.xb, cudaMemcpyHostToDevice, h->s_up));
+      CV_TRY(cv_csc_view_copy(h, *io.view, e0, e1, nullptr, h->xraw.as<char>(), h->s_up));
       io.x_bytes_sent += (e1 - e0) * (int64_t)io.xb;
     }
   }
@@ -1107,23 +1104,27 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
                                  double* out_z, double* out_matches, double* out_overlap,
                                  double* out_variability) {
   if (!h) return CV_ERR_INVALID;
+  CscView v;
+  CV_TRY(cv_csc_view_init(h, &v, P, N, colptr, colptr_type, rowidx, x, x_type));
+  return cv_deviations_view(h, v, K, annoptr, annoidx, index_base, bg, B, expectation, out_dev, out_z, out_matches,
+                            out_overlap, out_variability);
+}
+
+int cv_deviations_view(cv_handle* h, const CscView& v, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
+                       int index_base, const int32_t* bg, int B, const double* expectation, double* out_dev,
+                       double* out_z, double* out_matches, double* out_overlap, double* out_variability) {
   cudaSetDevice(h->device);
   CV_TRY(cv_settle(h));
   h->replay_valid = false;
+  const int64_t P = v.P, N = v.N;
+  const int x_type = v.x_type;
   // the streamed pipeline needs the expectation up front and the dense path; otherwise (or when
   // the dense path turns out not to be exact for these inputs) the call is the plain sequence
-  bool try_stream = expectation != nullptr && h->opt_path != 1 && P > 0 && N > 0 && P <= 0x7fffffff &&
-                    N <= 0x7fffffff && colptr && K >= 1 && annoptr && B >= 1 && B <= 255 && x_type != CV_I64 &&
-                    (colptr_type == CV_I32 || colptr_type == CV_I64);
+  bool try_stream = expectation != nullptr && h->opt_path != 1 && K >= 1 && annoptr && B >= 1 && B <= 255;
   int64_t nnz = 0;
-  std::vector<int64_t> cp64;
   if (try_stream) {
-    cp64.resize((size_t)N + 1);
-    if (colptr_type == CV_I32) for (int64_t i = 0; i <= N; ++i) cp64[(size_t)i] = ((const int32_t*)colptr)[i];
-    else memcpy(cp64.data(), colptr, (size_t)(N + 1) * 8);
-    nnz = cp64[(size_t)N];
-    bool ok = cp64[0] == 0 && nnz > 0 && nnz < (1ll << 32) && rowidx && x && annoptr[0] == 0 && annoptr[K] >= 0;
-    for (int64_t i = 0; ok && i < N; ++i) ok = cp64[(size_t)i + 1] >= cp64[(size_t)i];
+    nnz = v.cp[(size_t)N];
+    bool ok = cv_csc_view_check(h, v) == CV_OK && nnz > 0 && annoptr[0] == 0 && annoptr[K] >= 0;
     if (ok) {
       // same cost model as the resident call, on the host-known shape (largest count unknown yet:
       // one u8 plane assumed, verified once the counts have passed K1)
@@ -1139,9 +1140,8 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
     try_stream = ok;
   }
   if (try_stream) {
-    size_t xb = (x_type == CV_F64) ? 8 : (x_type == CV_F32 || x_type == CV_I32) ? 4 : (x_type == CV_U8) ? 1 : 0;
-    if (!xb) try_stream = false;
-    else {
+    const size_t xb = v.xb;
+    {
       double t0 = wall_ms();
       h->have_counts = false;
       h->P = P; h->N = N; h->nnz = nnz;
@@ -1150,16 +1150,15 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
       CV_TRY(cv_ensure(h, h->xraw, (size_t)nnz * xb));
       CV_TRY(cv_counts_begin(h));
       // small inputs first, on the compute stream (the operand build needs them immediately)
-      CV_CUDA(h, cudaMemcpyAsync(h->colptr.p, cp64.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+      CV_CUDA(h, cudaMemcpyAsync(h->colptr.p, v.cp.data(), (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, h->stream));
       int rc = upload_annotations(h, K, annoptr, annoidx, index_base, bg, B, expectation, h->stream);
       if (rc != CV_OK) return rc;
       int64_t h2d_b = h->st.h2d_bytes + (N + 1) * 8 + nnz * 4;
       h->have_anno = true;
       DevIO io;
       io.stream_counts = true;
-      io.h_colptr = cp64.data();
-      io.h_rowidx = rowidx;
-      io.h_x = (const char*)x;
+      io.view = &v;
+      io.h_colptr = v.cp.data();
       io.x_type = x_type;
       io.xb = xb;
       io.out_dev = out_dev;
@@ -1170,7 +1169,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
         cv_handle* h;
         ~NarrowGuard() { if (h->narrower) cv_narrower_finish(h->narrower); }
       } narrow_guard{h};
-      if (h->opt_host_narrow && xb > 1) {
+      if (h->opt_host_narrow && xb > 1 && v.segs.size() == 1) {
         if (!h->narrower) {
           int ndev = 1;
           cudaGetDeviceCount(&ndev);
@@ -1186,7 +1185,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
           else cudaGetLastError();              // no page-locked memory to spare: the values travel as they are
         }
         if (h->stage8_cap >= (size_t)nnz) {
-          cv_narrower_start(h->narrower, x, x_type, nnz, h->stage8);
+          cv_narrower_start(h->narrower, v.segs[0].x, x_type, nnz, h->stage8);
           io.narrow = true;
         }
       }
@@ -1207,7 +1206,7 @@ extern "C" int cv_deviations_csc(cv_handle* h, int64_t P, int64_t N, const void*
       h->have_counts = false;                   // not exact on the dense path: redo as the plain sequence
     }
   }
-  CV_TRY(cv_set_counts_csc(h, P, N, colptr, colptr_type, rowidx, x, x_type));
+  CV_TRY(cv_set_counts_view(h, v));
   std::vector<double> e_default;
   if (!expectation) {
     e_default.resize((size_t)P);
@@ -1226,6 +1225,32 @@ extern "C" int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t
   if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no results");
   *dptr = h->varfinal.p;
   if (n_elems) *n_elems = h->K * 4;
+  return CV_OK;
+}
+
+// parts[n_parts][K][4] (device memory: an all-gather of every shard's varfinal, rank order) -> variab[K]
+__global__ void __launch_bounds__(128)
+k_var_merge_gathered(const double* __restrict__ parts, int n_parts, int K, double* __restrict__ variab) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  Welford tot = {0.0, 0.0, 0.0};
+  for (int s = 0; s < n_parts; ++s) {
+    const double* q = parts + ((int64_t)s * K + k) * 4;
+    Welford b = {q[0], q[1], q[2]};
+    tot = welford_merge(tot, b);
+  }
+  variab[k] = tot.n > 1.0 ? sqrt(tot.m2 / (tot.n - 1.0)) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// Reduction 2 of the multi-process layout with the host out of the loop: the caller all-gathers the
+// K x 4 partial tables on the device (NCCL, stream-ordered behind the step's kernels) and this merges
+// them into the handle's variability vector on the same stream.
+extern "C" int cv_variability_merge_device(cv_handle* h, const void* d_parts, int n_parts) {
+  if (!h || !d_parts || n_parts < 1) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no results");
+  CV_LAUNCH(h, k_var_merge_gathered, (unsigned)((h->K + 127) / 128), 128, 0, reinterpret_cast<const double*>(d_parts),
+            n_parts, (int)h->K, h->variab.as<double>());
   return CV_OK;
 }
 

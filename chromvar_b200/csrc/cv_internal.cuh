@@ -187,6 +187,26 @@ struct cv_handle {
   cv_stage_stats st = {};
 };
 
+// One shard's counts as the host holds them (cv_counts.cu): colptr rebased to the shard, the
+// nonzeros [e0, e1) of segment i live at rowidx[e - e0], x[(e - e0) * xb]
+struct CscSeg { int64_t e0, e1; const int32_t* rowidx; const char* x; };
+struct CscView {
+  int64_t P = 0, N = 0;
+  std::vector<int64_t> cp;
+  std::vector<CscSeg> segs;
+  int x_type = 0;
+  size_t xb = 0;
+};
+int cv_csc_view_init(cv_handle* h, CscView* v, int64_t P, int64_t N, const void* colptr, int colptr_type,
+                     const int32_t* rowidx, const void* x, int x_type);
+int cv_csc_view_check(cv_handle* h, const CscView& v);
+int cv_csc_view_copy(cv_handle* h, const CscView& v, int64_t e0, int64_t e1, int32_t* d_rowidx, char* d_x, cudaStream_t st);
+int cv_set_counts_view(cv_handle* h, const CscView& v);
+// cv_deviations.cu: cv_deviations_csc on a view (expectation may be NULL)
+int cv_deviations_view(cv_handle* h, const CscView& v, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
+                       int index_base, const int32_t* bg, int B, const double* expectation, double* out_dev,
+                       double* out_z, double* out_matches, double* out_overlap, double* out_variability);
+
 int cv_ensure(cv_handle* h, DevBuf& b, size_t bytes);
 void cv_release(DevBuf& b);
 int cv_sync_check(cv_handle* h);

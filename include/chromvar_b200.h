@@ -18,9 +18,16 @@
  *     device cv_create fails.
  *   - NA: entries the reference sets to NA (R/compute_deviations.R:458-461,517-520) are written
  *     as R's NA_real_ bit pattern 0x7FF00000000007A2.
- *   - One handle = one GPU.  Cells (columns of the counts matrix) shard across handles /
- *     processes; the two cross-shard reductions are exposed as device buffers so the host can
- *     run NCCL on them (cv_peak_totals_device, cv_variability_partials_device).
+ *   - One cv_handle = one GPU.  Cells (columns of the counts matrix) shard across GPUs.  Two ways
+ *     to use several GPUs:
+ *       (a) ONE process, cv_multi (section "several GPUs behind one call" below): the library shards
+ *           the caller's column blocks, runs one host thread per device and performs the two
+ *           cross-shard reductions itself over NVLink peer memory.  This is what the R shim binds
+ *           (R is single-process; the reference's own fan-out is bplapply inside one process,
+ *           R/compute_deviations.R:387-391).
+ *       (b) one process per GPU (torchrun): the two reductions are exposed as device buffers so the
+ *           host runs NCCL on them (cv_peak_totals_device, cv_variability_partials_device,
+ *           cv_variability_merge_device).
  */
 #ifndef CHROMVAR_B200_H
 #define CHROMVAR_B200_H
@@ -191,6 +198,61 @@ int cv_variability_partials_device(cv_handle* h, void** dptr, int64_t* n_elems);
 /* merge n_parts partial tables (host memory, each K x 4) -> sd[K] (n-1 denominator) */
 int cv_merge_variability(const double* parts, int n_parts, int64_t K, int na_rm, double* out_sd);
 
+/* Multi-process computeVariability without the host: `d_parts` is a DEVICE buffer holding n_parts
+ * tables of K x 4 doubles back to back (an NCCL all-gather of cv_variability_partials_device, in rank
+ * order); the merged row SDs replace this handle's variability (cv_deviations_download's
+ * out_variability).  Enqueued on the handle's stream, no host synchronisation. */
+int cv_variability_merge_device(cv_handle* h, const void* d_parts, int n_parts);
+
+/* ---- several GPUs behind one call (replaces the bplapply fan-out, R/compute_deviations.R:387-391) ----
+ * One process, n_dev devices, one host thread per device inside the library.  The counts arrive as
+ * column blocks (a dgCMatrix holds < 2^31 nonzeros -- @p is int32 -- so an atlas is a list of
+ * blocks); the library cuts the concatenated columns into one contiguous cell shard per
+ * device, balanced by nonzeros, and each shard may span several blocks.  Per-peak totals are
+ * summed and the per-annotation variability partials merged across devices by the library's own
+ * kernels over peer memory (staged device-to-device copies where peer access is unavailable).
+ * Replicated inputs: annotations, background matrix, expectation.  Outputs are the caller's K x N
+ * (N = all cells) column-major matrices; every shard writes its own slab of columns.
+ * Per-shard limits are those of a cv_handle (nonzeros < 2^32 per device). */
+typedef struct cv_multi cv_multi;
+typedef struct cv_csc_block {
+  int64_t n_cols;          /* cells in this block */
+  const void* colptr;      /* n_cols + 1 offsets, starting at 0 (a dgCMatrix's @p) */
+  int colptr_type;         /* CV_I32 or CV_I64 */
+  const int32_t* rowidx;   /* @i, 0-based */
+  const void* x;           /* @x */
+  int x_type;              /* CV_F64 / CV_F32 / CV_I32 / CV_U8, the same for every block */
+} cv_csc_block;
+/* devices: n_dev CUDA ordinals (NULL = 0 .. n_dev-1); the same seed keys every device's sampler */
+int cv_create_multi(const int* devices, int n_dev, uint64_t seed, cv_multi** out);
+void cv_destroy_multi(cv_multi* m);
+const char* cv_multi_last_error(const cv_multi* m);   /* m == NULL: a failed cv_create_multi */
+int cv_multi_n_devices(const cv_multi* m);
+int cv_multi_peer_access(const cv_multi* m);          /* 1: reductions read peer memory directly */
+cv_handle* cv_multi_handle(cv_multi* m, int i);       /* device i's engine (statistics, options) */
+int cv_multi_set_seed(cv_multi* m, uint64_t seed);
+/* cv_set_option on every device; "multi_p2p" 0 stages the peers' buffers instead of direct peer loads */
+int cv_multi_set_option(cv_multi* m, const char* key, int64_t value);
+/* counts resident on the devices, per-peak totals reduced (getFragmentsPer*, computeExpectations,
+ * getBackgroundPeaks then see the whole matrix).  bounds: n_dev + 1 cell offsets of the shards. */
+int cv_multi_set_counts(cv_multi* m, int64_t P, const cv_csc_block* blocks, int n_blocks);
+int cv_multi_shards(const cv_multi* m, int64_t* bounds);
+int cv_multi_fragments(cv_multi* m, double* out_per_peak, double* out_per_sample, double* out_total);
+int cv_multi_expectations(cv_multi* m, double* out_e);        /* default variant (global) */
+int cv_multi_background_peaks(cv_multi* m, const double* bias, int niter, double w, int bs, int32_t* out_bg);
+/* compute_deviations_core on resident counts / as ONE call on host data (arguments as cv_deviations /
+ * cv_deviations_csc; expectation == NULL in the _csc form means computeExpectations' default).
+ * out_variability: row SD of z over ALL cells. */
+int cv_multi_deviations(cv_multi* m, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
+                        int index_base, const int32_t* bg, int B, const double* expectation,
+                        double* out_dev, double* out_z, double* out_matches, double* out_overlap,
+                        double* out_variability);
+int cv_multi_deviations_csc(cv_multi* m, int64_t P, const cv_csc_block* blocks, int n_blocks, int64_t K,
+                            const int64_t* annoptr, const int32_t* annoidx, int index_base,
+                            const int32_t* bg, int B, const double* expectation, double* out_dev,
+                            double* out_z, double* out_matches, double* out_overlap,
+                            double* out_variability);
+
 /* ---- the reference's five registered native routines (src/RcppExports.cpp:59-119) --------- */
 /* row_sds(x, na_rm)  src/utils.cpp:9-25.  x: K x N col-major. */
 int cv_row_sds(cv_handle* h, int64_t K, int64_t N, const double* x, int na_rm, double* out_sd);
@@ -232,6 +294,7 @@ typedef struct cv_stage_stats {
   int32_t overflow_columns;  /* e2m1 operands: extra columns holding the terms of values outside {0,1,2,3,4,6}, all chunks */
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
+int cv_multi_stats(cv_multi* m, int i, cv_stage_stats* out);   /* device i of a cv_multi */
 
 /* Host-only: the conversion cv_deviations_csc applies to wide value types before the upload
  * ("host_narrow" option; a dgCMatrix's x slot is double, R/helper_functions.R:50-88).  x_type CV_F64 /

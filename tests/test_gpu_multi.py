@@ -1,0 +1,181 @@
+"""Several GPUs behind one call (cv_multi, chromvar_b200/csrc/cv_multi.cu): the counts arrive as
+column blocks, the library shards the cells, runs one engine per shard on its own host thread and
+does the two cross-shard reductions (per-peak totals, variability partials) itself.
+
+The property under test is "sharded == unsharded": every output column depends only on its own
+counts column plus replicated inputs (R/compute_deviations.R:486-504), so the sharded result must
+equal the single-engine result BITWISE when both run the same epilogue arithmetic -- with shards
+whose local per-peak totals contain zeros (check on the reduced totals) and with the expectation
+taken from the reduced totals.
+
+One-GPU boxes run the shards as several engines on the same device (devices = [0, 0, 0]: separate
+handles, streams and host threads, reductions through the same kernels); with >= 2 devices visible
+the same tests also run across devices, over peer memory and over the staged-copy route.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import chromvar_oracle as orc  # noqa: E402
+from test_gpu_parity import assert_close  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _layouts():
+    out = [("one_device_three_shards", [0, 0, 0], 1)]
+    n = _n_gpus()
+    if n >= 2:
+        out.append(("two_devices_p2p", [0, 1], 1))
+        out.append(("two_devices_staged", [0, 1], 0))
+    if n >= 4:
+        out.append(("four_devices", [0, 1, 2, 3], 1))
+    return out
+
+
+def _problem(seed=5):
+    from chromvar_b200 import synthetic
+    d = synthetic.make_config("small")                 # 20 000 peaks x 2 000 cells, 64 annotations
+    C = d["counts"].tocsc()
+    rng = np.random.default_rng(seed)
+    P, N = C.shape
+    # peaks that have fragments in the LAST cells only: zero in every shard but the last
+    late = rng.choice(P, 40, replace=False)
+    C = C.tolil()
+    C[late, :] = 0
+    for p in late:
+        C[p, N - 1 - int(rng.integers(20))] = 2.0
+    C = C.tocsc()
+    C.eliminate_zeros()
+    C.sort_indices()
+    return d, C
+
+
+def _split(C, cuts):
+    cuts = [0] + list(cuts) + [C.shape[1]]
+    return [C[:, a:b].tocsc() for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+@pytest.fixture(scope="module")
+def problem():
+    return _problem()
+
+
+@pytest.mark.parametrize("layout", _layouts(), ids=lambda l: l[0])
+def test_sharded_equals_unsharded_bitwise(engine, problem, layout):
+    from chromvar_b200 import _lib
+    name, devices, p2p = layout
+    d, C = problem
+    P, N = C.shape
+    ptr, idx = d["annoptr"], d["annoidx"].astype(np.int32)
+    K = len(ptr) - 1
+    # unsharded: one engine
+    for key, v in (("path", 2), ("dense_epilogue", 1), ("dense_fp4", -1), ("cell_chunk", 0), ("check_zero_peaks", 1)):
+        engine.set_option(key, v)
+    try:
+        engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+        engine.set_seed(123)
+        e1 = engine.expectations()
+        fpp1, fps1, tot1 = engine.fragments()
+        bg1 = engine.background_peaks(d["bias"], 50, 0.1, 50)
+        one = engine.deviations(ptr, idx, bg1, e1, index_base=1)
+    finally:
+        for key, v in (("path", 0), ("dense_epilogue", 0)):
+            engine.set_option(key, v)
+    # sharded, from three ragged column blocks (one of them a single column)
+    blocks = _split(C, [700, 701])
+    m = _lib.MultiHandle(devices, seed=123)
+    try:
+        m.set_option("multi_p2p", p2p)
+        m.set_option("path", 2)
+        m.set_option("dense_epilogue", 1)
+        m.set_counts(blocks)
+        b = m.shards()
+        assert b[0] == 0 and b[-1] == N and np.all(np.diff(b) > 0)
+        fpp, fps, tot = m.fragments()
+        assert np.array_equal(fpp, fpp1) and np.array_equal(fps, fps1) and tot == tot1
+        e = m.expectations()
+        assert np.array_equal(e, e1)
+        bg = m.background_peaks(d["bias"], 50, 0.1, 50)
+        assert np.array_equal(bg, bg1)                   # same seed, same global totals: same matrix
+        res = m.deviations(ptr, idx, bg, e, index_base=1)
+        for key in ("dev", "z", "matches", "overlap"):
+            assert np.array_equal(res[key], one[key], equal_nan=True), key
+        # variability over ALL cells: merged partials vs the single engine's (merge order differs)
+        assert_close(res["variability"], one["variability"], "variability")
+        assert_close(res["variability"], orc.row_sds(res["z"], True), "variability vs row_sds")
+        # the one-call form on host data: streamed per device, reductions afterwards
+        res2 = m.deviations_csc(blocks, ptr, idx, bg, e, index_base=1)
+        for key in ("dev", "z", "matches", "overlap"):
+            assert np.array_equal(res2[key], one[key], equal_nan=True), key
+        assert_close(res2["variability"], one["variability"], "variability (one call)")
+        # ... and with the default expectation (NULL): global totals first, then the deviations
+        res3 = m.deviations_csc(blocks, ptr, idx, bg, None, index_base=1)
+        for key in ("dev", "z"):
+            assert np.array_equal(res3[key], one[key], equal_nan=True), key
+        st = [m.stats(i) for i in range(len(devices))]
+        assert all(s["path"] == 1 for s in st)
+    finally:
+        m.close()
+    # against the oracle on a few annotations (the single engine's result is covered elsewhere)
+    sets = [idx[ptr[k]:ptr[k + 1]] for k in (0, 7, 31)]
+    ref = orc.compute_deviations_core(C, sets, bg1, e1)
+    assert_close(res["z"][[0, 7, 31]], ref["z"], "z vs oracle")
+
+
+def test_zero_peak_is_checked_on_the_reduced_totals(problem):
+    from chromvar_b200 import _lib
+    d, C = problem
+    P, N = C.shape
+    ptr, idx = d["annoptr"], d["annoidx"].astype(np.int32)
+    C0 = C.tolil()
+    C0[17, :] = 0                                        # no fragment anywhere
+    C0 = C0.tocsc()
+    bg = np.asfortranarray(np.random.default_rng(1).integers(1, P + 1, size=(P, 50)).astype(np.int32))
+    e = np.full(P, 1.0 / P)
+    m = _lib.MultiHandle([0, 0], seed=1)
+    try:
+        with pytest.raises(_lib.ChromVARError, match="All peaks must have at least one fragment"):
+            m.deviations_csc(_split(C0, [900]), ptr, idx, bg, e)
+        m.set_counts(_split(C0, [900]))
+        with pytest.raises(_lib.ChromVARError, match="All peaks must have at least one fragment"):
+            m.deviations(ptr, idx, bg, e)
+        # bad input in one block is reported with the reference's message
+        bad = C.copy()
+        bad.data = bad.data.copy()
+        bad.data[-3] = -1.0
+        with pytest.raises(_lib.ChromVARError, match="counts"):
+            m.set_counts(_split(bad, [900]))
+    finally:
+        m.close()
+
+
+def test_more_devices_than_cells_and_single_block():
+    from chromvar_b200 import _lib
+    rng = np.random.default_rng(2)
+    P, N = 300, 2
+    C = sp.csc_matrix(rng.integers(1, 4, size=(P, N)).astype(np.float64))
+    sets = [rng.choice(np.arange(1, P + 1), 30, replace=False) for _ in range(3)]
+    ptr = np.concatenate([[0], np.cumsum([len(s) for s in sets])]).astype(np.int64)
+    idx = np.concatenate(sets).astype(np.int32)
+    bg = np.asfortranarray(rng.integers(1, P + 1, size=(P, 50)).astype(np.int32))
+    e = orc.compute_expectations_core(C)
+    m = _lib.MultiHandle([0, 0, 0], seed=1)
+    try:
+        res = m.deviations_csc(C, ptr, idx, bg, e)
+        assert list(m.shards()) == [0, 1, 2, 2]
+        ref = orc.compute_deviations_core(C, sets, bg, e)
+        assert_close(res["dev"], ref["dev"], "deviations")
+        assert_close(res["z"], ref["z"], "z")
+    finally:
+        m.close()
