@@ -105,11 +105,12 @@ def set_seed(seed):
     _seed_rng = np.random.default_rng(seed)
 
 
-def _next_sampler_seed(force=False):
+def _next_sampler_seed():
+    """A fresh sampler seed for every getBackgroundPeaks call, like R advancing its RNG: without
+    set_seed() the stream starts from OS entropy (distributed.init() replaces that with one seed
+    broadcast from rank 0, so every rank draws the same background matrix)."""
     global _seed_rng
     if _seed_rng is None:
-        if not force:
-            return None
         _seed_rng = np.random.default_rng()
     return int(_seed_rng.integers(1, 2 ** 31 - 1))
 
@@ -134,9 +135,40 @@ def get_engine():
 
 
 class _CountsCache:
-    """Remembers which matrix object is resident on the device so that the usual sequence
-    getBackgroundPeaks(x) -> computeExpectations(x) -> computeDeviations(x, ...) uploads once."""
+    """Remembers which matrix is resident on the device so that the usual sequence
+    getBackgroundPeaks(x) -> computeExpectations(x) -> computeDeviations(x, ...) uploads once.
+    Python objects can be edited in place (mat.data[...] = ..., mat *= 2) without changing identity
+    or shape -- R's copy-on-modify cannot -- so residency is keyed on a content fingerprint, not on
+    the object alone: shape, number of stored entries, buffer addresses and checksums of the values
+    and of the structure (one pass over the host arrays, a few ms per 1e7 entries)."""
     obj = None
+    key = None
+
+
+def _fingerprint(mat):
+    if sp.issparse(mat):
+        m = mat
+        if not hasattr(m, "indptr"):
+            return ("sparse-other", id(mat))
+        d, i, p = m.data, m.indices, m.indptr
+        return ("csx", m.format, m.shape, int(m.nnz), d.__array_interface__["data"][0],
+                i.__array_interface__["data"][0], p.__array_interface__["data"][0], str(d.dtype),
+                float(np.sum(d, dtype=np.float64)) if d.size else 0.0,
+                float(np.dot(d[::7].astype(np.float64), (np.arange(d[::7].size) % 8191) + 1.0)) if d.size else 0.0,
+                int(np.sum(i[::3], dtype=np.int64)) if i.size else 0, int(p[-1]) if p.size else 0)
+    a = np.asarray(mat)
+    return ("dense", a.shape, a.__array_interface__["data"][0], str(a.dtype), float(np.sum(a, dtype=np.float64)),
+            float(np.sum(a[::5, ::3], dtype=np.float64)))
+
+
+def _is_resident(mat, eng):
+    return (_CountsCache.obj is mat and eng.P == mat.shape[0] and eng.N == mat.shape[1] and
+            _CountsCache.key == _fingerprint(mat))
+
+
+def _mark_resident(mat):
+    _CountsCache.obj = mat    # strong reference: the identity test stays meaningful
+    _CountsCache.key = _fingerprint(mat)
 
 
 def _is_matrix(x):
@@ -174,7 +206,7 @@ def _counts_matrix(object):
 def _load_counts(mat):
     """Make `mat` the engine's resident counts matrix (H2D + K1) unless it already is."""
     eng = get_engine()
-    if _CountsCache.obj is mat and eng.P == mat.shape[0] and eng.N == mat.shape[1]:
+    if _is_resident(mat, eng):
         return eng
     if sp.issparse(mat):
         m = mat if sp.isspmatrix_csc(mat) else sp.csc_matrix(mat)
@@ -184,12 +216,14 @@ def _load_counts(mat):
         if a.ndim != 2:
             raise ValueError("counts must be a matrix")
         eng.set_counts_dense(a)
-    _CountsCache.obj = mat    # strong reference: the identity test above stays meaningful
+    _mark_resident(mat)
     return eng
 
 
 def invalidate_counts_cache():
+    """Forget which matrix is resident (the next call uploads again)."""
     _CountsCache.obj = None
+    _CountsCache.key = None
 
 
 # --------------------------------------------------------------------------------------------
@@ -246,9 +280,7 @@ def getBackgroundPeaks(object, bias=None, niterations=50, w=0.1, bs=50):
     if bias.shape[0] != mat.shape[0]:
         raise ValueError("length(bias) == length(fragments_per_peak) is not TRUE")   # :123
     eng = _load_counts(mat)
-    seed = _next_sampler_seed()
-    if seed is not None:
-        eng.set_seed(seed)
+    eng.set_seed(_next_sampler_seed())
     try:
         return eng.background_peaks(bias, int(niterations), float(w), int(bs))
     except ChromVARError as e:
@@ -308,14 +340,14 @@ def compute_deviations_core(counts_mat, annoptr, annoidx, background_peaks, expe
             raise ValueError("background_peaks must hold integer peak indices")
     try:
         eng = get_engine()
-        resident = _CountsCache.obj is counts_mat and eng.P == P and eng.N == N
+        resident = _is_resident(counts_mat, eng)
         if not resident and sp.isspmatrix_csc(counts_mat):
             # counts not on the GPU yet: ONE library call, the H2D of the counts, the kernels and the
             # D2H of the results overlap (cv_deviations_csc); the counts are resident afterwards
             invalidate_counts_cache()
             res = eng.deviations_csc(P, N, counts_mat.indptr, counts_mat.indices, counts_mat.data, annoptr,
                                      annoidx.astype(np.int32), background_peaks, expectation, index_base=1)
-            _CountsCache.obj = counts_mat
+            _mark_resident(counts_mat)
         else:
             eng = _load_counts(counts_mat)
             res = eng.deviations(annoptr, annoidx.astype(np.int32), background_peaks, expectation, index_base=1)

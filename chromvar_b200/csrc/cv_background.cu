@@ -228,7 +228,9 @@ __device__ __forceinline__ double dnorm0(double x, double sigma) {
 }
 
 // One CTA per source bin i: wt[j] = weight(i, j) * [density[j] > 0], prefix-summed into the
-// CDF row cdf[i][.] (cdf[i][nb-1] == 1 exactly); optionally the normalised probabilities.
+// CDF row cdf[i][.]; optionally the normalised probabilities.  The running sum is not bit-equal to
+// the total, so the last occupied bin (and every empty bin behind it) is written as exactly 1: a
+// draw u1 in [0, 1) can then never fall past the last occupied bin.
 // weight(i, j) = binp[j + i*nb] when an explicit bin_p matrix is given (cv_bg_sample_helper),
 // else dnorm(euc_dist(bin_i, bin_j), 0, w) on the grid (R/background_peaks.R:144-145).
 #define CDF_THREADS 256
@@ -265,11 +267,21 @@ k_bin_cdf(const double* __restrict__ binp, GridParams g, double w, int nb,
     __syncthreads();
   }
   const double total = sh[CDF_THREADS - 1];
+  // last bin with a positive weight (occupied and within dnorm's range)
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = -1;
+  __syncthreads();
+  int my_last = -1;
+  for (int j = j0; j < j1; ++j)
+    if (weight(j) > 0.0) my_last = j;
+  if (my_last >= 0) atomicMax(&s_last, my_last);
+  __syncthreads();
+  const int last = s_last;
   double run = sh[threadIdx.x] - local;
   for (int j = j0; j < j1; ++j) {
     double wt = weight(j);
     run += wt;
-    cdf[(int64_t)i * nb + j] = run / total;
+    cdf[(int64_t)i * nb + j] = j >= last ? 1.0 : run / total;
     if (prob) prob[(int64_t)i * nb + j] = wt / total;
   }
 }
@@ -293,8 +305,9 @@ k_bg_sample(const int32_t* __restrict__ memb0, int P, int nb, const double* __re
     if (__ldg(row + mid) > u1) hi = mid; else lo = mid + 1;
   }
   uint32_t cnt = density[lo];
+  while (cnt == 0u && lo > 0) cnt = density[--lo];      // cannot happen with the clamped CDF; cheap to keep safe
   uint32_t within = (uint32_t)(u2 * (double)cnt);
-  if (within >= cnt) within = cnt - 1;
+  if (within >= cnt) within = cnt ? cnt - 1 : 0u;
   out[idx] = sorted[start[lo] + within] + 1;
 }
 

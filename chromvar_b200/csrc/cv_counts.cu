@@ -5,6 +5,8 @@
 //   getFragmentsPerPeak / getFragmentsPerSample / getTotalFragments  R/helper_functions.R:48-89
 //   counts_check                                                     R/utils.R:3-12
 //   compute_expectations_core                                        R/compute_deviations.R:415-448
+#include <math_constants.h>
+
 #include "cv_internal.cuh"
 
 static std::string g_create_err;
@@ -240,7 +242,7 @@ extern "C" int cv_stats(cv_handle* h, cv_stage_stats* out) {
 // flags[0] bit0: negative / non-finite / non-integer value; bit1: row index out of range;
 //          bit2: value >= 2^32
 // flags[1]: max value
-enum { FLAG_BADVAL = 1u, FLAG_BADROW = 2u, FLAG_HUGE = 4u, FLAG_BADIDX = 8u, FLAG_ZEROPEAK = 16u };
+enum { FLAG_BADVAL = 1u, FLAG_BADROW = 2u, FLAG_HUGE = 4u, FLAG_BADIDX = 8u, FLAG_ZEROPEAK = 16u, FLAG_FRACTION = 32u };
 
 // column of nonzero e: largest c with colptr[c] <= e   (searched in [lo, hi])
 __device__ __forceinline__ int find_col(const int64_t* __restrict__ colptr, int lo, int hi,
@@ -276,7 +278,8 @@ template <>
 __device__ __forceinline__ uint32_t load_count<double>(const double* __restrict__ x, int64_t e,
                                                        uint32_t& bad) {
   double v = x[e];
-  if (!(v >= 0.0) || v != floor(v)) { bad |= FLAG_BADVAL; return 0; }  // also catches NaN
+  if (!(v >= 0.0) || v == CUDART_INF) { bad |= FLAG_BADVAL; return 0; }  // also catches NaN
+  if (v != floor(v)) { bad |= FLAG_FRACTION; return 0; }
   if (v >= 4294967296.0) { bad |= FLAG_HUGE; return 0; }
   return (uint32_t)v;
 }
@@ -284,7 +287,8 @@ template <>
 __device__ __forceinline__ uint32_t load_count<float>(const float* __restrict__ x, int64_t e,
                                                       uint32_t& bad) {
   float v = x[e];
-  if (!(v >= 0.0f) || v != floorf(v)) { bad |= FLAG_BADVAL; return 0; }
+  if (!(v >= 0.0f) || v == CUDART_INF_F) { bad |= FLAG_BADVAL; return 0; }
+  if (v != floorf(v)) { bad |= FLAG_FRACTION; return 0; }
   if (v >= 4294967296.0f) { bad |= FLAG_HUGE; return 0; }
   return (uint32_t)v;
 }
@@ -733,9 +737,12 @@ int cv_counts_finish_async(cv_handle* h) {
 int cv_counts_verdict(cv_handle* h, const uint32_t* flags) {
   if (flags[0] & FLAG_BADROW) CV_FAIL(h, CV_ERR_INVALID, "counts: row index outside [0, P)");
   if (flags[0] & FLAG_HUGE) CV_FAIL(h, CV_ERR_UNSUPPORTED, "counts: value >= 2^32");
-  if (flags[0] & FLAG_BADVAL)
-    CV_FAIL(h, CV_ERR_INVALID,
-            "counts must be finite, non-negative and integer-valued (counts_check)");
+  if (flags[0] & FLAG_BADVAL)       // counts_check, R/utils.R:3-12: min(assays(object)$counts) >= 0
+    CV_FAIL(h, CV_ERR_INVALID, "counts must be finite and non-negative: min(assays(object)$counts) >= 0 is not TRUE (counts_check)");
+  if (flags[0] & FLAG_FRACTION)     // a restriction of this engine, not of the reference
+    CV_FAIL(h, CV_ERR_UNSUPPORTED,
+            "counts hold fractional values: this engine computes exact integer sums and accepts whole-number counts only "
+            "(the reference also runs on fractional counts, e.g. depth-normalised matrices; round them or use the R path)");
   h->max_val = flags[1];
   h->max_cell_tot = (uint64_t)flags[2] | ((uint64_t)flags[3] << 32);
   h->have_counts = true;

@@ -11,7 +11,8 @@ background matrix, expectation).  Exactly two cross-shard reductions exist (SURV
 
 With NCCL both run in place on the engine's device buffers (no host staging); with gloo (CPU
 tests) the same functions take host arrays.  The background matrix needs no broadcast: the
-sampler is a pure function of (global totals, bias, seed).
+sampler is a pure function of (global totals, bias, seed), and init() broadcasts ONE seed from
+rank 0 (share_seed) from which every rank derives the same per-call sampler seeds.
 """
 import os
 
@@ -38,7 +39,28 @@ def init(backend=None):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     else:
         dist.init_process_group(backend=backend)
+    share_seed()
     return rank, ws, local
+
+
+def share_seed(seed=None):
+    """One sampler seed stream for all ranks: rank 0's seed (given, or fresh entropy) is broadcast and
+    becomes every rank's api.set_seed().  Each later getBackgroundPeaks() call advances that stream
+    identically on every rank, so all cell shards are bias-corrected against the SAME background
+    matrix without broadcasting the matrix itself."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy) & (2 ** 62 - 1)
+    t = torch.tensor([int(seed)], dtype=torch.int64)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+    seed = int(t.item())
+    api.set_seed(seed)
+    return seed
 
 
 def shard_columns(colptr, world_size):

@@ -59,8 +59,12 @@ def _prep(object, annotations, background_peaks, expectation):
         raise ValueError("Annotations are not valid")
     if names is None:
         names = [str(i + 1) for i in range(len(sets))]
-    if not np.issubdtype(background_peaks.dtype, np.integer):
-        background_peaks = background_peaks.astype(np.int32)
+    if not np.issubdtype(background_peaks.dtype, np.integer):                 # as api.compute_deviations_core
+        bgf = background_peaks
+        with np.errstate(invalid="ignore"):
+            background_peaks = bgf.astype(np.int32)
+        if not np.array_equal(background_peaks, bgf):
+            raise ValueError("background_peaks must hold integer peak indices")
     return counts_mat, [np.asarray(s).astype(np.int64) for s in sets], list(names), background_peaks, expectation
 
 
@@ -195,7 +199,7 @@ def getPermutedData(object, niterations=10, w=0.1, bs=50):
     C = sp.csc_matrix(api.counts_check(object).assays["counts"])
     assays = dict(object.assays)
     for it in range(int(niterations)):
-        api.get_engine().set_seed(api._next_sampler_seed(force=True))      # a fresh draw per iteration (:184-186)
+        api.get_engine().set_seed(api._next_sampler_seed())      # a fresh draw per iteration (:184-186)
         bg = _bg_for_perm(object, C.shape[1], w, bs)                       # P x N
         cols = [C[np.asarray(bg[:, x]).astype(np.int64) - 1, x] for x in range(C.shape[1])]
         assays["perm_%d" % (it + 1)] = sp.hstack(cols).tocsc()
@@ -220,9 +224,7 @@ def getBackgroundPeaksAlternative(object, bias=None, niterations=50, window=500)
     if bias.shape[0] != mat.shape[0]:
         raise ValueError("length(bias) must equal nrow(object)")
     eng = api._load_counts(mat)
-    seed = api._next_sampler_seed()
-    if seed is not None:
-        eng.set_seed(seed)
+    eng.set_seed(api._next_sampler_seed())
     try:
         return eng.background_peaks_knn(bias, int(niterations), int(window))
     except ChromVARError as e:

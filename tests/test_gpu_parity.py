@@ -121,7 +121,7 @@ def test_mini_end_to_end_reproduces_bundled_mini_dev(golden_mini):
                                       colData={"Cell_Type": g["cell_type"], "depth": g["depth"]})
     ix = api.SummarizedExperiment({"matches": A}, colData={"name": g["ix_names"]})
     api.invalidate_counts_cache()
-    api.get_engine().set_seed(2017)
+    api.set_seed(2017)
     dev = api.computeDeviations(counts, ix)
     z, d = api.deviationScores(dev), api.deviations(dev)
     assert z.shape == (3, 35) and not np.isnan(z).any()

@@ -170,3 +170,38 @@ def test_bench_reference_arm_runs_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--quick",
                         "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_counts_fingerprint_sees_in_place_edits():
+    """residency of the counts on the GPU must not be decided by object identity alone --
+    an in-place edit keeps identity, shape and buffer addresses."""
+    import scipy.sparse as sp
+    from chromvar_b200 import api
+    rng = np.random.default_rng(0)
+    C = sp.random(200, 50, density=0.1, format="csc", random_state=np.random.RandomState(1),
+                  data_rvs=lambda n: rng.integers(1, 5, n).astype(np.float64))
+    k0 = api._fingerprint(C)
+    assert api._fingerprint(C) == k0
+    C.data[7] += 1.0                                  # same object, same buffers
+    k1 = api._fingerprint(C)
+    assert k1 != k0
+    C *= 2                                            # scipy keeps the object, rescales the values
+    assert api._fingerprint(C) != k1
+    D = np.asfortranarray(rng.integers(0, 4, size=(30, 20)).astype(np.float64))
+    kd = api._fingerprint(D)
+    D[3, 3] += 2
+    assert api._fingerprint(D) != kd
+
+
+def test_every_background_call_draws_a_fresh_seed():
+    """like R advancing its RNG, each getBackgroundPeaks call takes the next seed of the
+    stream; set_seed() makes the sequence reproducible."""
+    from chromvar_b200 import api
+    api.set_seed(11)
+    a = [api._next_sampler_seed() for _ in range(3)]
+    api.set_seed(11)
+    b = [api._next_sampler_seed() for _ in range(3)]
+    assert a == b and len(set(a)) == 3
+    api._seed_rng = None
+    assert api._next_sampler_seed() != api._next_sampler_seed()
+    api._seed_rng = None
