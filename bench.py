@@ -12,7 +12,12 @@ batch of synthetic scATAC input: BASELINE.json config 2 (100k peaks x 10k cells,
   value : device-timed (CUDA events on the library's stream), inputs resident in HBM.
   e2e   : the same metric through the C ABI with pinned HOST buffers, every step paying the
           H2D of counts / annotations / background / expectation and the D2H of both K x N
-          result matrices.
+          result matrices; e2e.pageable: the same call on pageable host memory (what R passes).
+  parity: at every N, every rank checks a random annotation sample of its own results against the
+          CPU restatement (oracle/), integer observed / background sums included.
+  workloads: N = 1: configs 3, 4 and the config-5 shard (device-timed, parity, roofline, timed
+          getBackgroundPeaks); N > 1: the atlas (one config-5 shard per GPU) and `single_process`,
+          the same e2e call through cv_multi from ONE process driving all GPUs.
 """
 import argparse
 import json
@@ -198,7 +203,7 @@ def make_workload(rank, cells, quick, workload=None, gen="host", device=None):
         name = workload or WORKLOAD
         cfg = dict(synthetic.CONFIGS[name])
         cfg.update(over)
-        big = cfg["density"] < 1.0 and cfg["P"] * cfg["N"] * cfg["density"] >= 5e8
+        big = cfg["density"] < 1.0 and cfg["P"] * cfg["N"] * cfg["density"] >= 1e8
         use_dev = device is not None and (gen == "device" or (gen == "auto" and big))
         d = synthetic.make_config(name, seed_offset=rank, device=device if use_dev else None, **over)
         if use_dev:
@@ -213,80 +218,141 @@ def make_workload(rank, cells, quick, workload=None, gen="host", device=None):
     return d, name
 
 
-# ------------------------------------------------------------------------------------------------
-# reference arm: CPU restatement of the reference algorithm (the reference's R path cannot run:
-# no R on this image).  Only this leg and cpu_baseline execute anything under oracle/.
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_step(d, bg, e, anno_slice, workers, want_results=False):
-    from oracle import chromvar_oracle as orc
+def workload_config(name, d, ws, background):
+    """The `config` object of the JSON line: what the workload IS.  Built by this one function for both
+    arms so that their lines describe the same configuration key for key (engine choices such as
+    kernel / tile / step call live under "engine", not here)."""
+    C = d["counts"]
+    return {"workload": name, "peaks": int(C.shape[0]), "cells_per_gpu": int(C.shape[1]),
+            "annotations": int(len(d["annoptr"]) - 1), "niterations": NITER, "nnz_per_gpu": int(C.nnz),
+            "nnz_annotations": int(d["annoptr"][-1]), "cells_total": int(C.shape[1]) * int(ws),
+            "generator": d["cfg"].get("generator", "numpy (make_counts)"), "background": background,
+            "l2": "256 MB flush write between timed steps"}
+
+
+BG_KIND = "synthetic.background_matrix(seed 20173): numpy generative sampler, same matrix for both arms"
+
+
+def sets_of(d, ks):
     ptr, idx = d["annoptr"], d["annoidx"]
-    sets = [idx[ptr[k]:ptr[k + 1]].astype(np.int64) for k in anno_slice]
+    return [idx[ptr[k]:ptr[k + 1]].astype(np.int64) for k in ks]
+
+
+# ------------------------------------------------------------------------------------------------
+# parity: results against the CPU restatement of the reference (oracle/), random annotation sample,
+# integer sums included (SURVEY 8d "parity assertions in every timed run")
+# ------------------------------------------------------------------------------------------------
+def rel_err(got, ref):
+    """(max abs(d) / max(abs(ref), 1e-3), NA / NaN / inf masks equal)"""
+    ng, nr = np.isnan(got), np.isnan(ref)
+    ig, ir = np.isinf(got), np.isinf(ref)
+    ok = bool(np.array_equal(ng, nr) and np.array_equal(ig, ir) and np.array_equal(got[ig], ref[ir]))
+    m = ~(nr | ng | ir | ig)
+    worst = float((np.abs(got[m] - ref[m]) / np.maximum(np.abs(ref[m]), 1e-3)).max()) if m.any() else 0.0
+    return worst, ok
+
+
+def parity_block(eng, d, bg, e, got_dev, got_z, rank, workers, n_anno, cell_lo, cell_hi, slab=384, timed=False):
+    """Random sample of n_anno annotations: deviations / z of cells [cell_lo, cell_hi) of the results
+    `got_*` (K x N, whatever call produced them) against the oracle; observed and background integer
+    sums bit-equal on a slab of `slab` cells (a separate call of the same kernels with the sums kept).
+    Leaves the slab resident on the engine: call it last.  Returns (report, seconds of the oracle run,
+    annotations x cells it covered)."""
+    from oracle import chromvar_oracle as orc
+    C = d["counts"]
+    P, N = C.shape
+    K = len(d["annoptr"]) - 1
+    rng = np.random.default_rng(9000 + rank)
+    ks = np.sort(rng.choice(K, size=min(n_anno, K), replace=False))
+    Csub = C[:, cell_lo:cell_hi].tocsc() if (cell_lo, cell_hi) != (0, N) else C
+    farm = orc.TaskFarm(Csub, sets_of(d, range(K)), bg, e, workers)
     t0 = time.perf_counter()
-    res = orc.deviations_task_farm(d["counts"], sets, bg, e, workers)
+    ref_z, ref_dev = farm.run(ks)
     dt = time.perf_counter() - t0
-    return (dt, res) if want_results else dt
+    farm.close()
+    ez, okz = rel_err(np.asarray(got_z[ks][:, cell_lo:cell_hi]), ref_z)
+    ed, okd = rel_err(np.asarray(got_dev[ks][:, cell_lo:cell_hi]), ref_dev)
+    rep = {"annotations_checked": int(ks.size), "annotation_sample": "random, seed %d" % (9000 + rank),
+           "cells": int(cell_hi - cell_lo), "tolerance": 1e-5, "max_rel_err": max(ez, ed),
+           "na_masks_equal": bool(okz and okd)}
+    # integer sums on a slab of cells
+    c0 = int(rng.integers(0, max(1, N - slab + 1)))
+    c1 = min(N, c0 + slab)
+    Cs = C[:, c0:c1].tocsc()
+    eng.set_option("check_zero_peaks", 0)
+    eng.set_counts_csc(P, c1 - c0, Cs.indptr, Cs.indices, Cs.data)
+    got = eng.deviations(d["annoptr"], d["annoidx"].astype(np.int32), bg, e, index_base=1, sums=True)
+    farm = orc.TaskFarm(Cs, sets_of(d, range(K)), bg, e, workers)
+    rz, rd, robs, rsamp = farm.run(ks, sums=True)
+    farm.close()
+    obs_eq = bool(np.array_equal(got["observed"][ks], robs.astype(np.int64)))
+    samp_eq = bool(np.array_equal(got["sampled"][ks], rsamp.astype(np.int64)))
+    e2, ok2 = rel_err(got["z"][ks], rz)
+    e3, ok3 = rel_err(got["dev"][ks], rd)
+    rep["integer_sums"] = {"cells": int(c1 - c0), "first_cell": c0, "observed_bit_equal": obs_eq,
+                           "background_bit_equal": samp_eq, "sums_compared": int(ks.size * (NITER + 1) * (c1 - c0)),
+                           "max_rel_err_slab": max(e2, e3)}
+    rep["max_rel_err"] = max(rep["max_rel_err"], e2, e3)
+    rep["na_masks_equal"] = bool(rep["na_masks_equal"] and ok2 and ok3)
+    rep["pass"] = bool(rep["na_masks_equal"] and rep["max_rel_err"] <= 1e-5 and obs_eq and samp_eq)
+    return rep, dt, int(ks.size) * int(cell_hi - cell_lo)
 
 
-def parity_report(got_dev, got_z, ref_dev, ref_z):
-    """GPU results of the timed e2e step against the CPU restatement on the sampled annotations:
-    abs(d) <= 1e-5 * max(abs(ref), 1e-3) and identical NA masks."""
-    out = {"annotations_checked": int(ref_z.shape[0]), "cells": int(ref_z.shape[1]), "tolerance": 1e-5}
-    worst = 0.0
-    ok = True
-    for g, r in ((got_dev, ref_dev), (got_z, ref_z)):
-        ng, nr = np.isnan(g), np.isnan(r)
-        ok &= bool(np.array_equal(ng, nr))
-        m = ~(nr | ng | np.isinf(r))
-        if m.any():
-            worst = max(worst, float((np.abs(g[m] - r[m]) / np.maximum(np.abs(r[m]), 1e-3)).max()))
-    out["max_rel_err"] = worst
-    out["na_masks_equal"] = ok
-    out["pass"] = bool(ok and worst <= 1e-5)
-    return out
+def reduce_parity(rep, ws, dist, dev):
+    """All ranks -> one verdict: pass only if every rank passed; the worst error."""
+    if ws == 1:
+        rep["ranks_checked"] = 1
+        return rep
+    import torch
+    t = torch.tensor([1.0 if rep["pass"] else 0.0, -rep["max_rel_err"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    rep = dict(rep)
+    rep["pass"] = bool(t[0].item() >= 1.0)
+    rep["max_rel_err"] = float(-t[1].item())
+    rep["ranks_checked"] = ws
+    return rep
 
 
-def host_background(d, rng):
-    """A background matrix for the reference arm when no GPU sampler is available: peaks with a
-    similar fragment total (what the sampler's bins encode), cheap and deterministic."""
-    fpp = np.asarray(d["counts"].sum(axis=1)).ravel()
-    order = np.argsort(fpp, kind="stable")
-    rank_of = np.empty_like(order)
-    rank_of[order] = np.arange(order.size)
-    P = fpp.size
-    jitter = rng.integers(-200, 201, size=(P, NITER))
-    pos = np.clip(rank_of[:, None] + jitter, 0, P - 1)
-    return np.asfortranarray((order[pos] + 1).astype(np.int32))
-
-
+# ------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference algorithm on the box's host cores (the
+# reference's R path cannot run: no R on this image).  Only this leg, cpu_baseline and the parity
+# block execute anything under oracle/.
+# ------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank, ws = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    from chromvar_b200 import synthetic
+    from oracle import chromvar_oracle as orc
     d, name = make_workload(0, args.cells, args.quick, args.workload)
     C = d["counts"]
     P, N = C.shape
     K = len(d["annoptr"]) - 1
     e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
-    bg = host_background(d, np.random.default_rng(20173))
+    bg = synthetic.background_matrix(C, d["bias"], NITER, 0.1, 50, seed=20173)
     workers = os.cpu_count() or 1
-    S = max(1, min(K, workers))
+    S = max(1, min(K, 2 * workers))                       # two annotations per worker and step
+    farm = orc.TaskFarm(C, sets_of(d, range(K)), bg, e, workers)      # pool + row-major counts: set up once
     times = []
+    rng = np.random.default_rng(4242)
     for s in range(args.warmup + args.steps):
-        sl = [(s * S + j) % K for j in range(S)]
-        dt = cpu_reference_step(d, bg, e, sl, workers)
+        ks = rng.choice(K, size=S, replace=False)
+        t0 = time.perf_counter()
+        farm.run(ks)
+        dt = time.perf_counter() - t0
         log("[bench/reference] step %d: %d annotations x %d cells in %.2fs" % (s, S, N, dt))
         if s >= args.warmup:
             times.append(dt)
+    farm.close()
     tot = float(np.sum(times))
     value = S * N * len(times) / tot
-    sample = "%d of %d annotations x all %d cells per step, fork pool of %d workers" % (S, K, N, workers)
+    sample = "%d random annotations of %d x all %d cells per step, fork pool of %d workers kept across steps" % (S, K, N, workers)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
-                   "niterations": NITER, "nnz": int(C.nnz)},
+        "config": workload_config(name, d, args.gpus, BG_KIND),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
                          "note": "CPU restatement of the reference algorithm (scipy fp64, per-annotation "
                                  "sparse products incl. the per-annotation colSums, fork pool = "
@@ -299,34 +365,88 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from chromvar_b200 import _lib, distributed as cvd
+def issue_peak_tflops(sm_mhz, operand_bits, n_sms=148):
+    """Issue ceiling of the tcgen05 pipe for this kernel's instruction shape, from the probe
+    (tools/fp4_probe.cu, profiles/r01j): one M128 N256 instruction per SM every 128.1 cycles, K = 64
+    (e2m1, kind::mxf4) or 32 (u8, kind::i8) peaks per instruction."""
+    kk = 64 if operand_bits == 4 else 32
+    return n_sms * (2.0 * 128 * 256 * kk / 128.1) * sm_mhz * 1e6 / 1e12
 
-    rank, ws, local = cvd.init()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    eng = _lib.Handle(local, seed=20173)
-    eng.set_option("path", args.path)
-    eng.set_option("dense_cta_pair", args.pair)
-    eng.set_option("dense_fp4", args.fp4)
-    eng.set_option("dense_lockstep", args.lockstep)
-    eng.set_option("host_narrow", args.host_narrow)
-    eng.set_option("tail_chunk", args.tail_chunk)
-    if args.chunk:
-        eng.set_option("cell_chunk", args.chunk)
-    if args.band:
-        eng.set_option("dense_band", args.band)
-    if args.debug_no_tma:
-        eng.set_option("debug_no_tma", args.debug_no_tma)
-    d, name = make_workload(rank, args.cells, args.quick, args.workload, gen=args.gen, device="cuda:%d" % local)
+
+def roofline_of(st, c_ms, total_ms_per_step, flops_alg, peaks, peaks_kind, sm_mhz, workload, bytes_alg=0, upd=0):
+    share = c_ms / total_ms_per_step if total_ms_per_step else None
+    if st["path"] == 1:
+        fp4 = st.get("operand_bits") == 4
+        launches = max(1, st["n_cell_tiles"] * max(st["planes"], 1))
+        achieved = flops_alg / (c_ms * 1e-3) / 1e12
+        peak_issue = issue_peak_tflops(sm_mhz or 1965.0, 4 if fp4 else 8)
+        mult = 4.0 if fp4 else 2.0
+        kname = "k_dense_contract_fp4" if fp4 else ("k_dense_contract_pair" if st["cell_tile"] == 256 else "k_dense_contract")
+        return {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak_issue, "unit": "TFLOP/s",
+                "frac": achieved / peak_issue,
+                "peak_kind": "probe-measured tcgen05 issue rate of this instruction shape (%s, 128.1 cycles per "
+                             "M128 N256 K%d instruction and SM) x 148 SMs x the SM clock sampled in this run (%.0f MHz)"
+                             % ("kind::mxf4 e2m1" if fp4 else "kind::i8 u8", 64 if fp4 else 32, sm_mhz or 1965.0),
+                "peak_bf16_derived_burst": mult * peaks["bf16_tflops"],
+                "frac_vs_bf16_derived_burst": achieved / (mult * peaks["bf16_tflops"]),
+                "peak_bf16_derived_kind": peaks_kind + " MEASURED_PEAKS bf16 burst x %d (%s vs bf16 MAC rate); a cuBLAS-bf16-"
+                                          "derived figure under-states this pipe for 97 %%-zero operands (no power throttling)"
+                                          % (int(mult), "e2m1" if fp4 else "int8"),
+                "peak_nominal": 9000.0 if fp4 else 4500.0, "frac_vs_nominal": achieved / (9000.0 if fp4 else 4500.0),
+                "traffic": ncu_traffic(kname, workload),
+                "ms_per_launch": c_ms / launches, "launches_per_step": int(launches),
+                "algorithmic_ops_per_launch": flops_alg / launches, "padded_ops_per_step": st["contract_flops"],
+                "share_of_step": share, "operand_bits": st.get("operand_bits"),
+                "overflow_columns_per_step": st.get("overflow_columns")}
+    achieved = bytes_alg / (c_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peaks_kind, "ms_per_launch": c_ms,
+            "algorithmic_bytes_per_launch": int(bytes_alg), "updates_per_launch": int(upd), "share_of_step": share}
+
+
+def dtype_string(st):
+    if st["path"] != 1:
+        return "int32 sums, f64 epilogue"
+    return "%s, %s epilogue" % ("e2m1 x e2m1 -> f32 holding exact integers (tcgen05 kind::mxf4)" if st.get("operand_bits") == 4
+                                else "u8 x u8 -> s32 (tcgen05 kind::i8)",
+                                "u64 fixed-point mean / f32 two-sweep variance / f64 tail" if st.get("epilogue") == 32 else "f64")
+
+
+class Timed:
+    """K steps of `step()` on the engine's stream, each bracketed by CUDA events, L2 flushed between."""
+
+    def __init__(self, torch, eng, dev):
+        self.torch, self.eng, self.dev = torch, eng, dev
+        self.ext = torch.cuda.ExternalStream(eng.stream(), device=dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def run(self, step, steps):
+        torch = self.torch
+        pending = []
+        for _ in range(steps):
+            with torch.cuda.stream(self.ext):
+                self.flush.zero_()                           # L2 flush between timed iterations
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(self.ext)
+            step()
+            ev1.record(self.ext)
+            pending.append((ev0, ev1))
+        self.eng.deviations_wait()                           # flag words of the queued calls verified here
+        torch.cuda.synchronize(self.dev)
+        return [a.elapsed_time(b) for a, b in pending]
+
+
+def run_workload(torch, dist, eng, dev, rank, ws, d, name, args, steps, warmup, with_e2e, gloo_group=None, parity_anno=None,
+                 full_cells_parity=True, bg_from="synthetic"):
+    """One workload on this rank's engine: set-up, K device-timed steps, (optionally) the e2e legs,
+    parity.  Returns a dict of measurements (every rank; rank 0 assembles the JSON)."""
+    from chromvar_b200 import _lib, distributed as cvd, synthetic
     C = d["counts"]
     P, N = C.shape
     K = len(d["annoptr"]) - 1
     nnz = int(C.nnz)
+    timed = Timed(torch, eng, dev)
+    ext = timed.ext
 
     def pin(a):
         """Pinned copy of a (memory order kept: the background matrix stays column-major); arrays
@@ -342,243 +462,373 @@ def run_ours(args):
                                pin(C.data.astype(np.float64, copy=False)))
     h_ptr, h_idx = pin(d["annoptr"]), pin(d["annoidx"].astype(np.int32))
 
+    def barrier():
+        if ws > 1:
+            dist.barrier(group=gloo_group) if gloo_group is not None else dist.barrier()
+        torch.cuda.synchronize(dev)
+
     # ---- setup (untimed): counts -> HBM, global per-peak totals, expectation, background -------
-    eng.set_counts_csc(P, N, h_colptr, h_rowidx, h_x)
+    eng.set_option("check_zero_peaks", 1 if ws == 1 else 0)   # a shard may hold no fragment of a peak; e is global
+    if "dense" in d and ws == 1:
+        eng.set_counts_dense(d["dense"])                      # bulk: base-matrix input as the reference holds it
+    else:
+        eng.set_counts_csc(P, N, h_colptr, h_rowidx, h_x)
     cvd.allreduce_peak_totals(eng)                       # NCCL all-reduce of int64[P+1] when ws > 1
     t0 = time.perf_counter()
     e = eng.expectations()
     t_exp = time.perf_counter() - t0
+    eng.set_seed(20173)
     eng.background_peaks(d["bias"], NITER, 0.1, 50)      # warm-up (allocations, module load)
     t0 = time.perf_counter()
-    bg = eng.background_peaks(d["bias"], NITER, 0.1, 50)
+    bg_gpu = eng.background_peaks(d["bias"], NITER, 0.1, 50)
     t_bg = time.perf_counter() - t0
     bg_ms_dev = eng.stats()["ms_background"]
-    # the sampler of makePermutedSets (get_background_peaks_alternative, R/test_sets.R:291-330): exact
-    # 10 nearest neighbours of every peak in the whitened (fragments, bias) plane + the draws
-    eng.background_peaks_knn(d["bias"], NITER, 10)
-    t0 = time.perf_counter()
-    eng.background_peaks_knn(d["bias"], NITER, 10)
-    t_knn = time.perf_counter() - t0
-    knn_ms_dev = eng.stats()["ms_background"]
+    other = {"getBackgroundPeaks_ms_device": bg_ms_dev, "getBackgroundPeaks_ms_wall": 1e3 * t_bg,
+             "getBackgroundPeaks_peaks": int(P), "sampled_indices_per_s": P * NITER / max(t_bg, 1e-9),
+             "getBackgroundPeaks_hbm_frac_of_write": (4.0 * P * NITER + 16.0 * P) / max(bg_ms_dev * 1e-3, 1e-12) / 1e9 /
+             peaks_json()[0]["hbm_gbs"], "computeExpectations_ms_wall": 1e3 * t_exp}
+    if bg_from == "synthetic" and ws == 1:
+        # the matrix both arms are fed (see workload_config): host generative sampler, seeded
+        bg = synthetic.background_matrix(C, d["bias"], NITER, 0.1, 50, seed=20173)
+        bg_kind = BG_KIND
+    else:
+        bg = bg_gpu                                       # shards: the GPU sampler on the reduced totals (same seed on every rank)
+        bg_kind = "cv_background_peaks (GPU sampler, seed 20173%s)" % (", global totals" if ws > 1 else "")
     h_bg, h_e = pin(bg), pin(e)
     eng.deviations_upload(h_ptr, h_idx, h_bg, h_e, index_base=1)
 
-    ext = torch.cuda.ExternalStream(eng.stream(), device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def barrier():
-        if ws > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # One rank: the K timed steps are enqueued back to back through cv_deviations_compute_async (every
-    # kernel of the path runs each step; the host-side verdicts are those of the checked warm-up calls),
-    # so a descheduled host thread -- these shared boxes stall the host for 10-100 ms at a time -- no
-    # longer shows up as GPU idle time inside a step.  Several ranks: the variability reduction needs
-    # each step's partials on the host, so the checked call and its synchronisation stay.
-    use_async = args.async_steps == 1 if ws == 1 else args.async_steps == 2
-    gathered = mine = None
-
-    def step():
-        if use_async:
-            eng.deviations_compute_async(rebuild_counts_layout=True)
-            if ws > 1:
-                # reduction 2 stays in every step, on the device: NCCL all-gather of the K x 4 partials
-                # behind the step's kernels (stream-ordered, no host wait); Chan merge after the loop
-                with torch.cuda.stream(ext):
-                    dist.all_gather_into_tensor(gathered, mine)
-            return
-        eng.deviations_compute(rebuild_counts_layout=True, keep_sums=False)
-        if ws > 1:
-            cvd.gather_variability(eng)                  # reduction 2 (K x 4 doubles)
-
-    if use_async and ws > 1:
-        eng.deviations_compute(rebuild_counts_layout=True, keep_sums=False)      # the checked call: verdicts, buffers
+    # ---- the timed step: every kernel of the path, queued without host synchronisation ------------
+    # cv_deviations_compute_async replays the verdicts of the checked warm-up call; with several ranks
+    # reduction 2 (variability partials) stays in every step, on the device: NCCL all-gather of the
+    # K x 4 partials behind the step's kernels + cv_variability_merge_device.  Same definition at every N.
+    eng.deviations_compute(rebuild_counts_layout=True, keep_sums=False)      # the checked call: verdicts, buffers
+    mine = gathered = None
+    if ws > 1:
         mine = torch.as_tensor(eng.variability_partials_device(), device=dev)    # the engine's own buffer (grow-only)
         gathered = torch.empty(ws * mine.numel(), dtype=mine.dtype, device=dev)
-    for _ in range(args.warmup):
+
+    def step(collective=True):
+        eng.deviations_compute_async(rebuild_counts_layout=True)
+        if ws > 1 and collective:
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(gathered, mine)
+            eng.variability_merge_device(gathered.data_ptr(), ws)
+
+    for _ in range(warmup):
         step()
-    if use_async:
-        eng.deviations_wait()
+    eng.deviations_wait()
     launches0 = eng.stats()["kernel_launches"]
-    sampler = ClockSampler(local, args.clock_sampler)
+    sampler = ClockSampler(dev.index, args.clock_sampler)
     sampler.start()
     barrier()
-    step_ms, contract_ms, stage_acc = [], [], np.zeros(4)
-    upd = bytes_alg = path = 0
-    pending = []
-    for _ in range(args.steps):
-        with torch.cuda.stream(ext):
-            flush.zero_()                                # L2 flush between timed iterations
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(ext)
-        step()
-        ev1.record(ext)
-        if use_async:
-            pending.append((ev0, ev1))                   # settled after the loop
-            continue
-        ev1.synchronize()
-        step_ms.append(ev0.elapsed_time(ev1))
-        if sampler.mode == "inline":
-            sampler.sample()
-        st = eng.stats()
-        contract_ms.append(st["ms_contract"])
-        stage_acc += [st["ms_counts_layout"], st["ms_anno_prep"], st["ms_contract"], st["ms_finalize"]]
-        upd, bytes_alg, path = st["contract_updates"], st["contract_bytes"], st["path"]
-        tile_cells, gemm_launches, padded_flops = st["cell_tile"], st["n_cell_tiles"] * max(st["planes"], 1), st["contract_flops"]
-    if use_async:
-        eng.deviations_wait()                            # flag words of the queued calls verified here
-        torch.cuda.synchronize(dev)
-        if ws > 1:
-            sd_all = _lib.merge_variability(gathered.view(ws, -1, 4).cpu().numpy(), na_rm=True)
-            assert sd_all.shape[0] == K and np.isfinite(sd_all).any()
-        step_ms = [a.elapsed_time(b) for a, b in pending]
-        st = eng.stats()                                 # timed spans of the last queued step
-        contract_ms = [st["ms_contract"]]
-        stage_acc += np.array([st["ms_counts_layout"], st["ms_anno_prep"], st["ms_contract"], st["ms_finalize"]]) * args.steps
-        upd, bytes_alg, path = st["contract_updates"], st["contract_bytes"], st["path"]
-        tile_cells, gemm_launches, padded_flops = st["cell_tile"], st["n_cell_tiles"] * max(st["planes"], 1), st["contract_flops"]
+    step_ms = timed.run(step, steps)
     barrier()
     launches = eng.stats()["kernel_launches"] - launches0
+    st = eng.stats()                                     # timed spans of the last queued step
     total_ms = float(np.sum(step_ms))
-    log("[bench] rank %d: ms of each timed step: %s" % (rank, [round(x, 2) for x in step_ms]))
+    log("[bench] rank %d %s: ms of each timed step: %s" % (rank, name, [round(x, 2) for x in step_ms]))
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
-    value = K * N * ws * args.steps / (total_ms_max * 1e-3)
-
-    # ---- e2e through the C ABI with pinned host buffers ---------------------------------------------
-    out = dict(dev=pin(np.empty((K, N), np.float64, order="F").ravel(order="K")).reshape((K, N), order="F"),
-               z=pin(np.empty((K, N), np.float64, order="F").ravel(order="K")).reshape((K, N), order="F"),
-               matches=np.empty(K), overlap=np.empty(K), variability=np.empty(K))
-
-    def e2e_step():
-        # compute_deviations_core as the R shim calls it: ONE ABI call on host buffers (counts CSC,
-        # annotations, background, expectation in; deviations / z out).  The library overlaps the
-        # chunked H2D of the counts and the chunked D2H of the results with the kernels.
-        eng.deviations_csc(P, N, h_colptr, h_rowidx, h_x, h_ptr, h_idx, h_bg, h_e, index_base=1, out=out)
-        if ws > 1:
-            cvd.gather_variability(eng)
-
+    res = {"name": name, "config": workload_config(name, d, ws, bg_kind), "P": P, "N": N, "K": K, "nnz": nnz, "step_ms": step_ms, "total_ms_max": total_ms_max,
+           "value": K * N * ws * steps / (total_ms_max * 1e-3), "launches": int(launches), "st": st, "other": other,
+           "bg_kind": bg_kind, "steps": steps, "warmup": warmup}
     if ws > 1:
-        eng.set_option("check_zero_peaks", 0)     # a shard may hold no fragment of a peak; e is global
+        sd_all = eng.deviations_download(vectors_only=True)["variability"]
+        res["variability_merged_on_device"] = bool(sd_all.shape[0] == K and np.isfinite(sd_all).any())
 
-    e2e_step()
-    e2e_step()
-    barrier()
-    import gc
-    gc.collect()
-    gc.disable()                 # a gen-2 collection of the harness costs ~10 ms when it lands inside a step
-    t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 10)) if not args.e2e_steps else args.e2e_steps
-    e2e_each, e2e_lib = [], []
-    for _ in range(n_e2e):
-        t1 = time.perf_counter()
-        e2e_step()
-        e2e_each.append(1e3 * (time.perf_counter() - t1))
-        e2e_lib.append(eng.stats()["ms_h2d"])          # wall clock inside cv_deviations_csc
-        if sampler.mode == "inline":
-            sampler.sample()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    gc.enable()
-    clocks = sampler.stop()                              # sampled across both timed regions
-    e2e_stats = eng.stats()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if ws > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = K * N * ws * n_e2e / float(te.item())
-    host_in = h_colptr.nbytes + h_rowidx.nbytes + h_x.nbytes + h_ptr.nbytes + h_idx.nbytes + h_bg.nbytes + h_e.nbytes
-    # bytes that crossed PCIe: the library narrows the fp64 values to bytes on host threads before the
-    # copy (cv_hostnarrow.cpp), so fewer bytes travel than the host buffers hold
-    h2d = int(e2e_stats.get("h2d_bytes", 0)) or host_in
-    d2h = 2 * K * N * 8 + 3 * K * 8
+    # ---- e2e through the C ABI: one cv_deviations_csc call per step on HOST buffers ----------------
+    out = None
+    if with_e2e:
+        def outbuf(pinned):
+            mk = (lambda a: pin(a.ravel(order="K")).reshape((K, N), order="F")) if pinned else (lambda a: a)
+            return dict(dev=mk(np.empty((K, N), np.float64, order="F")), z=mk(np.empty((K, N), np.float64, order="F")),
+                        matches=np.empty(K), overlap=np.empty(K), variability=np.empty(K))
+
+        def e2e_leg(bufs, o, n_steps):
+            cp, ri, x, ap, ai, b, ee = bufs
+
+            def one():
+                # compute_deviations_core as the R shim calls it: ONE ABI call on host buffers (counts CSC,
+                # annotations, background, expectation in; deviations / z out).  The library overlaps the
+                # chunked H2D of the counts and the chunked D2H of the results with the kernels.
+                eng.deviations_csc(P, N, cp, ri, x, ap, ai, b, ee, index_base=1, out=o)
+                if ws > 1:
+                    with torch.cuda.stream(ext):
+                        dist.all_gather_into_tensor(gathered, torch.as_tensor(eng.variability_partials_device(), device=dev))
+                    eng.variability_merge_device(gathered.data_ptr(), ws)
+                    torch.cuda.synchronize(dev)
+            one()
+            one()
+            barrier()
+            import gc
+            gc.collect()
+            gc.disable()             # a gen-2 collection of the harness costs ~10 ms when it lands inside a step
+            t0 = time.perf_counter()
+            each, lib = [], []
+            for _ in range(n_steps):
+                t1 = time.perf_counter()
+                one()
+                each.append(1e3 * (time.perf_counter() - t1))
+                lib.append(eng.stats()["ms_h2d"])          # wall clock inside cv_deviations_csc
+                if sampler.mode == "inline":
+                    sampler.sample()
+            barrier()
+            dt = time.perf_counter() - t0
+            gc.enable()
+            te = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if ws > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te.item()), each, lib
+
+        n_e2e = max(1, min(steps, 10)) if not args.e2e_steps else args.e2e_steps
+        out = outbuf(True)
+        pinned_bufs = (h_colptr, h_rowidx, h_x, h_ptr, h_idx, h_bg, h_e)
+        t_pin, each_pin, lib_pin = e2e_leg(pinned_bufs, out, n_e2e)
+        e2e_stats = eng.stats()
+        # the same call on PAGEABLE host memory: what R hands over (R's vectors are ordinary heap memory)
+        pageable = tuple(np.array(a, copy=True, order="K") for a in pinned_bufs)
+        out_pg = outbuf(False)
+        t_pg, each_pg, lib_pg = e2e_leg(pageable, out_pg, n_e2e)
+        host_in = sum(a.nbytes for a in pinned_bufs)
+        res["e2e"] = {"value": K * N * ws * n_e2e / t_pin, "unit": UNIT,
+                      "h2d_bytes_per_step": int(e2e_stats.get("h2d_bytes", 0)) or int(host_in),
+                      "d2h_bytes_per_step": int(2 * K * N * 8 + 3 * K * 8), "host_input_bytes_per_step": int(host_in),
+                      "host_memory": "pinned (cudaHostAlloc'ed by torch)",
+                      "ms_per_step": 1e3 * t_pin / n_e2e, "steps": n_e2e, "ms_per_step_median": float(np.median(each_pin)),
+                      "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
+                      "gemm_kernel": ("k_dense_contract_fp4" if e2e_stats.get("operand_bits") == 4 else "k_dense_contract_pair")
+                      if e2e_stats["cell_tile"] == 256 else ("k_dense_contract" if e2e_stats["path"] == 1 else "k_contract"),
+                      "cell_chunks": int(e2e_stats["n_cell_tiles"]), "ms_each_step": [round(t, 2) for t in each_pin],
+                      "ms_inside_library": [round(t, 2) for t in lib_pin],
+                      "device_ms": {k: round(float(e2e_stats[k]), 3) for k in
+                                    ("ms_counts_layout", "ms_anno_prep", "ms_contract", "ms_finalize")},
+                      "pageable": {"value": K * N * ws * n_e2e / t_pg, "unit": UNIT, "ms_per_step": 1e3 * t_pg / n_e2e,
+                                   "ms_per_step_median": float(np.median(each_pg)), "steps": n_e2e,
+                                   "host_memory": "pageable numpy arrays (what R's .Call passes), outputs pageable too",
+                                   "ms_each_step": [round(t, 2) for t in each_pg],
+                                   "results_equal_pinned_leg": bool(np.array_equal(out_pg["z"], out["z"], equal_nan=True))}}
+    res["clocks"] = sampler.stop()
+    res["bg"], res["e"], res["out"] = bg, e, out
+    return res
+
+
+def check_workload_parity(torch, dist, eng, dev, rank, ws, d, res, args, n_anno, full_cells):
+    """Parity of a workload's results (see parity_block); also yields the cpu_baseline figure."""
+    C = d["counts"]
+    P, N = C.shape
+    workers = max(1, (os.cpu_count() or 1) // ws)
+    if res["out"] is not None:
+        got_dev, got_z = res["out"]["dev"], res["out"]["z"]
+    else:
+        o = eng.deviations_download()
+        got_dev, got_z = o["dev"], o["z"]
+    if full_cells:
+        lo, hi = 0, N
+    else:
+        rng = np.random.default_rng(77 + rank)
+        lo = int(rng.integers(0, max(1, N - 2048 + 1)))
+        hi = min(N, lo + 2048)
+    rep, dt, units = parity_block(eng, d, res["bg"], res["e"], got_dev, got_z, rank, workers, n_anno, lo, hi)
+    cpu = {"value": units / dt, "unit": UNIT, "cores": workers, "kind": "port",
+           "sample": "%d random annotations of %d x %d of %d cells, fork pool of %d workers, %.1fs"
+                     % (rep["annotations_checked"], len(d["annoptr"]) - 1, hi - lo, N, workers, dt)}
+    return reduce_parity(rep, ws, dist, dev), cpu
+
+
+def sub_record(res, parity, cpu, peaks, peaks_kind, extra=None):
+    """A compact record of one extra workload (configs 3 / 4 / 5-shard, atlas)."""
+    st = res["st"]
+    P, N, K = res["P"], res["N"], res["K"]
+    ms_step = res["total_ms_max"] / res["steps"]
+    sm_mhz = (res.get("clocks") or {}).get("sm_mhz")
+    roof = roofline_of(st, st["ms_contract"], float(np.mean(res["step_ms"])), 2.0 * (NITER + 1) * K * P * N, peaks, peaks_kind,
+                       sm_mhz, res["name"], st["contract_bytes"], st["contract_updates"])
+    rec = {"workload": res["name"], "peaks": P, "cells_per_gpu": N, "annotations": K, "nnz_per_gpu": res["nnz"],
+           "value": res["value"], "unit": UNIT, "ms_per_step": ms_step, "steps": res["steps"], "warmup": res["warmup"],
+           "ms_each_step": [round(x, 2) for x in res["step_ms"]], "dtype": dtype_string(st),
+           "stages_ms": {"counts_layout": st["ms_counts_layout"], "anno_prep": st["ms_anno_prep"],
+                         "contract": st["ms_contract"], "finalize": st["ms_finalize"]},
+           "digit_planes": st["planes"], "gpu_launches": res["launches"], "roofline": roof, "parity": parity,
+           "cpu_baseline": cpu, "background": res["bg_kind"], "other_paths": res["other"], "clocks": res.get("clocks")}
+    if extra:
+        rec.update(extra)
+    return rec
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from chromvar_b200 import _lib, distributed as cvd
+
+    rank, ws, local = cvd.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    gloo = dist.new_group(backend="gloo") if ws > 1 else None       # host-side barriers that keep the GPUs free
+    eng = _lib.Handle(local, seed=20173)
+    eng.set_option("path", args.path)
+    eng.set_option("dense_cta_pair", args.pair)
+    eng.set_option("dense_fp4", args.fp4)
+    eng.set_option("dense_lockstep", args.lockstep)
+    eng.set_option("host_narrow", args.host_narrow)
+    eng.set_option("tail_chunk", args.tail_chunk)
+    if args.chunk:
+        eng.set_option("cell_chunk", args.chunk)
+    if args.band:
+        eng.set_option("dense_band", args.band)
+    if args.debug_no_tma:
+        eng.set_option("debug_no_tma", args.debug_no_tma)
+    peaks, peaks_kind = peaks_json()
+    d, name = make_workload(rank, args.cells, args.quick, args.workload, gen=args.gen, device="cuda:%d" % local)
+    P, N = d["counts"].shape
+    K = len(d["annoptr"]) - 1
+
+    main = run_workload(torch, dist, eng, dev, rank, ws, d, name, args, args.steps, args.warmup, with_e2e=True,
+                        gloo_group=gloo)
+    st = main["st"]
+
+    # ---- the R call path on all GPUs of this node from ONE process (cv_multi), rank 0 only -----------
+    single = None
+    if ws > 1 and not args.no_single_process:
+        dist.barrier(group=gloo)
+        if rank == 0:
+            try:
+                single = single_process_leg(torch, d, main, ws, args)
+            except Exception as ex:                      # reported, never fatal for the main line
+                single = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            log("[bench] single-process leg: %s" % {k: v for k, v in (single or {}).items() if k != "ms_each_step"})
+        dist.barrier(group=gloo)
+
+    # ---- parity + CPU baseline of the main workload (changes the resident counts: after the timing) ---
+    parity = cpu = None
+    if not args.no_cpu_baseline:
+        n_anno = 2 * max(1, (os.cpu_count() or 1) // ws) if main["nnz"] < 1e8 else max(4, (os.cpu_count() or 1) // ws)
+        parity, cpu = check_workload_parity(torch, dist, eng, dev, rank, ws, d, main, args, n_anno,
+                                            full_cells=main["nnz"] < 1e8)
+        log("[bench] rank %d parity of the timed e2e results vs the CPU restatement: %s" % (rank, parity))
+    del main["out"]
+
+    # ---- other BASELINE configurations, driver-visible (N = 1: configs 3, 4, 5-shard; N > 1: the atlas) --
+    subs = {}
+    if not args.quick and args.workload is None and not args.no_sub_workloads:
+        del d
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        names = ["cfg3_kmers", "cfg4_bulk", "cfg5_atlas_shard"] if ws == 1 else ["cfg5_atlas_shard"]
+        for wname in names:
+            try:
+                t_sub = time.time()
+                dd, _ = make_workload(rank, 0, False, wname, gen="auto", device="cuda:%d" % local)
+                r = run_workload(torch, dist, eng, dev, rank, ws, dd, wname, args, args.sub_steps, 1, with_e2e=False,
+                                 gloo_group=gloo, bg_from="gpu")
+                extra = {}
+                if ws > 1:
+                    # the same shard on rank 0 alone (the other GPUs idle): atlas speed-up on THIS box
+                    dist.barrier(group=gloo)
+                    if rank == 0:
+                        tm = Timed(torch, eng, dev)
+                        solo = tm.run(lambda: eng.deviations_compute_async(rebuild_counts_layout=True), args.sub_steps)
+                        solo_value = r["K"] * r["N"] * args.sub_steps / (float(np.sum(solo)) * 1e-3)
+                        extra = {"one_gpu_shard_value_same_box": solo_value, "one_gpu_shard_ms_each_step": [round(x, 2) for x in solo],
+                                 "speedup_vs_one_gpu_shard": r["value"] / solo_value, "cells_total": r["N"] * ws,
+                                 "scaling": "weak: one config-5 shard (125k cells) per GPU, %d GPUs = %d cells" % (ws, r["N"] * ws)}
+                    dist.barrier(group=gloo)
+                par, cpu_s = (None, None)
+                if not args.no_cpu_baseline:
+                    par, cpu_s = check_workload_parity(torch, dist, eng, dev, rank, ws, dd, r, args,
+                                                       n_anno=max(4, min(8, (os.cpu_count() or 1) // ws)), full_cells=wname == "cfg4_bulk")
+                key = {"cfg3_kmers": "cfg3", "cfg4_bulk": "cfg4", "cfg5_atlas_shard": "cfg5_shard" if ws == 1 else "atlas"}[wname]
+                if rank == 0:
+                    subs[key] = sub_record(r, par, cpu_s, peaks, peaks_kind, extra)
+                    subs[key]["wall_s_incl_generation"] = round(time.time() - t_sub, 1)
+                    log("[bench] %s: %.3g z/s, %.1f ms/step, parity %s" % (key, r["value"], r["total_ms_max"] / r["steps"], par))
+                del dd, r
+                gc.collect()
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                if rank == 0:
+                    subs[wname] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+                log("[bench] rank %d: sub-workload %s failed: %s" % (rank, wname, ex))
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel -----------------------------------------------------------
-    peaks, peaks_kind = peaks_json()
-    c_ms = float(np.mean(contract_ms))
-    share = c_ms / (total_ms / args.steps)
-    if path == 1:
-        # dense tcgen05 path: algorithmic ops = 2 (B+1) K P N, int8 peak = 2 x the
-        # measured bf16 figure (sustained: the kernel runs inside a multi-step loop)
-        flops = 2.0 * (NITER + 1) * K * P * N
-        fp4 = st.get("operand_bits") == 4
-        # e2m1 operands (kind::mxf4) retire twice the MACs per cycle of u8: peak = 4 x bf16
-        mult = 4.0 if fp4 else 2.0
-        peak = mult * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        achieved = flops / (c_ms * 1e-3) / 1e12
-        kname = "k_dense_contract_fp4" if fp4 else ("k_dense_contract_pair" if tile_cells == 256 else "k_dense_contract")
-        roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(kname, name),
-                "peak_kind": peaks_kind + (" (4 x bf16 sustained = e2m1 dense)" if fp4 else " (2 x bf16 sustained = int8 dense)"),
-                "peak_burst": mult * peaks["bf16_tflops"], "peak_nominal": 9000.0 if fp4 else 4500.0,
-                "ms_per_launch": c_ms / max(gemm_launches, 1), "launches_per_step": int(gemm_launches),
-                "algorithmic_ops_per_launch": flops / max(gemm_launches, 1),
-                "padded_ops_per_step": padded_flops, "share_of_step": share,
-                "operand_bits": st.get("operand_bits"), "overflow_columns_per_step": st.get("overflow_columns")}
-    else:
-        achieved = bytes_alg / (c_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_contract", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                "peak_kind": peaks_kind, "ms_per_launch": c_ms, "algorithmic_bytes_per_launch": int(bytes_alg),
-                "updates_per_launch": int(upd), "share_of_step": share}
-
-    # ---- CPU baseline beside it (N=1 only): bounded sample of the same workload ---------------
-    cpu = parity = None
-    if ws == 1 and not args.no_cpu_baseline:
-        workers = os.cpu_count() or 1
-        S = max(1, min(K, (2 if nnz < 1e8 else 1) * workers))
-        dt, (ref_z, ref_dev) = cpu_reference_step(d, bg, e, list(range(S)), workers, want_results=True)
-        cpu = {"value": S * N / dt, "unit": UNIT, "cores": workers, "kind": "port",
-               "sample": "%d of %d annotations x all %d cells, fork pool of %d workers, %.1fs" % (S, K, N, workers, dt)}
-        parity = parity_report(out["dev"][:S], out["z"][:S], ref_dev, ref_z)
-        log("[bench] parity of the timed e2e results vs the CPU restatement: %s" % parity)
-
+    sm_mhz = (main["clocks"] or {}).get("sm_mhz")
+    c_ms = st["ms_contract"]
+    roof = roofline_of(st, c_ms, float(np.mean(main["step_ms"])), 2.0 * (NITER + 1) * K * P * N, peaks, peaks_kind, sm_mhz,
+                       name, st["contract_bytes"], st["contract_updates"])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
-        "dtype": ("%s, %s epilogue" % ("e2m1 x e2m1 -> f32 holding exact integers (tcgen05 kind::mxf4)" if st.get("operand_bits") == 4
-                                       else "u8 x u8 -> s32 (tcgen05 kind::i8)",
-                                       "u64 fixed-point / f32 / f64" if st.get("epilogue") == 32 else "f64"))
-                 if path == 1 else "int32 sums, f64 epilogue",
-        "data": "synthetic",
-        "config": {"workload": name, "peaks": int(P), "cells_per_gpu": int(N), "annotations": int(K),
-                   "niterations": NITER, "nnz_per_gpu": nnz, "nnz_annotations": int(d["annoptr"][-1]),
-                   "cells_total": int(N) * ws, "generator": d["cfg"].get("generator", "numpy (make_counts)"),
-                   "l2": "256 MB flush write between timed steps", "cell_tile": int(tile_cells),
-                   "step_call": ("cv_deviations_compute_async: K steps queued back to back, settled after the loop"
-                                 if use_async else "cv_deviations_compute: one checked call per step"),
-                   "path": ("dense_tcgen05_cta_pair" if tile_cells == 256 else "dense_tcgen05") if path == 1
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": ws, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["total_ms_max"] / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype_string(st), "data": "synthetic",
+        "config": main["config"],
+        "engine": {"cell_tile": int(st["cell_tile"]),
+                   "step_call": "cv_deviations_compute_async: K steps queued back to back, settled after the loop"
+                                + ("; per step an NCCL all-gather of the K x 4 variability partials + cv_variability_merge_device, "
+                                   "stream-ordered" if ws > 1 else ""),
+                   "path": ("dense_tcgen05_cta_pair" if st["cell_tile"] == 256 else "dense_tcgen05") if st["path"] == 1
                    else "row_gather_spmm"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "host_input_bytes_per_step": int(host_in),
-                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
-                "ms_per_step_median": float(np.median(e2e_each)),
-                "call": "cv_deviations_csc (chunked H2D / kernels / D2H overlapped)",
-                "gemm_kernel": ("k_dense_contract_fp4" if e2e_stats.get("operand_bits") == 4 else "k_dense_contract_pair") if e2e_stats["cell_tile"] == 256 else
-                ("k_dense_contract" if e2e_stats["path"] == 1 else "k_contract"),
-                "cell_chunks": int(e2e_stats["n_cell_tiles"]), "ms_each_step": [round(t, 2) for t in e2e_each],
-                "ms_inside_library": [round(t, 2) for t in e2e_lib],
-                "device_ms": {k: round(float(e2e_stats[k]), 3) for k in
-                              ("ms_counts_layout", "ms_anno_prep", "ms_contract", "ms_finalize")}},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "e2e": main["e2e"],
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
         "roofline": roof,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu if ws == 1 else None,
         "parity": parity,
-        "stages_ms": dict(zip(["counts_layout", "anno_prep", "contract", "finalize"],
-                              (stage_acc / args.steps).round(4).tolist())),
-        "other_paths": {"getBackgroundPeaks_ms_device": bg_ms_dev, "getBackgroundPeaks_ms_wall": 1e3 * t_bg,
-                        "sampled_indices_per_s": P * NITER / max(t_bg, 1e-9),
-                        "computeExpectations_ms_wall": 1e3 * t_exp,
-                        "backgroundPeaksAlternative_window10_ms_device": knn_ms_dev,
-                        "backgroundPeaksAlternative_window10_ms_wall": 1e3 * t_knn},
+        "stages_ms": {"counts_layout": st["ms_counts_layout"], "anno_prep": st["ms_anno_prep"],
+                      "contract": st["ms_contract"], "finalize": st["ms_finalize"]},
+        "ms_each_step": [round(x, 2) for x in main["step_ms"]],
+        "other_paths": main["other"],
+        "workloads": subs or None,
+        "single_process": single,
     }
+    if ws > 1 and "variability_merged_on_device" in main:
+        line["variability_merged_on_device"] = main["variability_merged_on_device"]
     emit_json(line)
+
+
+def single_process_leg(torch, d, main, ws, args):
+    """compute_deviations_core through cv_multi: ONE process (this one) drives all `ws` GPUs of the
+    node -- the call the R shim makes (cvb_deviations_csc).  The counts are `ws` column blocks (this
+    rank's matrix repeated: the same per-GPU work as the multi-process line), host memory pageable."""
+    from chromvar_b200 import _lib
+    C = d["counts"]
+    P, N = C.shape
+    K = len(d["annoptr"]) - 1
+    m = _lib.MultiHandle(list(range(ws)), seed=20173)
+    try:
+        for key, v in (("path", args.path), ("dense_cta_pair", args.pair), ("dense_fp4", args.fp4), ("tail_chunk", args.tail_chunk)):
+            m.set_option(key, v)
+        blocks = m._blocks([C] * ws)
+        out = dict(dev=np.empty((K, N * ws), np.float64, order="F"), z=np.empty((K, N * ws), np.float64, order="F"),
+                   matches=np.empty(K), overlap=np.empty(K), variability=np.empty(K))
+        ptr, idx = d["annoptr"], d["annoidx"].astype(np.int32)
+        bg, e = main["bg"], main["e"]
+
+        def one():
+            m.deviations_csc(None, ptr, idx, bg, e, index_base=1, out=out, blocks=blocks)
+        one()
+        one()
+        n = max(1, min(args.steps, 10))
+        each = []
+        t0 = time.perf_counter()
+        for _ in range(n):
+            t1 = time.perf_counter()
+            one()
+            each.append(1e3 * (time.perf_counter() - t1))
+        dt = time.perf_counter() - t0
+        same = bool(main["out"] is not None and np.array_equal(out["z"][:, :N], main["out"]["z"], equal_nan=True))
+        reps = bool(all(np.array_equal(out["z"][:, b * N:(b + 1) * N], out["z"][:, :N], equal_nan=True) for b in range(1, ws)))
+        return {"call": "cv_multi_deviations_csc: one process, one host thread per GPU inside the library, counts as %d column "
+                        "blocks, pageable host memory, reductions over peer memory" % ws,
+                "n_gpus": ws, "peer_access": m.peer_access(), "value": K * N * ws * n / dt, "unit": UNIT,
+                "ms_per_step": 1e3 * dt / n, "ms_per_step_median": float(np.median(each)), "steps": n,
+                "ms_each_step": [round(t, 2) for t in each], "shards": [int(x) for x in m.shards()],
+                "z_equals_multi_process_result_bitwise": same, "z_equal_across_shards_bitwise": reps}
+    finally:
+        m.close()
 
 
 _REAL_STDOUT = None
@@ -623,11 +873,12 @@ def main():
     ap.add_argument("--band", type=int, default=0, help="dense path: groups per raster band (experiment)")
     ap.add_argument("--debug-no-tma", type=int, default=0, help="experiment: GEMM without operand loads (1) / MMA issue patterns (2-5); NOT a bench value")
     ap.add_argument("--pair", type=int, default=-1, help="dense GEMM kernel: 1 CTA pair (cta_group::2), 0 single CTA, -1 library default (by context)")
-    ap.add_argument("--async-steps", type=int, default=1,
-                    help="1 (default): one rank enqueues the timed steps back to back (cv_deviations_compute_async), several ranks run one checked call + host-side variability merge per step; 2: several ranks queue their steps too (all-gather on the device); 0: one checked call per step")
     ap.add_argument("--clock-sampler", default="thread", choices=["thread", "inline", "off"],
                     help="SM clock / throttle reasons through NVML: polled by a thread every 100 ms, or by the main thread between steps")
     ap.add_argument("--tail-chunk", type=int, default=1, help="e2e call: 1 (default) ends with a short fourth cell chunk, 0: three chunks")
+    ap.add_argument("--sub-steps", type=int, default=3, help="timed steps of each extra workload (configs 3 / 4 / 5-shard, atlas)")
+    ap.add_argument("--no-sub-workloads", action="store_true", help="only the main workload (config 2)")
+    ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the one-process cv_multi leg")
     ap.add_argument("--pin-cores", type=int, default=0,
                     help="multi-GPU experiment: 1 keeps each rank on its own block of host cores (cores / ranks, by "
                          "local rank); measured on 8x B200 / 32 cores: no gain for the e2e call, device-timed step slower")

@@ -221,6 +221,42 @@ def make_config(name, seed_offset=0, device=None, **override):
     return dict(counts=counts, bias=bias, annoptr=annoptr, annoidx=annoidx, cfg=cfg)
 
 
+def background_matrix(counts, bias, niterations=50, w=0.1, bs=50, seed=20173):
+    """A GC-bias x intensity matched background matrix (P x niterations, 1-based, column-major int32)
+    as INPUT for both bench arms: numpy statement of the generative form of getBackgroundPeaks
+    (whiten (log10 fragments, bias) by the Cholesky factor of their covariance, bs x bs grid, nearest
+    grid point, destination bin ~ dnorm(distance, 0, w) over occupied bins, uniform peak inside it).
+    The timed GPU sampler (cv_background_peaks) and its parity tests are separate; this exists so the
+    CPU arm and the GPU arm of bench.py are fed the identical matrix without a GPU."""
+    rng = np.random.default_rng(seed)
+    fpp = np.asarray(counts.sum(axis=1)).ravel().astype(np.float64)
+    P = fpp.size
+    X = np.column_stack([np.log10(fpp), np.asarray(bias, np.float64)])
+    L = np.linalg.cholesky(np.cov(X.T))
+    T = np.linalg.solve(L, X.T).T
+    lo, hi = T.min(axis=0), T.max(axis=0)
+    g1, g2 = np.linspace(lo[0], hi[0], bs), np.linspace(lo[1], hi[1], bs)
+    b1 = np.clip(np.rint((T[:, 0] - lo[0]) / (g1[1] - g1[0])), 0, bs - 1).astype(np.int64)
+    b2 = np.clip(np.rint((T[:, 1] - lo[1]) / (g2[1] - g2[0])), 0, bs - 1).astype(np.int64)
+    memb = b1 * bs + b2
+    order = np.argsort(memb, kind="stable")
+    dens = np.bincount(memb, minlength=bs * bs)
+    start = np.concatenate([[0], np.cumsum(dens)])
+    occ = np.nonzero(dens)[0]
+    xy = np.column_stack([g1[occ // bs], g2[occ % bs]])
+    out = np.empty((P, niterations), np.int32, order="F")
+    for b in occ:
+        src = order[start[b]:start[b + 1]]
+        d = np.sqrt(((xy - np.array([g1[b // bs], g2[b % bs]])) ** 2).sum(axis=1))
+        pr = np.exp(-0.5 * (d / w) ** 2)
+        cdf = np.cumsum(pr / pr.sum())
+        cdf[-1] = 1.0
+        dest = occ[np.searchsorted(cdf, rng.random((src.size, niterations)), side="right").clip(max=occ.size - 1)]
+        within = (rng.random((src.size, niterations)) * dens[dest]).astype(np.int64)
+        out[src, :] = order[start[dest] + np.minimum(within, dens[dest] - 1)] + 1
+    return out
+
+
 def random_background(P, B, rng):
     """A stand-in background matrix (1-based, P x B) for tests that only need *some* valid bg."""
     return np.asfortranarray(rng.integers(1, P + 1, size=(P, B)).astype(np.int32))
