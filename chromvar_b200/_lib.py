@@ -30,7 +30,7 @@ EXPORTS = [
     "cv_deviations_download",
     "cv_variability_partials_device", "cv_merge_variability", "cv_row_sds", "cv_row_sds_perm",
     "cv_prob_sample_replace", "cv_bg_sample_helper", "cv_euc_dist", "cv_stats", "cv_e2m1_terms", "cv_host_narrow",
-    "cv_variability_merge_device",
+    "cv_variability_merge_device", "cv_permuted_counts", "cv_permuted_counts_fetch", "cv_deviations_covariability",
     "cv_create_multi", "cv_destroy_multi", "cv_multi_last_error", "cv_multi_n_devices", "cv_multi_peer_access",
     "cv_multi_handle", "cv_multi_set_seed", "cv_multi_set_option", "cv_multi_stats", "cv_multi_set_counts",
     "cv_multi_shards", "cv_multi_fragments", "cv_multi_expectations", "cv_multi_background_peaks",
@@ -117,6 +117,9 @@ def load(build_if_missing=True):
         "cv_stats": (i32, [vp, C.POINTER(StageStats)]),
         "cv_host_narrow": (i32, [vp, i32, i64, vp, i32]),
         "cv_variability_merge_device": (i32, [vp, vp, i32]),
+        "cv_permuted_counts": (i32, [vp, vp, dbl, i32, vp, C.POINTER(i64)]),
+        "cv_permuted_counts_fetch": (i32, [vp, i64, vp, vp]),
+        "cv_deviations_covariability": (i32, [vp, i64, i64, vp, vp]),
         "cv_create_multi": (i32, [vp, i32, u64, C.POINTER(vp)]),
         "cv_destroy_multi": (None, [vp]),
         "cv_multi_last_error": (C.c_char_p, [vp]),
@@ -445,6 +448,33 @@ class Handle:
         n, d = x.shape
         out = np.empty((n, n), np.float64, order="F")
         self._check(self.lib.cv_euc_dist(self._h, n, d, _ptr(x), _ptr(out)))
+        return out
+
+    def permuted_counts(self, bias, w=0.1, bs=50):
+        """cv_permuted_counts: one permuted assay of the resident counts (getPermutedData), gathered on
+        the device; returns (colptr int64[N+1], rowidx int32, x float64) of the CSC result."""
+        bias = _carr(bias, np.float64)
+        if bias.shape[0] != self.P:
+            raise ChromVARError(CV_ERR_INVALID, "length(bias) must equal nrow(counts)")
+        colptr = np.empty(self.N + 1, np.int64)
+        nnz = C.c_int64()
+        self._check(self.lib.cv_permuted_counts(self._h, _ptr(bias), float(w), int(bs), _ptr(colptr), C.byref(nnz)))
+        rowidx, x = np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
+        self._check(self.lib.cv_permuted_counts_fetch(self._h, nnz.value, _ptr(rowidx), _ptr(x)))
+        return colptr, rowidx, x
+
+    def deviations_covariability(self, z=None):
+        """cv_deviations_covariability: K x K normalised covariance of the rows of z (host matrix), or of
+        the z still resident from the last deviations call (z = None)."""
+        if z is None:
+            K = self.K
+            out = np.empty((K, K), np.float64, order="F")
+            self._check(self.lib.cv_deviations_covariability(self._h, 0, 0, None, _ptr(out)))
+            return out
+        z = np.asfortranarray(np.asarray(z, np.float64))
+        K, N = z.shape
+        out = np.empty((K, K), np.float64, order="F")
+        self._check(self.lib.cv_deviations_covariability(self._h, K, N, _ptr(z), _ptr(out)))
         return out
 
     def set_seed(self, seed):

@@ -286,16 +286,12 @@ k_bin_cdf(const double* __restrict__ binp, GridParams g, double w, int nb,
   }
 }
 
-// ---- K4: the draws ----------------------------------------------------------------------------------
-// out: P x niter column-major, 1-based.  HBM-bound on the 4*P*niter bytes written.
-__global__ void __launch_bounds__(256)
-k_bg_sample(const int32_t* __restrict__ memb0, int P, int nb, const double* __restrict__ cdf,
-            const uint32_t* __restrict__ density, const uint32_t* __restrict__ start,
-            const int32_t* __restrict__ sorted, int niter, uint32_t seed_lo, uint32_t seed_hi,
-            int32_t* __restrict__ out) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)P * niter) return;
-  int p = (int)(idx % P), it = (int)(idx / P);
+// one draw: background peak (0-based) of peak p in iteration it -- Philox counter (p, it), CDF search over
+// the destination bins of p's bin, uniform peak inside the bin
+__device__ __forceinline__ int bg_draw(int p, int it, const int32_t* __restrict__ memb0, int nb,
+                                       const double* __restrict__ cdf, const uint32_t* __restrict__ density,
+                                       const uint32_t* __restrict__ start, const int32_t* __restrict__ sorted,
+                                       uint32_t seed_lo, uint32_t seed_hi) {
   Philox4 r = philox4x32_10((uint32_t)p, (uint32_t)it, CV_STREAM_BACKGROUND, 0u, seed_lo, seed_hi);
   double u1 = u01_53(r.v[0], r.v[1]), u2 = u01_53(r.v[2], r.v[3]);
   const double* row = cdf + (int64_t)memb0[p] * nb;
@@ -308,7 +304,20 @@ k_bg_sample(const int32_t* __restrict__ memb0, int P, int nb, const double* __re
   while (cnt == 0u && lo > 0) cnt = density[--lo];      // cannot happen with the clamped CDF; cheap to keep safe
   uint32_t within = (uint32_t)(u2 * (double)cnt);
   if (within >= cnt) within = cnt ? cnt - 1 : 0u;
-  out[idx] = sorted[start[lo] + within] + 1;
+  return sorted[start[lo] + within];
+}
+
+// ---- K4: the draws ----------------------------------------------------------------------------------
+// out: P x niter column-major, 1-based.  HBM-bound on the 4*P*niter bytes written.
+__global__ void __launch_bounds__(256)
+k_bg_sample(const int32_t* __restrict__ memb0, int P, int nb, const double* __restrict__ cdf,
+            const uint32_t* __restrict__ density, const uint32_t* __restrict__ start,
+            const int32_t* __restrict__ sorted, int niter, uint32_t seed_lo, uint32_t seed_hi,
+            int32_t* __restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)P * niter) return;
+  int p = (int)(idx % P), it = (int)(idx / P);
+  out[idx] = bg_draw(p, it, memb0, nb, cdf, density, start, sorted, seed_lo, seed_hi) + 1;
 }
 
 __global__ void k_u32_to_f64(const uint32_t* __restrict__ in, double* __restrict__ out, int n) {
@@ -480,5 +489,130 @@ extern "C" int cv_background_peaks(cv_handle* h, const double* bias, int niter, 
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   if (out_membership)
     for (int64_t i = 0; i < P; ++i) out_membership[i] += 1;   // 1-based like nn.idx
+  return CV_OK;
+}
+
+// =========================================================================================================
+// getPermutedData (R/background_peaks.R:178-203): a permuted assay = reorder_columns(counts, bg) with
+// bg = getBackgroundPeaks(object, niterations = ncol(object)): column c of the result is
+// counts[bg[, c], c].  The P x N index matrix never exists: row r of column c draws its source peak
+// on the fly (the sampler's counter is (peak, iteration = c), so this IS the matrix getBackgroundPeaks
+// would return), looks the source up in a dense copy of counts column c and keeps the nonzeros.
+// Two passes over the draws (count, then fill in row order); one CTA per column at a time.
+// =========================================================================================================
+#define PERM_THREADS 512
+struct PermTables {
+  const int32_t* memb0; const double* cdf; const uint32_t* density; const uint32_t* start; const int32_t* sorted;
+  int nb; uint32_t seed_lo, seed_hi;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(PERM_THREADS)
+k_perm_gather(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx, const uint32_t* __restrict__ val,
+              int P, int N, PermTables t, uint32_t* __restrict__ dense /*[gridDim.x][P], zero*/,
+              uint32_t* __restrict__ colcnt, const uint32_t* __restrict__ outptr, int32_t* __restrict__ out_row,
+              double* __restrict__ out_x) {
+  __shared__ uint32_t s_warp[PERM_THREADS / 32];
+  __shared__ uint32_t s_base;
+  uint32_t* d = dense + (int64_t)blockIdx.x * P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = blockIdx.x; c < N; c += gridDim.x) {
+    const int64_t e0 = colptr[c], e1 = colptr[c + 1];
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += PERM_THREADS) d[rowidx[e]] = val[e];
+    if (threadIdx.x == 0) s_base = FILL ? outptr[c] : 0u;
+    __syncthreads();
+    uint32_t total = 0;
+    for (int r0 = 0; r0 < P; r0 += PERM_THREADS) {
+      const int r = r0 + threadIdx.x;
+      uint32_t v = 0u;
+      if (r < P) v = d[bg_draw(r, c, t.memb0, t.nb, t.cdf, t.density, t.start, t.sorted, t.seed_lo, t.seed_hi)];
+      const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+      if (!FILL) {
+        if (lane == 0) total += __popc(m);
+      } else {
+        // ordered compaction of this tile of rows: warp counts -> offsets -> writes
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+        for (int w = 0; w < PERM_THREADS / 32; ++w) {
+          const uint32_t n = s_warp[w];
+          if (w < warp) before += n;
+          all += n;
+        }
+        if (v != 0u) {
+          const uint32_t pos = s_base + before + __popc(m & ((1u << lane) - 1u));
+          out_row[pos] = r;
+          out_x[pos] = (double)v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += all;
+      }
+    }
+    if (!FILL) {
+      if (lane == 0) s_warp[warp] = total;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < PERM_THREADS / 32; ++w) s += s_warp[w];
+        colcnt[c] = s;
+      }
+    }
+    __syncthreads();
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += PERM_THREADS) d[rowidx[e]] = 0u;     // leave the scratch zeroed
+    __syncthreads();
+  }
+}
+
+__global__ void k_u32_prefix_to_i64(const uint32_t* __restrict__ in, int64_t* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int64_t)in[i];
+}
+
+// buffers: bk[13] dense scratch, bk[14] column counts / offsets (u32[N+1] x 2), bk[15] colptr i64; results in tmp1 / tmp2
+extern "C" int cv_permuted_counts(cv_handle* h, const double* bias, double w, int bs, int64_t* out_colptr,
+                                  int64_t* out_nnz) {
+  if (!h || !out_colptr || !out_nnz) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  // the sampler's tables for this (counts, bias, w, bs): whitening, bins, CDF rows (one iteration drawn on the way)
+  CV_TRY(cv_background_peaks(h, bias, 1, w, bs, nullptr, nullptr, nullptr, nullptr, nullptr));
+  const int64_t P = h->P, N = h->N;
+  const int grid = (int)std::min<int64_t>(N, (int64_t)h->num_sms * 2);
+  CV_TRY(cv_ensure(h, h->bk[13], (size_t)grid * P * 4));
+  CV_TRY(cv_ensure(h, h->bk[14], (size_t)(N + 1) * 4 * 2));
+  CV_TRY(cv_ensure(h, h->bk[15], (size_t)(N + 1) * 8));
+  uint32_t* cnt = h->bk[14].as<uint32_t>();
+  uint32_t* off = cnt + (N + 1);
+  CV_CUDA(h, cudaMemsetAsync(h->bk[13].p, 0, (size_t)grid * P * 4, h->stream));
+  CV_CUDA(h, cudaMemsetAsync(cnt, 0, (size_t)(N + 1) * 4, h->stream));
+  PermTables t;
+  t.memb0 = h->bk[2].as<int32_t>(); t.cdf = h->bk[9].as<double>(); t.density = h->bk[6].as<uint32_t>();
+  t.start = h->bk[7].as<uint32_t>(); t.sorted = h->bk[8].as<int32_t>(); t.nb = bs * bs;
+  t.seed_lo = (uint32_t)(h->seed & 0xffffffffu); t.seed_hi = (uint32_t)(h->seed >> 32);
+  CV_LAUNCH(h, k_perm_gather<false>, grid, PERM_THREADS, 0, h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(),
+            h->val.as<uint32_t>(), (int)P, (int)N, t, h->bk[13].as<uint32_t>(), cnt, nullptr, nullptr, nullptr);
+  CV_TRY(cv_exclusive_scan_u32_async(h, cnt, off, N));
+  CV_LAUNCH(h, k_u32_prefix_to_i64, (unsigned)((N + 1 + 255) / 256), 256, 0, off, h->bk[15].as<int64_t>(), (int)(N + 1));
+  CV_CUDA(h, cudaMemcpyAsync(out_colptr, h->bk[15].p, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int64_t nnz = out_colptr[N];
+  if (nnz >= (1ll << 32)) CV_FAIL(h, CV_ERR_UNSUPPORTED, "permuted counts hold >= 2^32 nonzeros");
+  *out_nnz = nnz;
+  CV_TRY(cv_ensure(h, h->tmp1, (size_t)std::max<int64_t>(nnz, 1) * 4));
+  CV_TRY(cv_ensure(h, h->tmp2, (size_t)std::max<int64_t>(nnz, 1) * 8));
+  CV_LAUNCH(h, k_perm_gather<true>, grid, PERM_THREADS, 0, h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(),
+            h->val.as<uint32_t>(), (int)P, (int)N, t, h->bk[13].as<uint32_t>(), cnt, off, h->tmp1.as<int32_t>(),
+            h->tmp2.as<double>());
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CV_OK;
+}
+
+extern "C" int cv_permuted_counts_fetch(cv_handle* h, int64_t nnz, int32_t* out_rowidx, double* out_x) {
+  if (!h || nnz < 0) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (h->tmp1.cap < (size_t)nnz * 4 || h->tmp2.cap < (size_t)nnz * 8) CV_FAIL(h, CV_ERR_STATE, "no permuted counts: call cv_permuted_counts first");
+  if (out_rowidx && nnz) CV_CUDA(h, cudaMemcpyAsync(out_rowidx, h->tmp1.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_x && nnz) CV_CUDA(h, cudaMemcpyAsync(out_x, h->tmp2.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
   return CV_OK;
 }

@@ -224,3 +224,111 @@ extern "C" int cv_euc_dist(cv_handle* h, int64_t n, int64_t d, const double* x, 
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
   return CV_OK;
 }
+
+// =========================================================================================================
+// deviationsCovariability (R/kmers.R:51-57): covs = cov(t(z)) (pairs of annotations over the cells,
+// two-pass, n - 1), then row i divided by row_sds(z)[i]^2.  NaN / NA anywhere in rows i or j makes the
+// pair NaN, as stats::cov(use = "everything") does.  z stays in HBM: [K][N] row-major as the deviation
+// kernels leave it, or a K x N column-major host matrix uploaded first.  fp64 SYRK, 64 x 64 output tile
+// per CTA, 4 x 4 per thread, the N axis staged through shared memory 16 cells at a time.
+// =========================================================================================================
+#define COV_TILE 64
+#define COV_KC 16
+
+__global__ void __launch_bounds__(256)
+k_row_means(const double* __restrict__ z, int64_t K, int64_t N, int64_t ld_row, int64_t ld_col, double* __restrict__ mean) {
+  __shared__ double sh[256];
+  const int64_t k = blockIdx.x;
+  double s = 0.0;
+  for (int64_t c = threadIdx.x; c < N; c += 256) s += z[k * ld_row + c * ld_col];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mean[k] = sh[0] / (double)N;
+}
+
+__global__ void __launch_bounds__(256)
+k_cov_tiles(const double* __restrict__ z, int64_t K, int64_t N, int64_t ld_row, int64_t ld_col,
+            const double* __restrict__ mean, double* __restrict__ cov /* K x K */) {
+  __shared__ double sa[COV_KC][COV_TILE + 1], sb[COV_KC][COV_TILE + 1];
+  const int64_t i0 = (int64_t)blockIdx.y * COV_TILE, j0 = (int64_t)blockIdx.x * COV_TILE;
+  if (j0 > i0) return;                                   // lower triangle; mirrored on the way out
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4] = {};
+  for (int64_t c0 = 0; c0 < N; c0 += COV_KC) {
+    for (int t = threadIdx.x; t < COV_TILE * COV_KC; t += 256) {
+      // row-major z: consecutive threads read consecutive cells of one row; column-major: consecutive rows
+      const int r = ld_col == 1 ? t / COV_KC : t % COV_TILE, cc = ld_col == 1 ? t % COV_KC : t / COV_TILE;
+      const int64_t c = c0 + cc;
+      const int64_t ia = i0 + r, jb = j0 + r;
+      sa[cc][r] = (ia < K && c < N) ? z[ia * ld_row + c * ld_col] - mean[ia] : 0.0;
+      sb[cc][r] = (jb < K && c < N) ? z[jb * ld_row + c * ld_col] - mean[jb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < COV_KC; ++cc) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = sa[cc][ty * 4 + u]; b[u] = sb[cc][tx * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+  const double inv = 1.0 / (double)(N - 1);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int64_t i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+      if (i < K && j < K) {
+        const double cv = acc[u][v] * inv;
+        cov[i + j * K] = cv;
+        cov[j + i * K] = cv;
+      }
+    }
+}
+
+// covs / matrix(vars^2, byrow = FALSE): entry (i, j) divided by var_i = covs[i, i]
+__global__ void k_cov_normalise(const double* __restrict__ cov, int64_t K, double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * K) return;
+  const int64_t i = idx % K;
+  out[idx] = cov[idx] / cov[i + i * K];
+}
+
+extern "C" int cv_deviations_covariability(cv_handle* h, int64_t K, int64_t N, const double* z, double* out) {
+  if (!h || !out) return CV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CV_TRY(cv_settle(h));
+  const double* dz;
+  int64_t ld_row, ld_col;
+  if (z) {
+    if (K < 1 || N < 2) CV_FAIL(h, CV_ERR_INVALID, "covariability needs K >= 1 annotations and N >= 2 cells");
+    CV_TRY(cv_ensure(h, h->tmp0, (size_t)K * N * 8));
+    CV_CUDA(h, cudaMemcpyAsync(h->tmp0.p, z, (size_t)K * N * 8, cudaMemcpyHostToDevice, h->stream));
+    dz = h->tmp0.as<double>(); ld_row = 1; ld_col = K;                  // K x N column-major
+  } else {
+    if (!h->have_results) CV_FAIL(h, CV_ERR_STATE, "no resident z: call cv_deviations first or pass z");
+    K = h->K; N = h->N;
+    if (N < 2) CV_FAIL(h, CV_ERR_INVALID, "covariability needs N >= 2 cells");
+    dz = h->z_rm.as<double>(); ld_row = N; ld_col = 1;                  // [K][N] row-major, resident
+  }
+  CV_TRY(cv_ensure(h, h->tmp1, (size_t)K * 8));
+  CV_TRY(cv_ensure(h, h->tmp2, (size_t)K * K * 8 * 2));
+  double* mean = h->tmp1.as<double>();
+  double* cov = h->tmp2.as<double>();
+  double* nrm = cov + K * K;
+  CV_LAUNCH(h, k_row_means, (unsigned)K, 256, 0, dz, K, N, ld_row, ld_col, mean);
+  const unsigned nt = (unsigned)((K + COV_TILE - 1) / COV_TILE);
+  CV_LAUNCH(h, k_cov_tiles, dim3(nt, nt), 256, 0, dz, K, N, ld_row, ld_col, mean, cov);
+  CV_LAUNCH(h, k_cov_normalise, (unsigned)((K * K + 255) / 256), 256, 0, cov, K, nrm);
+  CV_CUDA(h, cudaMemcpyAsync(out, nrm, (size_t)K * K * 8, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CV_OK;
+}

@@ -175,9 +175,9 @@ def deviationsCovariability(object):
     """R/kmers.R:51-57: cov(t(z)) with row i divided by var_i (row_sds on the GPU)."""
     if not isinstance(object, api.chromVARDeviations):
         raise TypeError('inherits(object, "chromVARDeviations") is not TRUE')
-    z = api.deviationScores(object)
-    v = api.get_engine().row_sds(z, False)
-    return np.cov(z) / (v ** 2)[:, None]
+    # the K x K covariance runs on the device (cv_deviations_covariability): z of a k-mer run is
+    # 2080 x 50 000, its covariance 4e11 multiply-adds
+    return api.get_engine().deviations_covariability(api.deviationScores(object))
 
 
 def _bg_for_perm(object, n, w, bs):
@@ -196,13 +196,22 @@ def getPermutedData(object, niterations=10, w=0.1, bs=50):
     counts[bg[, x], x] with bg = getBackgroundPeaks(object, niterations = ncol(object))."""
     if not isinstance(object, api.SummarizedExperiment):
         raise TypeError("object must be a SummarizedExperiment")
-    C = sp.csc_matrix(api.counts_check(object).assays["counts"])
+    mat = api.counts_check(object).assays["counts"]
+    bias = object.rowData.get("bias")
+    if bias is None:
+        raise ValueError("bias is missing (rowData(object)$bias)")
+    eng = api._load_counts(mat)
     assays = dict(object.assays)
     for it in range(int(niterations)):
-        api.get_engine().set_seed(api._next_sampler_seed())      # a fresh draw per iteration (:184-186)
-        bg = _bg_for_perm(object, C.shape[1], w, bs)                       # P x N
-        cols = [C[np.asarray(bg[:, x]).astype(np.int64) - 1, x] for x in range(C.shape[1])]
-        assays["perm_%d" % (it + 1)] = sp.hstack(cols).tocsc()
+        eng.set_seed(api._next_sampler_seed())                   # a fresh draw per iteration (:184-186)
+        # draws and row gather on the device (cv_permuted_counts): the P x N index matrix never exists
+        try:
+            colptr, rowidx, x = eng.permuted_counts(np.asarray(bias, np.float64), float(w), int(bs))
+        except ChromVARError as e:
+            raise ValueError(str(e)) from e
+        M = sp.csc_matrix((x, rowidx, colptr), shape=mat.shape)
+        M.has_sorted_indices = True
+        assays["perm_%d" % (it + 1)] = M
     return api.SummarizedExperiment(assays, rowData=object.rowData, colData=object.colData,
                                     rownames=object.rownames, colnames=object.colnames)
 

@@ -271,6 +271,21 @@ int cv_bg_sample_helper(cv_handle* h, int64_t P, const int32_t* bin_membership, 
 /* euc_dist(x)  src/utils.cpp:107-117.  x: n x d col-major -> out n x n. */
 int cv_euc_dist(cv_handle* h, int64_t n, int64_t d, const double* x, double* out);
 
+/* ---- next rows of SURVEY 8f on the device --------------------------------------------------- */
+/* getPermutedData (R/background_peaks.R:178-203): ONE permuted assay of the resident counts =
+ * reorder_columns(counts, getBackgroundPeaks(object, niterations = ncol(object))), i.e. column c
+ * of the result is counts[bg[, c], c].  The P x N index matrix is never materialised: the draws
+ * (same Philox counters as cv_background_peaks: (peak, iteration = c)) happen inside the gather.
+ * Two calls because the result's size is only known afterwards: cv_permuted_counts fills
+ * out_colptr (N + 1, 0-based offsets) and *out_nnz; cv_permuted_counts_fetch copies the row indices
+ * (0-based, increasing within a column) and values of that result. */
+int cv_permuted_counts(cv_handle* h, const double* bias, double w, int bs, int64_t* out_colptr, int64_t* out_nnz);
+int cv_permuted_counts_fetch(cv_handle* h, int64_t nnz, int32_t* out_rowidx, double* out_x);
+/* deviationsCovariability (R/kmers.R:51-57): cov(t(z)) with row i divided by row_sds(z)[i]^2.
+ * z: K x N column-major host matrix, or NULL = the z of the last deviations call on this handle,
+ * still in HBM (K, N then come from the handle).  out: K x K column-major. */
+int cv_deviations_covariability(cv_handle* h, int64_t K, int64_t N, const double* z, double* out);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct cv_stage_stats {
   double ms_counts_layout;   /* row/col sums + cell-tiled row layout build (K1) */

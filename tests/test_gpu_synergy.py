@@ -94,9 +94,19 @@ def test_covariability_and_permuted_data(engine, golden_mini):
     assert p1.shape == C.shape and (p1 != p2).nnz > 0
     # reproduce iteration 1 draw for draw: same seed stream -> same background matrix
     api.set_seed(12)
-    api.get_engine().set_seed(api._next_sampler_seed(force=True))
+    api.get_engine().set_seed(api._next_sampler_seed())
     bgN = synergy._bg_for_perm(counts, C.shape[1], 0.1, 50)
     ref = orc.reorder_columns(C, bgN)
     assert (ref != p1).nnz == 0
     invalid = (bgN < 1) | (bgN > C.shape[0])
     assert not invalid.any()
+    assert p1.has_sorted_indices and np.all(np.diff(p1.indptr) >= 0) and p1.data.min() >= 1
+    # covariability of the z still resident on the device == of the host copy; a larger K x K case
+    eng = api.get_engine()
+    rng = np.random.default_rng(3)
+    Z = rng.normal(size=(150, 333))
+    Z[7, 5] = np.nan                                   # cov(use = "everything"): row / column 7 become NA
+    got = eng.deviations_covariability(Z)
+    ref = orc.deviations_covariability(Z)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert_close(got, ref, "covariability 150 x 150")
