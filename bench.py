@@ -863,7 +863,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="number of timed e2e steps (default min(steps, 10))")
     ap.add_argument("--gen", default="auto", choices=["auto", "host", "device"],
                     help="synthetic counts on the host (numpy) or on the GPU (same model, torch); auto: GPU for >= 5e8 nonzeros")
-    ap.add_argument("--host-narrow", type=int, default=0, help="e2e call: 0 sends the fp64 values as they are (default), 1 narrows them to bytes on host threads, n > 1: with n threads")
+    ap.add_argument("--host-narrow", type=int, default=-1, help="e2e call: -1 (library default) host threads stage / narrow PAGEABLE caller memory only, 0 never, 1 always, n > 1: with n threads")
     ap.add_argument("--quick", action="store_true", help="small workload (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (cost model), 1 row-gather SpMM, 2 dense tcgen05")

@@ -136,6 +136,8 @@ extern "C" void cv_destroy(cv_handle* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->narrower) cv_narrower_destroy(h->narrower);
   if (h->stage8) cudaFreeHost(h->stage8);
+  if (h->stage_ri) cudaFreeHost(h->stage_ri);
+  if (h->stage_out) cudaFreeHost(h->stage_out);
   if (h->s_up) cudaStreamDestroy(h->s_up);
   if (h->s_dn) cudaStreamDestroy(h->s_dn);
   if (h->s_aux) cudaStreamDestroy(h->s_aux);
@@ -181,11 +183,11 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
   if (!strcmp(key, "tail_chunk")) { h->opt_tail_chunk = value != 0; return CV_OK; }
   if (!strcmp(key, "host_narrow")) {
-    // 0 (default): the counts' values cross PCIe in the caller's type; n >= 1: narrowed to bytes on the
-    // host first (cv_hostnarrow.cpp), n = 1 with the default number of threads, n > 1 with n threads.
-    // Measured (profiles/r01u_summary.md): neutral on one GPU with page-locked buffers (the call is
-    // compute-bound), a loss on an 8-GPU host with 4 cores per GPU (the conversion competes for cores)
-    h->opt_host_narrow = (int)(value < 0 ? 0 : value);
+    // -1 (default): host threads stage / narrow PAGEABLE caller memory (cv_hostnarrow.cpp); 0 never; n >= 1
+    // always, n = 1 with the default number of threads, n > 1 with n threads.  Measured for PINNED caller
+    // memory (profiles/r01u_summary.md): neutral on one GPU (the call is compute-bound), a loss on an
+    // 8-GPU host with 4 cores per GPU (the conversion competes for cores) -- hence off for pinned memory
+    h->opt_host_narrow = (int)(value < 0 ? -1 : value);
     if (h->narrower && value > 1 && cv_narrower_threads(h->narrower) != (int)value) {
       cv_narrower_destroy(h->narrower);
       h->narrower = nullptr;

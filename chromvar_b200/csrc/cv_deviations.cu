@@ -479,6 +479,8 @@ struct DevIO {
   int x_type = 0;
   size_t xb = 0;
   bool narrow = false;               // values are being narrowed to bytes on host threads (h->narrower -> h->stage8)
+  bool stage_ri = false;             // ... and the row indices staged in page-locked memory alongside (h->stage_ri)
+  bool land_out = false;             // results land in page-locked memory (h->stage_out) and are copied on by host threads
   int64_t x_bytes_sent = 0;          // bytes of values that actually crossed PCIe
   // results leaving chunk by chunk (K x N column-major: a cell chunk is a contiguous slab)
   double* out_dev = nullptr;
@@ -495,11 +497,21 @@ static int enqueue_counts_upload(cv_handle* h, DevIO& io, int64_t c0, int64_t c1
   const int64_t e0 = io.h_colptr[c0], e1 = io.h_colptr[c1];
   int x_type = io.x_type;
   if (e1 > e0) {
-    CV_TRY(cv_csc_view_copy(h, *io.view, e0, e1, h->rowidx.as<int32_t>(), nullptr, h->s_up));
-    // the row indices are on their way while the last slices of this chunk finish narrowing.
+    bool narrowed = false;
+    if (io.stage_ri) {
+      // pageable caller memory: this chunk's slices (row indices copied, values narrowed) are waited
+      // for first, then both travel from page-locked memory as asynchronous DMA
+      narrowed = cv_narrower_wait(h->narrower, e0, e1) != 0;
+      CV_CUDA(h, cudaMemcpyAsync(h->rowidx.as<int32_t>() + e0, h->stage_ri + e0, (size_t)(e1 - e0) * 4,
+                                 cudaMemcpyHostToDevice, h->s_up));
+    } else {
+      CV_TRY(cv_csc_view_copy(h, *io.view, e0, e1, h->rowidx.as<int32_t>(), nullptr, h->s_up));
+      // the row indices are on their way while the last slices of this chunk finish narrowing
+      narrowed = io.narrow && cv_narrower_wait(h->narrower, e0, e1);
+    }
     // xraw is staging only (K1 of this chunk reads it on the same stream before the next chunk's
     // copy lands), so a byte chunk and a chunk in the caller's type may share it.
-    if (io.narrow && cv_narrower_wait(h->narrower, e0, e1)) {
+    if (narrowed) {
       CV_CUDA(h, cudaMemcpyAsync(h->xraw.as<char>() + (size_t)e0, h->stage8 + e0, (size_t)(e1 - e0),
                                  cudaMemcpyHostToDevice, h->s_up));
       x_type = CV_U8;
@@ -519,9 +531,32 @@ static int enqueue_counts_upload(cv_handle* h, DevIO& io, int64_t c0, int64_t c1
   return CV_OK;
 }
 
+struct LandCopy { cv_narrower* nw; void* dst; const void* src; size_t n; };
+static void CUDART_CB land_copy_cb(void* p) {
+  LandCopy* c = reinterpret_cast<LandCopy*>(p);
+  cv_narrower_copy(c->nw, c->dst, c->src, c->n);          // no CUDA call in here: only queues the pieces
+  delete c;
+}
+
 static int enqueue_result_download(cv_handle* h, const DevIO& io, int64_t c0, int64_t c1, cudaEvent_t ready) {
   const int64_t K = h->K;
   CV_CUDA(h, cudaStreamWaitEvent(h->s_dn, ready, 0));
+  if (io.land_out) {
+    // pageable destination: DMA into the page-locked landing buffer, then the host threads copy the
+    // slab on into the caller's matrix (in pieces, in parallel) as soon as it has landed
+    const size_t slab = (size_t)(c1 - c0) * K * 8, mat = (size_t)h->N * K * 8;
+    double* outs[2] = {io.out_dev, io.out_z};
+    const double* srcs[2] = {h->dev_cm.as<double>(), h->z_cm.as<double>()};
+    for (int m = 0; m < 2; ++m) {
+      if (!outs[m]) continue;
+      char* land = h->stage_out + (size_t)m * mat + (size_t)c0 * K * 8;
+      CV_CUDA(h, cudaMemcpyAsync(land, srcs[m] + c0 * K, slab, cudaMemcpyDeviceToHost, h->s_dn));
+      LandCopy* c = new LandCopy{h->narrower, outs[m] + c0 * K, land, slab};
+      cudaError_t e = cudaLaunchHostFunc(h->s_dn, land_copy_cb, c);
+      if (e != cudaSuccess) { delete c; CV_CUDA(h, e); }
+    }
+    return CV_OK;
+  }
   if (io.out_dev)
     CV_CUDA(h, cudaMemcpyAsync(io.out_dev + c0 * K, h->dev_cm.as<double>() + c0 * K, (size_t)(c1 - c0) * K * 8,
                                cudaMemcpyDeviceToHost, h->s_dn));
@@ -1169,28 +1204,59 @@ int cv_deviations_view(cv_handle* h, const CscView& v, int64_t K, const int64_t*
         cv_handle* h;
         ~NarrowGuard() { if (h->narrower) cv_narrower_finish(h->narrower); }
       } narrow_guard{h};
-      if (h->opt_host_narrow && xb > 1 && v.segs.size() == 1) {
-        if (!h->narrower) {
-          int ndev = 1;
-          cudaGetDeviceCount(&ndev);
-          const int hw = (int)std::thread::hardware_concurrency();
-          const int t = h->opt_host_narrow > 1 ? h->opt_host_narrow : std::max(1, std::min(8, hw / std::max(ndev, 1) - 1));
-          h->narrower = cv_narrower_create(t);
-        }
-        if (h->stage8_cap < (size_t)nnz) {
-          if (h->stage8) cudaFreeHost(h->stage8);
-          h->stage8 = nullptr;
-          h->stage8_cap = 0;
-          if (cudaHostAlloc((void**)&h->stage8, (size_t)nnz, cudaHostAllocDefault) == cudaSuccess) h->stage8_cap = (size_t)nnz;
-          else cudaGetLastError();              // no page-locked memory to spare: the values travel as they are
-        }
-        if (h->stage8_cap >= (size_t)nnz) {
-          cv_narrower_start(h->narrower, v.segs[0].x, x_type, nnz, h->stage8);
+      // host threads between the caller's memory and the DMA engines ("host_narrow"): always when asked
+      // for (n >= 1), by default (-1) when the caller's memory is PAGEABLE (R's vectors are): row
+      // indices staged, values narrowed, results landed in page-locked memory.  Pinned caller memory
+      // travels directly by default.
+      auto pageable = [](const void* p) {
+        cudaPointerAttributes a;
+        if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return p != nullptr; }
+        return a.type == cudaMemoryTypeUnregistered;
+      };
+      const bool one_seg = v.segs.size() == 1;
+      const bool in_pageable = one_seg && pageable(v.segs[0].x) && pageable(v.segs[0].rowidx);
+      const bool want_workers = h->opt_host_narrow >= 1 || (h->opt_host_narrow < 0 && in_pageable && nnz >= (1 << 20));
+      auto ensure_pinned = [&](void** buf, size_t* cap, size_t bytes) {
+        if (*cap >= bytes) return true;
+        if (*buf) cudaFreeHost(*buf);
+        *buf = nullptr;
+        *cap = 0;
+        if (cudaHostAlloc(buf, bytes, cudaHostAllocDefault) == cudaSuccess) { *cap = bytes; return true; }
+        cudaGetLastError();                     // no page-locked memory to spare: direct copies
+        return false;
+      };
+      if (want_workers && !h->narrower) {
+        int ndev = 1;
+        cudaGetDeviceCount(&ndev);
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int t = h->opt_host_narrow > 1 ? h->opt_host_narrow : std::max(1, std::min(6, hw / std::max(ndev, 1) - 1));
+        h->narrower = cv_narrower_create(t);
+      }
+      if (want_workers && xb > 1 && one_seg) {
+        size_t cap8 = h->stage8_cap;
+        void* b8 = h->stage8;
+        if (ensure_pinned(&b8, &cap8, (size_t)nnz)) {
+          h->stage8 = (uint8_t*)b8; h->stage8_cap = cap8;
+          const int32_t* ri = nullptr;
+          if (in_pageable) {
+            size_t capr = h->stage_ri_cap * 4;
+            void* br = h->stage_ri;
+            if (ensure_pinned(&br, &capr, (size_t)nnz * 4)) { ri = v.segs[0].rowidx; io.stage_ri = true; }
+            h->stage_ri = (int32_t*)br; h->stage_ri_cap = capr / 4;
+          }
+          cv_narrower_start(h->narrower, v.segs[0].x, x_type, nnz, h->stage8, ri, h->stage_ri);
           io.narrow = true;
-        }
+        } else { h->stage8 = (uint8_t*)b8; h->stage8_cap = cap8; }
+      }
+      if (want_workers && (out_dev || out_z) && (pageable(out_dev) || pageable(out_z)) &&
+          (size_t)K * (size_t)N * 16 <= ((size_t)2 << 30)) {
+        size_t capo = h->stage_out_cap;
+        void* bo = h->stage_out;
+        if (ensure_pinned(&bo, &capo, (size_t)K * (size_t)N * 16)) io.land_out = true;
+        h->stage_out = (char*)bo; h->stage_out_cap = capo;
       }
       rc = deviations_run(h, 0, 0, &io);
-      if (h->narrower) cv_narrower_finish(h->narrower);
+      if (h->narrower) cv_narrower_finish(h->narrower);      // incl. the last slabs of the results
       if (rc == CV_OK) {
         CV_TRY(download_results(h, io.results_streamed ? nullptr : out_dev, io.results_streamed ? nullptr : out_z,
                                 out_matches, out_overlap, out_variability, nullptr, nullptr));

@@ -8,10 +8,17 @@
 // host's PCIe uplinks, and for pageable caller memory (R's) the large copy starts from pinned
 // memory.  A slice holding anything but an integer in 0..255 (a large count, a fraction, NaN) is
 // reported and that chunk travels in its original type; validation stays on the device (K1).
+//
+// The same worker threads stage PAGEABLE caller memory (what R passes): the row indices of a slice are
+// copied into page-locked memory next to the narrowed values, so every upload is a true asynchronous
+// DMA from pinned memory instead of the driver's single-threaded bounce copy, and finished slabs of
+// the results are copied from a page-locked landing buffer into the caller's matrices in parallel
+// pieces (cv_narrower_copy).
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -86,25 +93,48 @@ struct cv_narrower {
   int x_type = 0;
   int64_t n = 0, n_slices = 0;
   uint8_t* out = nullptr;
+  const int32_t* ri = nullptr;                 // optional: row indices staged slice by slice next to the values
+  int32_t* ri_out = nullptr;
   std::atomic<int64_t> next{0};
+  // plain copies (results leaving through page-locked memory): pieces handed out under the mutex
+  struct Copy { char* dst; const char* src; size_t n; };
+  std::deque<Copy> copies;
+  int64_t copies_open = 0;                     // queued + running
   std::vector<std::atomic<uint8_t>> flag;      // 0 pending, 1 all values narrowed, 2 slice holds something else
+
+  void do_slice(int64_t s) {
+    const int64_t a = s * SLICE, b = std::min(n, a + SLICE);
+    if (ri) memcpy(ri_out + a, ri + a, (size_t)(b - a) * 4);
+    const bool ok = narrow_any(x, x_type, a, out + a, b - a);
+    flag[(size_t)s].store(ok ? 1 : 2, std::memory_order_release);
+  }
 
   void run() {
     uint64_t seen = 0;
     for (;;) {
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv_job.wait(lk, [&] { return quit || generation != seen; });
+        cv_job.wait(lk, [&] { return quit || generation != seen || !copies.empty(); });
         if (quit) return;
         seen = generation;
         ++active;
       }
       for (;;) {
+        Copy c{nullptr, nullptr, 0};
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          if (!copies.empty()) { c = copies.front(); copies.pop_front(); }
+        }
+        if (c.dst) {                            // results first: they free the landing buffer's consumers
+          memcpy(c.dst, c.src, c.n);
+          std::lock_guard<std::mutex> lk(mu);
+          --copies_open;
+          cv_idle.notify_all();
+          continue;
+        }
         const int64_t s = next.fetch_add(1, std::memory_order_relaxed);
         if (s >= n_slices) break;
-        const int64_t a = s * SLICE, b = std::min(n, a + SLICE);
-        const bool ok = narrow_any(x, x_type, a, out + a, b - a);
-        flag[(size_t)s].store(ok ? 1 : 2, std::memory_order_release);
+        do_slice(s);
       }
       {
         std::lock_guard<std::mutex> lk(mu);
@@ -124,12 +154,32 @@ cv_narrower* cv_narrower_create(int threads) {
 
 int cv_narrower_threads(const cv_narrower* nw) { return nw ? (int)nw->workers.size() : 0; }
 
-// No worker touches the caller's buffers after this returns (pending slices are dropped).
+// No worker touches the caller's buffers after this returns (pending slices are dropped, queued
+// copies are carried out).
 void cv_narrower_finish(cv_narrower* nw) {
   if (!nw) return;
   nw->next.store(nw->n_slices, std::memory_order_relaxed);
   std::unique_lock<std::mutex> lk(nw->mu);
-  nw->cv_idle.wait(lk, [&] { return nw->active == 0; });
+  nw->cv_idle.wait(lk, [&] { return nw->active == 0 && nw->copies_open == 0; });
+}
+
+// memcpy(dst, src, n) on the worker threads, in pieces; returns at once.  May be called from a CUDA
+// host callback (no CUDA call inside).  cv_narrower_copies_wait / cv_narrower_finish wait for them.
+void cv_narrower_copy(cv_narrower* nw, void* dst, const void* src, size_t n) {
+  const size_t piece = (size_t)4 << 20;
+  {
+    std::lock_guard<std::mutex> lk(nw->mu);
+    for (size_t o = 0; o < n; o += piece) {
+      nw->copies.push_back(cv_narrower::Copy{(char*)dst + o, (const char*)src + o, std::min(piece, n - o)});
+      ++nw->copies_open;
+    }
+  }
+  nw->cv_job.notify_all();
+}
+
+void cv_narrower_copies_wait(cv_narrower* nw) {
+  std::unique_lock<std::mutex> lk(nw->mu);
+  nw->cv_idle.wait(lk, [&] { return nw->copies_open == 0; });
 }
 
 void cv_narrower_destroy(cv_narrower* nw) {
@@ -145,11 +195,14 @@ void cv_narrower_destroy(cv_narrower* nw) {
 }
 
 // Start converting x[0, n) (x_type CV_F64 / CV_F32 / CV_I32) into out[0, n); returns at once.
-void cv_narrower_start(cv_narrower* nw, const void* x, int x_type, int64_t n, uint8_t* out) {
+// ri / ri_out (optional): the row indices of every slice are copied to ri_out alongside.
+void cv_narrower_start(cv_narrower* nw, const void* x, int x_type, int64_t n, uint8_t* out, const int32_t* ri,
+                       int32_t* ri_out) {
   cv_narrower_finish(nw);
   {
     std::lock_guard<std::mutex> lk(nw->mu);
     nw->x = x; nw->x_type = x_type; nw->n = n; nw->out = out;
+    nw->ri = ri; nw->ri_out = ri_out;
     nw->n_slices = (n + SLICE - 1) / SLICE;
     if ((int64_t)nw->flag.size() < nw->n_slices) {
       std::vector<std::atomic<uint8_t>> f((size_t)nw->n_slices);
@@ -176,9 +229,7 @@ int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1) {
         // nobody will ever set this flag, so the waiting thread converts the slice itself
         std::unique_lock<std::mutex> lk(nw->mu);
         if (nw->active == 0 && nw->flag[(size_t)s].load(std::memory_order_acquire) == 0) {
-          const int64_t a = s * SLICE, b = std::min(nw->n, a + SLICE);
-          const bool ok1 = narrow_any(nw->x, nw->x_type, a, nw->out + a, b - a);
-          nw->flag[(size_t)s].store(ok1 ? 1 : 2, std::memory_order_release);
+          nw->do_slice(s);
           continue;
         }
       }
@@ -194,7 +245,7 @@ int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1) {
 extern "C" int cv_host_narrow(const void* x, int x_type, int64_t n, uint8_t* out, int threads) {
   if (!x || !out || n < 0 || (x_type != CV_F64 && x_type != CV_F32 && x_type != CV_I32)) return -CV_ERR_INVALID;
   cv_narrower* nw = cv_narrower_create(threads);
-  cv_narrower_start(nw, x, x_type, n, out);
+  cv_narrower_start(nw, x, x_type, n, out, nullptr, nullptr);
   const int ok = cv_narrower_wait(nw, 0, n);
   cv_narrower_destroy(nw);
   return ok;

@@ -72,6 +72,10 @@ struct cv_handle {
   struct cv_narrower* narrower = nullptr;   // host threads converting x to bytes ahead of the uploads (cv_hostnarrow.cpp)
   uint8_t* stage8 = nullptr;          // page-locked staging of the narrowed values
   size_t stage8_cap = 0;
+  int32_t* stage_ri = nullptr;        // page-locked staging of the row indices (pageable caller memory)
+  size_t stage_ri_cap = 0;            // in elements
+  char* stage_out = nullptr;          // page-locked landing buffer of the results (pageable caller memory)
+  size_t stage_out_cap = 0;
   // cv_deviations_compute_async: a resident call whose host-side verdicts (index checks, exactness
   // bounds, e2m1 feasibility) are known from the last fully checked call on the SAME resident inputs
   // is enqueued without any host synchronisation; cv_deviations_wait settles it
@@ -80,7 +84,7 @@ struct cv_handle {
   bool replaying = false;             // deviations_run is enqueueing a replay
   bool async_pending = false;         // a replay is in flight: flags / timings not collected yet
   int opt_tail_chunk = 1;             // "tail_chunk": streamed call ends with a short fourth cell chunk
-  int opt_host_narrow = 0;            // "host_narrow": 0 (default) keeps the caller's value type on the wire
+  int opt_host_narrow = -1;           // "host_narrow": -1 (default) host threads stage / narrow PAGEABLE caller memory, 0 never, n >= 1 always
   // timed spans of the current call (CUDA events on `stream`), summed per category afterwards
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -219,7 +223,10 @@ struct cv_narrower;
 cv_narrower* cv_narrower_create(int threads);
 int cv_narrower_threads(const cv_narrower* nw);
 void cv_narrower_destroy(cv_narrower* nw);
-void cv_narrower_start(cv_narrower* nw, const void* x, int x_type, int64_t n, uint8_t* out);
+void cv_narrower_start(cv_narrower* nw, const void* x, int x_type, int64_t n, uint8_t* out, const int32_t* ri,
+                       int32_t* ri_out);
+void cv_narrower_copy(cv_narrower* nw, void* dst, const void* src, size_t n);
+void cv_narrower_copies_wait(cv_narrower* nw);
 int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1);
 void cv_narrower_finish(cv_narrower* nw);
 int cv_settle(cv_handle* h);            // cv_deviations.cu: waits for a pending replay and collects its verdict

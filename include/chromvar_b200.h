@@ -88,10 +88,14 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *                      0 for a shard of a larger matrix (the caller checks the reduced totals)
  *   "tail_chunk"       cv_deviations_csc: 1 (default) a short fourth cell chunk ends the call so that little
  *                      of the results is still on its way to the host when the last GEMM finishes; 0: three chunks
- *   "host_narrow"      cv_deviations_csc: 0 (default) the counts' values cross PCIe in the caller's type;
- *                      1: host threads convert wide types (a dgCMatrix's double x) to bytes ahead of the
- *                      uploads, chunks holding anything but integers 0..255 still travel as they are;
- *                      n > 1: with n threads.  Same results bit for bit. */
+ *   "host_narrow"      cv_deviations_csc: host threads between the caller's memory and the DMA engines.
+ *                      -1 (default): when the caller's arrays are PAGEABLE (R's vectors are) the row indices
+ *                      are staged and the values narrowed to bytes into page-locked memory slice by slice
+ *                      ahead of the uploads, and the results land in page-locked memory and are copied on
+ *                      in parallel pieces -- instead of the driver's single-threaded bounce copies; pinned
+ *                      caller memory travels directly.  0: never.  1: always (also for pinned memory: fewer
+ *                      bytes on a shared PCIe fabric); n > 1: with n threads.  Chunks holding anything but
+ *                      integers 0..255 travel as they are.  Same results bit for bit. */
 int cv_set_option(cv_handle* h, const char* key, int64_t value);
 /* the CUDA stream all of this handle's kernels run on (a cudaStream_t), for event timing */
 void* cv_stream(cv_handle* h);

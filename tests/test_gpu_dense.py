@@ -282,10 +282,17 @@ def test_streamed_call_validates_and_falls_back(engine):
     engine.set_option("path", 2)
     try:
         x = C.data.astype(np.float64).copy()
-        x[len(x) // 2] = 2.5                                   # counts_check fails in the middle chunk
+        x[len(x) // 2] = 2.5                                   # a fractional count in the middle chunk
         with pytest.raises(_lib.ChromVARError) as ei:
             engine.deviations_csc(P, N, C.indptr, C.indices, x, ptr, idx, bg, e)
-        assert ei.value.code == _lib.CV_ERR_INVALID and "integer" in str(ei.value)
+        # a restriction of this engine (exact integer sums), reported as such -- NOT as counts_check,
+        # which only requires counts >= 0 (R/utils.R:3-12)
+        assert ei.value.code == _lib.CV_ERR_UNSUPPORTED and "fractional" in str(ei.value)
+        assert "counts_check" not in str(ei.value)
+        x[len(x) // 2] = -1.0                                  # counts_check proper
+        with pytest.raises(_lib.ChromVARError) as ei:
+            engine.deviations_csc(P, N, C.indptr, C.indices, x, ptr, idx, bg, e)
+        assert ei.value.code == _lib.CV_ERR_INVALID and "counts_check" in str(ei.value)
         bad_bg = bg.copy()
         bad_bg[17, 3] = P + 1
         with pytest.raises(_lib.ChromVARError) as ei:
@@ -366,4 +373,35 @@ def test_streamed_call_host_narrowing(engine):
     finally:
         engine.set_option("path", 0)
         engine.set_option("cell_chunk", 0)
+        engine.set_option("host_narrow", -1)
+
+
+def test_streamed_call_stages_pageable_memory(engine):
+    """Default ("host_narrow" = -1): pageable caller arrays (numpy's, R's) are staged by host threads --
+    row indices copied, values narrowed, results landed in page-locked memory -- pinned ones travel
+    directly.  Same results bit for bit either way."""
+    import torch
+    C, P, N, bg, e, ptr, idx = _small_problem()
+    assert C.nnz >= 1 << 20
+    engine.set_option("path", 2)
+    try:
+        x64 = np.ascontiguousarray(C.data.astype(np.float64))
+        ri = np.ascontiguousarray(C.indices.astype(np.int32))
         engine.set_option("host_narrow", 0)
+        base = engine.deviations_csc(P, N, C.indptr, ri, x64, ptr, idx, bg, e)
+        wide = engine.stats()["h2d_bytes"]
+        engine.set_option("host_narrow", -1)
+        got = engine.deviations_csc(P, N, C.indptr, ri, x64, ptr, idx, bg, e)      # pageable: staged
+        assert wide - engine.stats()["h2d_bytes"] == 7 * C.nnz
+        for key in ("dev", "z", "variability", "matches", "overlap"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), key
+        # pinned inputs: the default leaves them alone (all 8 bytes per value cross PCIe)
+        xp = torch.from_numpy(x64).pin_memory().numpy()
+        rp = torch.from_numpy(ri).pin_memory().numpy()
+        got = engine.deviations_csc(P, N, C.indptr, rp, xp, ptr, idx, bg, e)
+        assert engine.stats()["h2d_bytes"] == wide
+        for key in ("dev", "z"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), key
+    finally:
+        engine.set_option("path", 0)
+        engine.set_option("host_narrow", -1)
