@@ -321,6 +321,7 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   const unsigned full = 0xffffffffu;
   int lane = threadIdx.x & 31;
   uint32_t bad = 0, vmax = 0;
+  bool unsorted = false;
   int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (int64_t base = e_begin + warp_id * 32; base < nnz; base += warps_total * 32) {
@@ -331,6 +332,9 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
     if (active) {
       v = load_count<XT>(x, e, bad);
       int r = rowidx[e];
+      // flags[4]: some column lists its rows out of order (legal, just rare: R's dgCMatrix and scipy keep
+      // them sorted); the per-range builders of the dense path then scan whole columns instead of searching
+      if (e > __ldg(colptr + c) && rowidx[e - 1] > r) unsorted = true;
       if (r < 0 || r >= P) { bad |= FLAG_BADROW; v = 0; }
       else if (v) atomicAdd(peak_tot + r, (unsigned long long)v);
       val[e] = v;
@@ -355,6 +359,7 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   bad |= __shfl_xor_sync(full, bad, 4);
   bad |= __shfl_xor_sync(full, bad, 2);
   bad |= __shfl_xor_sync(full, bad, 1);
+  if (__any_sync(full, unsorted) && lane == 0) atomicOr(flags + 4, 1u);
   if (lane == 0) {
     if (bad) atomicOr(flags + 0, bad);
     if (vmax) atomicMax(flags + 1, vmax);
@@ -392,32 +397,70 @@ __global__ void k_u64_to_f64(const unsigned long long* __restrict__ in, double* 
 
 // dense column-major -> CSC (rows within a column land in arbitrary order; nothing downstream
 // depends on the order).  Pass 1 counts nonzeros per column, pass 2 writes them.
+// Dense P x N input -> CSC with the rows of every column in increasing order (what dgCMatrix and
+// scipy guarantee, and what the per-range builders of the dense path search in): per-(column, block of
+// 256 rows) nonzero counts, a scan over the blocks of each column, then an ordered fill.
 template <typename XT>
 __global__ void __launch_bounds__(256)
-k_dense_count(const XT* __restrict__ x, int64_t P, int64_t N, unsigned long long* __restrict__ cnt) {
-  int64_t c = blockIdx.y;
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool nz = r < P && x[c * P + r] != (XT)0;
-  unsigned m = __ballot_sync(0xffffffffu, nz);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt + c, (unsigned long long)__popc(m));
+k_dense_count(const XT* __restrict__ x, int64_t P, int64_t N, uint32_t* __restrict__ blkcnt) {
+  __shared__ uint32_t s_w[8];
+  const int64_t c = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool nz = r < P && x[c * P + r] != (XT)0;
+  const unsigned m = __ballot_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    blkcnt[c * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// one CTA per column: exclusive scan of its block counts (in place), column total -> cnt[c]
+__global__ void __launch_bounds__(1024)
+k_dense_blkscan(uint32_t* __restrict__ blkcnt, int nblk, unsigned long long* __restrict__ cnt) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  uint32_t* row = blkcnt + (int64_t)blockIdx.x * nblk;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < nblk ? row[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblk) row[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cnt[blockIdx.x] = (unsigned long long)carry;
 }
 
 template <typename XT>
 __global__ void __launch_bounds__(256)
 k_dense_fill(const XT* __restrict__ x, int64_t P, int64_t N, const int64_t* __restrict__ colptr,
-             unsigned long long* __restrict__ cursor, int32_t* __restrict__ rowidx,
-             XT* __restrict__ xout) {
-  int64_t c = blockIdx.y;
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  XT v = r < P ? x[c * P + r] : (XT)0;
-  bool nz = v != (XT)0;
-  unsigned m = __ballot_sync(0xffffffffu, nz);
-  int lane = threadIdx.x & 31;
-  unsigned long long base = 0;
-  if (lane == 0 && m) base = atomicAdd(cursor + c, (unsigned long long)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
+             const uint32_t* __restrict__ blkoff, int32_t* __restrict__ rowidx, XT* __restrict__ xout) {
+  __shared__ uint32_t s_w[8];
+  const int64_t c = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const XT v = r < P ? x[c * P + r] : (XT)0;
+  const bool nz = v != (XT)0;
+  const unsigned m = __ballot_sync(0xffffffffu, nz);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_w[warp] = __popc(m);
+  __syncthreads();
   if (nz) {
-    int64_t pos = colptr[c] + (int64_t)base + __popc(m & ((1u << lane) - 1u));
+    uint32_t before = 0;
+    for (int w = 0; w < warp; ++w) before += s_w[w];
+    const int64_t pos = colptr[c] + blkoff[c * gridDim.x + blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
     rowidx[pos] = (int32_t)r;
     xout[pos] = v;
   }
@@ -862,7 +905,10 @@ static int dense_to_csc(cv_handle* h, const XT* xd, int64_t P, int64_t N) {
   CV_CUDA(h, cudaMemsetAsync(cnt, 0, (size_t)(N + 1) * 8, h->stream));
   dim3 grid((unsigned)((P + 255) / 256), (unsigned)N);
   if (N > 65535) CV_FAIL(h, CV_ERR_UNSUPPORTED, "dense counts input with more than 65535 columns; pass CSC");
-  CV_LAUNCH(h, k_dense_count<XT>, grid, 256, 0, xd, P, N, cnt);
+  CV_TRY(cv_ensure(h, h->tmp0, (size_t)grid.x * (size_t)N * 4));
+  uint32_t* blk = h->tmp0.as<uint32_t>();
+  CV_LAUNCH(h, k_dense_count<XT>, grid, 256, 0, xd, P, N, blk);
+  CV_LAUNCH(h, k_dense_blkscan, (unsigned)N, 1024, 0, blk, (int)grid.x, cnt);
   CV_LAUNCH(h, k_scan_small_u64, 1, 1024, 0, cnt, h->colptr.as<int64_t>(), N);
   int64_t nnz = 0;
   CV_CUDA(h, cudaMemcpyAsync(&nnz, h->colptr.as<int64_t>() + N, 8, cudaMemcpyDeviceToHost, h->stream));
@@ -871,8 +917,7 @@ static int dense_to_csc(cv_handle* h, const XT* xd, int64_t P, int64_t N) {
   h->nnz = nnz;
   CV_TRY(cv_ensure(h, h->rowidx, (size_t)nnz * 4));
   CV_TRY(cv_ensure(h, h->xraw, (size_t)nnz * sizeof(XT)));
-  CV_CUDA(h, cudaMemsetAsync(cnt, 0, (size_t)(N + 1) * 8, h->stream));
-  CV_LAUNCH(h, k_dense_fill<XT>, grid, 256, 0, xd, P, N, h->colptr.as<int64_t>(), cnt,
+  CV_LAUNCH(h, k_dense_fill<XT>, grid, 256, 0, xd, P, N, h->colptr.as<int64_t>(), blk,
             h->rowidx.as<int32_t>(), h->xraw.as<XT>());
   return CV_OK;
 }

@@ -190,6 +190,49 @@ k_dense_cells(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   }
 }
 
+// The same for long columns (bulk data: every peak of every sample holds a count): work item = (cell,
+// range of DC_RANGE peaks), so a dense 500 000-peak column is built by 16 CTAs at once instead of one
+// CTA passing over it several times.  Sorted columns (flags4 == 0, checked by K1) are entered by
+// binary search; unsorted ones are scanned whole and filtered.
+#define DC_RANGE 32768
+__global__ void __launch_bounds__(256)
+k_dense_cells_split(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
+                    const uint32_t* __restrict__ val, int N, int c0, int n_rows_padded, int shift, int64_t Ppad,
+                    const uint32_t* __restrict__ k1_flags, uint8_t* __restrict__ Cd) {
+  __shared__ __align__(16) uint32_t sm[DC_RANGE / 4];
+  const int n_ranges = (int)((Ppad + DC_RANGE - 1) / DC_RANGE);
+  const bool sorted = k1_flags[4] == 0u;
+  for (int64_t item = blockIdx.x; item < (int64_t)n_rows_padded * n_ranges; item += gridDim.x) {
+    const int r = (int)(item / n_ranges), rg = (int)(item % n_ranges);
+    const int c = c0 + r;
+    const int64_t q0 = (int64_t)rg * DC_RANGE, q1 = min(Ppad, q0 + DC_RANGE);
+    const int nw = (int)(q1 - q0) >> 2;                  // Ppad is a multiple of 128
+    for (int i = threadIdx.x; i < (nw >> 2); i += 256) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    int64_t beg = c < N ? colptr[c] : 0, end = c < N ? colptr[c + 1] : 0;
+    if (sorted && end > beg) {
+      int64_t lo = beg, hi = end;                        // first entry with row >= q0
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(rowidx + mid) < q0) lo = mid + 1; else hi = mid; }
+      beg = lo;
+      hi = end;                                          // first entry with row >= q1
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(rowidx + mid) < q1) lo = mid + 1; else hi = mid; }
+      end = lo;
+    }
+    for (int64_t x = beg + threadIdx.x; x < end; x += 256) {
+      const int q = __ldg(rowidx + x);
+      if (q >= q0 && q < q1) {
+        const int off = q - (int)q0;
+        // (duplicate row indices inside a column still sum, like Matrix does)
+        atomicAdd(&sm[off >> 2], ((__ldg(val + x) >> shift) & 0xFFu) << (8 * (off & 3)));
+      }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(Cd + (int64_t)r * Ppad + q0);
+    for (int i = threadIdx.x; i < (nw >> 2); i += 256) dst[i] = reinterpret_cast<const uint4*>(sm)[i];
+    __syncthreads();
+  }
+}
+
 // cnt[j][q] = #{p : bg[p, j] = q}; bg column-major, so reads are coalesced
 __global__ void k_bg_mult_count_cm(const int32_t* __restrict__ bg, int base, int64_t PB, int P,
                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
@@ -578,6 +621,14 @@ int cv_dense_rebuild_rows_u8(cv_handle* h, const DensePlan& pl) {
 
 // Cd rows [0, rows) <- cells [c0, c0 + rows), digit plane `shift` / 8.  Asynchronous.
 int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift) {
+  if (h->N > 0 && h->nnz / h->N > 16384) {
+    // long columns (bulk data): (cell, peak range) items -- config 4: 3.56 ms -> 0.2 ms per plane
+    const int64_t items = rows * ((pl.Ppad + DC_RANGE - 1) / DC_RANGE);
+    CV_LAUNCH(h, k_dense_cells_split, (unsigned)std::min<int64_t>(items, (int64_t)h->num_sms * 6), 256, 0,
+              h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), (int)h->N, (int)c0, (int)rows, shift,
+              pl.Ppad, h->flags.as<uint32_t>(), h->dn_C.as<uint8_t>());
+    return CV_OK;
+  }
   const int budget = h->max_smem_optin - 2048;
   const int chunk1 = (int)std::min<int64_t>(pl.Ppad, (budget / 128) * 128);
   CV_CUDA(h, cudaMemsetAsync(h->work_ctr.as<uint32_t>() + 1, 0, 4, h->stream));

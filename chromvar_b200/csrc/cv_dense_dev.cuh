@@ -361,17 +361,23 @@ __device__ __forceinline__ void dn_decode_tile(int band, int n_groups, int n_uni
 }
 
 // 1 / E[k][j] of the group's annotations -> shared memory (epilogue warps only: bar 1, 128 threads)
-template <int MODE>
+// NT = number of epilogue threads of the CTA (128: four warps; 256: eight warps, e2m1 kernel)
+template <int NT>
+__device__ __forceinline__ void dn_epi_bar() {
+  if (NT == 128) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+template <int MODE, int NT = 128>
 __device__ __forceinline__ void dn_epi_stage_tables(const DenseParams& prm, int k0, int nk, double* s_winv, int et) {
   const int I = prm.B + 1;
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  dn_epi_bar<NT>();
   if (MODE == DN_EPI_FUSED32) {
     uint32_t* s2 = reinterpret_cast<uint32_t*>(s_winv);
-    for (int i = et; i < nk * I; i += 128) s2[i] = prm.winv_fx[(int64_t)k0 * I + i];
+    for (int i = et; i < nk * I; i += NT) s2[i] = prm.winv_fx[(int64_t)k0 * I + i];
   } else {
-    for (int i = et; i < nk * I; i += 128) s_winv[i] = 1.0 / prm.etab[(int64_t)k0 * I + i];
+    for (int i = et; i < nk * I; i += NT) s_winv[i] = 1.0 / prm.etab[(int64_t)k0 * I + i];
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  dn_epi_bar<NT>();
 }
 
 // One epilogue thread = one cell (one TMEM lane): streams the 256 accumulator columns of its lane.
@@ -566,9 +572,10 @@ __device__ __forceinline__ void dn_epi_consume(const DenseParams& prm, int cb_lo
 }
 
 // merge the 4 epilogue warps' variability partials of every annotation of the group
+template <int NT = 128>
 __device__ __forceinline__ void dn_epi_merge(const DenseParams& prm, int cb_local, int k0, int nk,
                                              const double* s_wred, int et) {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  dn_epi_bar<NT>();
   if (et < nk) {
     DWelford tot = {0.0, 0.0, 0.0};
     double nf = 0.0;

@@ -35,6 +35,7 @@
 #define F4_SG_ROWS (F4_NA + F4_NB)
 #define F4_SF_COL 464                    // first TMEM column of the scale bytes
 #define F4_SMEM_BYTES DN_SMEM2_BYTES
+#define F4_THREADS 384                   // warps 0-3: TMA / MMA / TMEM allocation, warps 4-11: epilogue (two per TMEM lane quarter)
 enum { F4_FAIL_CAPACITY = 1u, F4_FAIL_DUPLICATE = 2u, F4_FAIL_NIBBLE = 4u };
 
 // ---- terms over S = {1, 2, 3, 4, 6} ---------------------------------------------------------------------
@@ -381,7 +382,7 @@ __host__ __device__ constexpr uint32_t make_idesc_mxf4(int M, int N) {
 // Work item = (256-cell unit, super-group): sub-tile A (256 stacked rows) then sub-tile B (208).
 // Same roles and barriers as k_dense_contract_pair; the accumulator stage is the sub-tile.
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F4_THREADS, 1)
 k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_ma,
                      const __grid_constant__ CUtensorMap map_mb, const DenseParams prm) {
   extern __shared__ unsigned char dn_smem_raw[];
@@ -395,7 +396,7 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + DN_STAGES2;
   uint64_t* tfull_bar = bars + 2 * DN_STAGES2;        // [2] per sub-tile
-  uint64_t* tempty_bar = bars + 2 * DN_STAGES2 + 2;   // [2] leader's: 256 arrivals
+  uint64_t* tempty_bar = bars + 2 * DN_STAGES2 + 2;   // [2] leader's: 512 arrivals (256 epilogue threads of each CTA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DN_STAGES2 + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -412,7 +413,7 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < DN_STAGES2; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 2 * (F4_THREADS - 128)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -424,7 +425,7 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 4) {
+  if (warp >= 4 && warp < 8) {
     // unit block scales (ue8m0 0x7F = 2^0) in every byte of the scale columns of this CTA's lanes
     const uint32_t la = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (int c = F4_SF_COL; c < 512; ++c)
@@ -516,9 +517,13 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue (both CTAs): one thread = one cell (TMEM lane of this CTA) =====
+    // ===== epilogue (both CTAs): one thread = one cell (TMEM lane of this CTA) x half of the sub-tile's
+    // annotations -- eight warps, two per lane quarter, so the two sweeps of the fixed-point form
+    // finish well inside the other sub-tile's MMAs =====
     const int q4 = warp & 3;
+    const int set = (warp - 4) >> 2;                     // 0: first half of the annotations, 1: the rest
     const int et = threadIdx.x - 128;
+    constexpr int NT = F4_THREADS - 128;
     uint32_t par = 0u;
     for (int64_t item = pair_id; item < prm.n_tiles; item += n_pairs) {
       int unit, sg;
@@ -528,15 +533,22 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
         const int k0 = sg * Gsg + (half ? prm.Ga : 0);
         if (k0 >= prm.K) continue;
         const int nk = min(half ? prm.Gb : prm.Ga, prm.K - k0);
-        dn_epi_stage_tables<MODE>(prm, k0, nk, s_winv, et);
+        dn_epi_stage_tables<MODE, NT>(prm, k0, nk, s_winv, et);
         mbar_wait_relaxed(tfull_bar + half, (par >> half) & 1u, 256);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * F4_NA);
-        dn_epi_consume<MODE, true>(prm, cb, k0, nk, taddr, s_winv, s_wred, q4, lane);
+        const int a0 = set ? (nk + 1) >> 1 : 0, a1 = set ? nk : (nk + 1) >> 1;
+        if (a1 > a0) {
+          const int I = prm.B + 1;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * F4_NA + a0 * I);
+          const double* tab = MODE == DN_EPI_FUSED32
+                                  ? reinterpret_cast<const double*>(reinterpret_cast<const uint32_t*>(s_winv) + a0 * I)
+                                  : s_winv + a0 * I;
+          dn_epi_consume<MODE, true>(prm, cb, k0 + a0, a1 - a0, taddr, tab, s_wred + a0 * 16, q4, lane);
+        }
         tc_fence_before();
         mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar + half), 0));
-        if (cb < prm.n_cell_blocks) dn_epi_merge(prm, cb, k0, nk, s_wred, et);
-        else asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (cb < prm.n_cell_blocks) dn_epi_merge<NT>(prm, cb, k0, nk, s_wred, et);
+        else dn_epi_bar<NT>();
         par ^= 1u << half;
       }
     }
@@ -697,11 +709,11 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   if (fixed_point_epilogue) {
     CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract_fp4<DN_EPI_FUSED32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     F4_SMEM_BYTES));
-    k_dense_contract_fp4<DN_EPI_FUSED32><<<2 * pairs, DN_THREADS, F4_SMEM_BYTES, h->stream>>>(map_c, map_ma, map_mb, prm);
+    k_dense_contract_fp4<DN_EPI_FUSED32><<<2 * pairs, F4_THREADS, F4_SMEM_BYTES, h->stream>>>(map_c, map_ma, map_mb, prm);
   } else {
     CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract_fp4<DN_EPI_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     F4_SMEM_BYTES));
-    k_dense_contract_fp4<DN_EPI_FUSED><<<2 * pairs, DN_THREADS, F4_SMEM_BYTES, h->stream>>>(map_c, map_ma, map_mb, prm);
+    k_dense_contract_fp4<DN_EPI_FUSED><<<2 * pairs, F4_THREADS, F4_SMEM_BYTES, h->stream>>>(map_c, map_ma, map_mb, prm);
   }
   h->launches++;
   CV_CUDA(h, cudaGetLastError());

@@ -405,3 +405,36 @@ def test_streamed_call_stages_pageable_memory(engine):
     finally:
         engine.set_option("path", 0)
         engine.set_option("host_narrow", -1)
+
+
+@pytest.mark.parametrize("shuffled", [False, True])
+def test_dense_long_columns_split_builder(engine, shuffled):
+    """Bulk-like input: every peak of every sample holds a count, so the cells operand is built by
+    (cell, peak range) items (k_dense_cells_split) -- by binary search into sorted columns, by a
+    filtered scan when a column lists its rows out of order (K1 notices)."""
+    rng = np.random.default_rng(21)
+    P, N, B = 70_000, 40, 50
+    X = rng.poisson(rng.lognormal(1.0, 1.0, (P, 1)) * rng.uniform(2, 6, (1, N))).astype(np.float64)
+    X[X.sum(axis=1) == 0, 0] = 1
+    C = sp.csc_matrix(X)
+    assert C.nnz / N > 16384 and X.max() > 255
+    indptr, indices, data = C.indptr.copy(), C.indices.copy(), C.data.copy()
+    if shuffled:
+        for c in range(0, N, 3):
+            a, b = indptr[c], indptr[c + 1]
+            perm = rng.permutation(b - a)
+            indices[a:b], data[a:b] = indices[a:b][perm], data[a:b][perm]
+    sets = [rng.choice(np.arange(1, P + 1), n, replace=False) for n in (5000, 700, 90, 20000)]
+    ptr, idx = sets_to_csr(sets)
+    bg = np.asfortranarray(rng.integers(1, P + 1, size=(P, B)).astype(np.int32))
+    e = orc.compute_expectations_core(C)
+    engine.set_option("path", 2)
+    try:
+        engine.set_counts_csc(P, N, indptr, indices, data)
+        got = engine.deviations(ptr, idx, bg, e, sums=True)
+        st = engine.stats()
+        assert st["path"] == 1 and st["planes"] == 2
+        ref = orc.compute_deviations_core(C, sets, bg, e, intermediate=True)
+        check_against_oracle(got, ref)
+    finally:
+        engine.set_option("path", 0)

@@ -214,10 +214,16 @@ def test_counts_validation(engine):
     from chromvar_b200 import _lib
     ptr = np.array([0, 2, 3], np.int64)
     idx = np.array([0, 1, 1], np.int32)
-    for bad in ([1.0, -1.0, 2.0], [1.0, 0.5, 2.0], [1.0, np.nan, 2.0]):
+    # counts_check (R/utils.R:3-12): min(counts) >= 0 -- negative and non-finite values
+    for bad in ([1.0, -1.0, 2.0], [1.0, np.nan, 2.0], [1.0, np.inf, 2.0]):
         with pytest.raises(_lib.ChromVARError) as ei:
             engine.set_counts_csc(2, 2, ptr, idx, np.array(bad))
-        assert ei.value.code == _lib.CV_ERR_INVALID
+        assert ei.value.code == _lib.CV_ERR_INVALID and "counts_check" in str(ei.value)
+    # fractional counts pass the reference's check; this engine (exact integer sums) does not take
+    # them and says so in its own words
+    with pytest.raises(_lib.ChromVARError) as ei:
+        engine.set_counts_csc(2, 2, ptr, idx, np.array([1.0, 0.5, 2.0]))
+    assert ei.value.code == _lib.CV_ERR_UNSUPPORTED and "fractional" in str(ei.value) and "counts_check" not in str(ei.value)
     with pytest.raises(_lib.ChromVARError):
         engine.set_counts_csc(2, 2, ptr, np.array([0, 5, 1], np.int32), np.ones(3))
 
