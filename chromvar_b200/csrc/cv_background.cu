@@ -28,6 +28,25 @@ struct GridParams {
   int bs;
 };
 
+// The front half's scalars stay on the device (no host round trip between its kernels): means,
+// Cholesky factor of the 2 x 2 covariance, ranges of the whitened coordinates, and the flags the host
+// reads once at the end of the call.
+struct FrontState {
+  double mx, my, r11, r12, r22, min1, max1, min2, max2;
+  uint32_t flags;           // 1: a peak without fragments, 2: covariance not positive definite
+  uint32_t pad;
+};
+enum { FRONT_ZERO_PEAK = 1u, FRONT_NOT_PD = 2u };
+
+__device__ __forceinline__ GridParams grid_from_state(const FrontState* st, int bs) {
+  GridParams g;
+  g.bs = bs;
+  g.min1 = st->min1; g.max1 = st->max1; g.min2 = st->min2; g.max2 = st->max2;
+  g.by1 = (g.max1 - g.min1) / (double)(bs - 1);   // seq(min, max, length.out = bs) (:134-137)
+  g.by2 = (g.max2 - g.min2) / (double)(bs - 1);
+  return g;
+}
+
 __device__ __forceinline__ double grid_line(double frm, double by, double to, int x, int n) {
   // base::seq(from, to, length.out = n): from + (0:(n-1)) * by with the last element = to
   if (x == n - 1) return to;
@@ -57,23 +76,55 @@ __device__ __forceinline__ double intensity(unsigned long long f) { return LOG ?
 template <bool LOG>
 __global__ void __launch_bounds__(RED_THREADS)
 k_front_sums(const unsigned long long* __restrict__ fpp, const double* __restrict__ bias, int P,
-             double* __restrict__ partial) {
+             double* __restrict__ partial, FrontState* st) {
   __shared__ double sh[2 * RED_THREADS];
   double v[2] = {0.0, 0.0};
+  bool zero = false;
   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < P; i += gridDim.x * RED_THREADS) {
+    if (fpp[i] == 0ull) zero = true;
     v[0] += intensity<LOG>(fpp[i]);
     v[1] += bias[i];
   }
+  if (zero) atomicOr(&st->flags, FRONT_ZERO_PEAK);
   block_reduce_sum<2>(v, sh);
   if (threadIdx.x == 0) { partial[blockIdx.x * 2] = v[0]; partial[blockIdx.x * 2 + 1] = v[1]; }
+}
+
+// the final stages of the reductions, one thread, blocks summed in index order (what the host loop
+// did before): stage 0 means, 1 covariance -> chol (upper-triangular R with t(R) R = cov), 2 ranges
+__global__ void k_front_finish(const double* __restrict__ partial, int G, int P, int stage, FrontState* st) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (stage == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < G; ++i) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
+    st->mx = a / (double)P;
+    st->my = b / (double)P;
+  } else if (stage == 1) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = 0; i < G; ++i) { a += partial[i * 3]; b += partial[i * 3 + 1]; c += partial[i * 3 + 2]; }
+    const double c11 = a / (double)(P - 1), c12 = b / (double)(P - 1), c22 = c / (double)(P - 1);   // stats::cov, n-1 (:130)
+    const double r11 = sqrt(c11);
+    const double r12 = c12 / r11;
+    const double r22 = sqrt(c22 - r12 * r12);
+    st->r11 = r11; st->r12 = r12; st->r22 = r22;
+    if (!(r11 > 0.0) || !(r22 > 0.0)) atomicOr(&st->flags, FRONT_NOT_PD);
+  } else {
+    double m0 = partial[0], m1 = partial[1], m2 = partial[2], m3 = partial[3];
+    for (int b = 1; b < G; ++b) {
+      m0 = fmin(m0, partial[b * 4 + 0]); m1 = fmax(m1, partial[b * 4 + 1]);
+      m2 = fmin(m2, partial[b * 4 + 2]); m3 = fmax(m3, partial[b * 4 + 3]);
+    }
+    st->min1 = m0; st->max1 = m1; st->min2 = m2; st->max2 = m3;
+  }
 }
 
 template <bool LOG>
 __global__ void __launch_bounds__(RED_THREADS)
 k_front_cov(const unsigned long long* __restrict__ fpp, const double* __restrict__ bias, int P,
-            double mx, double my, double* __restrict__ partial) {
+            const FrontState* __restrict__ st, double* __restrict__ partial) {
   __shared__ double sh[3 * RED_THREADS];
   double v[3] = {0.0, 0.0, 0.0};
+  const double mx = st->mx, my = st->my;
   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < P; i += gridDim.x * RED_THREADS) {
     double dx = intensity<LOG>(fpp[i]) - mx, dy = bias[i] - my;
     v[0] += dx * dx; v[1] += dx * dy; v[2] += dy * dy;
@@ -88,9 +139,10 @@ k_front_cov(const unsigned long long* __restrict__ fpp, const double* __restrict
 template <bool LOG>
 __global__ void __launch_bounds__(RED_THREADS)
 k_front_transform(const unsigned long long* __restrict__ fpp, const double* __restrict__ bias,
-                  int P, double r11, double r12, double r22, double* __restrict__ T,
+                  int P, const FrontState* __restrict__ st, double* __restrict__ T,
                   double* __restrict__ partial) {
   __shared__ double sh[4 * RED_THREADS];
+  const double r11 = st->r11, r12 = st->r12, r22 = st->r22;
   double mn1 = INFINITY, mx1 = -INFINITY, mn2 = INFINITY, mx2 = -INFINITY;
   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < P; i += gridDim.x * RED_THREADS) {
     double y1 = intensity<LOG>(fpp[i]) / r11;
@@ -130,10 +182,11 @@ __device__ __forceinline__ int nearest_line(double t, double frm, double by, dou
 
 // bin_membership (0-based) = nabor::knn(bin_data, trans, k = 1) on the product grid (:139-147):
 // bin id = x * bs + y with x the intensity axis.
-__global__ void k_membership(const double* __restrict__ T, int P, GridParams g,
+__global__ void k_membership(const double* __restrict__ T, int P, const FrontState* __restrict__ st, int bs,
                              int32_t* __restrict__ memb0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
+  const GridParams g = grid_from_state(st, bs);
   int x = nearest_line(T[i], g.min1, g.by1, g.max1, g.bs);
   int y = nearest_line(T[(int64_t)P + i], g.min2, g.by2, g.max2, g.bs);
   memb0[i] = x * g.bs + y;
@@ -235,11 +288,14 @@ __device__ __forceinline__ double dnorm0(double x, double sigma) {
 // else dnorm(euc_dist(bin_i, bin_j), 0, w) on the grid (R/background_peaks.R:144-145).
 #define CDF_THREADS 256
 __global__ void __launch_bounds__(CDF_THREADS)
-k_bin_cdf(const double* __restrict__ binp, GridParams g, double w, int nb,
+k_bin_cdf(const double* __restrict__ binp, const FrontState* __restrict__ fst, int bs, double w, int nb,
           const uint32_t* __restrict__ density, double* __restrict__ cdf,
           double* __restrict__ prob, int all_rows) {
   __shared__ double sh[CDF_THREADS];
   const int i = blockIdx.x;
+  GridParams g = {};
+  g.bs = 1;
+  if (!binp) g = grid_from_state(fst, bs);
   if (!all_rows && density[i] == 0) return;
   const int chunk = (nb + CDF_THREADS - 1) / CDF_THREADS;
   const int j0 = threadIdx.x * chunk, j1 = min(nb, j0 + chunk);
@@ -328,7 +384,7 @@ __global__ void k_u32_to_f64(const uint32_t* __restrict__ in, double* __restrict
 // buffers in h->bk[]: 0 bias, 1 T, 2 memb0, 3 partial, 4 local_rank, 5 blockhist, 6 density,
 // 7 start, 8 sorted, 9 cdf, 10 prob, 11 out, 12 density f64
 static int sample_from_bins(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
-                            const double* d_binp, GridParams g, double w, int niter,
+                            const double* d_binp, const FrontState* d_state, int bs, double w, int niter,
                             int32_t* host_out, double* host_binprob, double* host_density) {
   const int nblk = (int)((P + RANK_CHUNK - 1) / RANK_CHUNK);
   CV_TRY(cv_ensure(h, h->bk[4], (size_t)P * 4));
@@ -352,7 +408,7 @@ static int sample_from_bins(cv_handle* h, int64_t P, const int32_t* d_memb0, int
     CV_TRY(cv_ensure(h, h->bk[10], (size_t)nb * nb * 8));
     d_prob = h->bk[10].as<double>();
   }
-  CV_LAUNCH(h, k_bin_cdf, (unsigned)nb, CDF_THREADS, 0, d_binp, g, w, (int)nb, h->bk[6].as<uint32_t>(),
+  CV_LAUNCH(h, k_bin_cdf, (unsigned)nb, CDF_THREADS, 0, d_binp, d_state, bs, w, (int)nb, h->bk[6].as<uint32_t>(),
             h->bk[9].as<double>(), d_prob, host_binprob ? 1 : 0);
   const int64_t total = P * niter;
   CV_LAUNCH(h, k_bg_sample, (unsigned)((total + 255) / 256), 256, 0, d_memb0, (int)P, (int)nb,
@@ -377,9 +433,7 @@ int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_
                          const double* d_binp_colmajor, const double* d_bin_xy, double w, int niter,
                          int32_t* host_out, double* host_binprob, double* host_density) {
   (void)d_bin_xy;
-  GridParams g = {};
-  g.bs = 1;
-  return sample_from_bins(h, P, d_memb0, nb, d_binp_colmajor, g, w, niter, host_out, host_binprob,
+  return sample_from_bins(h, P, d_memb0, nb, d_binp_colmajor, nullptr, 1, w, niter, host_out, host_binprob,
                           host_density);
 }
 
@@ -400,59 +454,52 @@ int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm) {
   const int64_t P = h->P;
   if (P < 2) CV_FAIL(h, CV_ERR_INVALID, "need at least two peaks");
   const unsigned long long* fpp = h->peak_tot.as<unsigned long long>();
-
-  // (:122-125, :183-184) every peak needs a fragment
-  {
-    std::vector<unsigned long long> tot((size_t)P);
-    CV_CUDA(h, cudaMemcpyAsync(tot.data(), fpp, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
-    CV_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int64_t i = 0; i < P; ++i)
-      if (tot[(size_t)i] == 0) CV_FAIL(h, CV_ERR_INVALID, "All peaks must have at least one fragment in one sample");
-  }
   for (int64_t i = 0; i < P; ++i)
     if (!(bias[i] == bias[i]) || isinf(bias[i])) CV_FAIL(h, CV_ERR_INVALID, "bias holds a non-finite value at peak %lld", (long long)(i + 1));
 
   CV_TRY(cv_ensure(h, h->bk[0], (size_t)P * 8));
   CV_TRY(cv_ensure(h, h->bk[1], (size_t)P * 2 * 8));
-  CV_TRY(cv_ensure(h, h->bk[3], (size_t)RED_BLOCKS * 4 * 8));
+  CV_TRY(cv_ensure(h, h->bk[3], (size_t)RED_BLOCKS * 4 * 8 + sizeof(FrontState)));
   double* d_bias = h->bk[0].as<double>();
   double* d_T = h->bk[1].as<double>();
   double* d_part = h->bk[3].as<double>();
+  FrontState* d_st = reinterpret_cast<FrontState*>(d_part + RED_BLOCKS * 4);
   CV_CUDA(h, cudaMemcpyAsync(d_bias, bias, (size_t)P * 8, cudaMemcpyHostToDevice, h->stream));
   CV_CUDA(h, cudaEventRecord(h->ev[6], h->stream));
+  CV_CUDA(h, cudaMemsetAsync(d_st, 0, sizeof(FrontState), h->stream));
   const int G = (int)std::min<int64_t>(RED_BLOCKS, (P + RED_THREADS - 1) / RED_THREADS);
-  std::vector<double> part((size_t)RED_BLOCKS * 4);
 
-  if (log_intensity) CV_LAUNCH(h, k_front_sums<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part);
-  else CV_LAUNCH(h, k_front_sums<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part);
-  CV_CUDA(h, cudaMemcpyAsync(part.data(), d_part, (size_t)G * 2 * 8, cudaMemcpyDeviceToHost, h->stream));
-  CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  const double mx = sum_partials(part, 2, 0, G) / (double)P, my = sum_partials(part, 2, 1, G) / (double)P;
+  // sums -> means -> covariance -> chol -> forward solve + ranges: every scalar stays on the device
+  // (k_front_finish), so the seven launches queue without a host round trip in between
+  if (log_intensity) CV_LAUNCH(h, k_front_sums<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part, d_st);
+  else CV_LAUNCH(h, k_front_sums<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part, d_st);
+  CV_LAUNCH(h, k_front_finish, 1, 32, 0, d_part, G, (int)P, 0, d_st);
+  if (log_intensity) CV_LAUNCH(h, k_front_cov<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_part);
+  else CV_LAUNCH(h, k_front_cov<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_part);
+  CV_LAUNCH(h, k_front_finish, 1, 32, 0, d_part, G, (int)P, 1, d_st);
+  if (log_intensity) CV_LAUNCH(h, k_front_transform<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_T, d_part);
+  else CV_LAUNCH(h, k_front_transform<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_T, d_part);
+  CV_LAUNCH(h, k_front_finish, 1, 32, 0, d_part, G, (int)P, 2, d_st);
+  if (mm) {                                              // a caller that needs the ranges on the host
+    CV_TRY(cv_whiten_verdict(h, log_intensity));
+    FrontState hs;
+    CV_CUDA(h, cudaMemcpy(&hs, d_st, sizeof(hs), cudaMemcpyDeviceToHost));
+    mm[0] = hs.min1; mm[1] = hs.max1; mm[2] = hs.min2; mm[3] = hs.max2;
+  }
+  return CV_OK;
+}
 
-  if (log_intensity) CV_LAUNCH(h, k_front_cov<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, mx, my, d_part);
-  else CV_LAUNCH(h, k_front_cov<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, mx, my, d_part);
-  CV_CUDA(h, cudaMemcpyAsync(part.data(), d_part, (size_t)G * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+// reads the front half's flags (one stream synchronisation): the reference's stop() conditions
+int cv_whiten_verdict(cv_handle* h, int log_intensity) {
+  FrontState hs;
+  const FrontState* d_st = reinterpret_cast<const FrontState*>(h->bk[3].as<double>() + RED_BLOCKS * 4);
+  CV_CUDA(h, cudaMemcpyAsync(&hs, d_st, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  const double c11 = sum_partials(part, 3, 0, G) / (double)(P - 1);   // stats::cov, n-1 (:130)
-  const double c12 = sum_partials(part, 3, 1, G) / (double)(P - 1);
-  const double c22 = sum_partials(part, 3, 2, G) / (double)(P - 1);
-  // chol(): upper-triangular R with t(R) R = cov
-  const double r11 = sqrt(c11);
-  const double r12 = c12 / r11;
-  const double r22 = sqrt(c22 - r12 * r12);
-  if (!(r11 > 0.0) || !(r22 > 0.0))
+  // (:122-125, :183-184) every peak needs a fragment
+  if (hs.flags & FRONT_ZERO_PEAK) CV_FAIL(h, CV_ERR_INVALID, "All peaks must have at least one fragment in one sample");
+  if (hs.flags & FRONT_NOT_PD)
     CV_FAIL(h, CV_ERR_INVALID, "covariance of (%sfragments, bias) is not positive definite (chol would fail)",
             log_intensity ? "log10 " : "");
-
-  if (log_intensity) CV_LAUNCH(h, k_front_transform<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, r11, r12, r22, d_T, d_part);
-  else CV_LAUNCH(h, k_front_transform<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, r11, r12, r22, d_T, d_part);
-  CV_CUDA(h, cudaMemcpyAsync(part.data(), d_part, (size_t)G * 4 * 8, cudaMemcpyDeviceToHost, h->stream));
-  CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  mm[0] = part[0]; mm[1] = part[1]; mm[2] = part[2]; mm[3] = part[3];
-  for (int b = 1; b < G; ++b) {
-    mm[0] = fmin(mm[0], part[(size_t)b * 4 + 0]); mm[1] = fmax(mm[1], part[(size_t)b * 4 + 1]);
-    mm[2] = fmin(mm[2], part[(size_t)b * 4 + 2]); mm[3] = fmax(mm[3], part[(size_t)b * 4 + 3]);
-  }
   return CV_OK;
 }
 
@@ -465,19 +512,16 @@ extern "C" int cv_background_peaks(cv_handle* h, const double* bias, int niter, 
   if (bs > 200) CV_FAIL(h, CV_ERR_UNSUPPORTED, "bs > 200 is not supported");
   const int64_t P = h->P;
   const int64_t nb = (int64_t)bs * bs;
-  double mm[4];
-  CV_TRY(cv_whiten(h, bias, 1, mm));
+  CV_TRY(cv_whiten(h, bias, 1, nullptr));
   CV_TRY(cv_ensure(h, h->bk[2], (size_t)P * 4));
   double* d_T = h->bk[1].as<double>();
   int32_t* d_memb = h->bk[2].as<int32_t>();
-  GridParams g;
-  g.bs = bs;
-  g.min1 = mm[0]; g.max1 = mm[1]; g.min2 = mm[2]; g.max2 = mm[3];
-  g.by1 = (g.max1 - g.min1) / (double)(bs - 1);   // seq(min, max, length.out = bs) (:134-137)
-  g.by2 = (g.max2 - g.min2) / (double)(bs - 1);
-
-  CV_LAUNCH(h, k_membership, (unsigned)((P + 255) / 256), 256, 0, d_T, (int)P, g, d_memb);
-  CV_TRY(sample_from_bins(h, P, d_memb, nb, nullptr, g, w, niter, out_bg, out_binprob, out_density));
+  const FrontState* d_st = reinterpret_cast<const FrontState*>(h->bk[3].as<double>() + RED_BLOCKS * 4);
+  CV_LAUNCH(h, k_membership, (unsigned)((P + 255) / 256), 256, 0, d_T, (int)P, d_st, bs, d_memb);
+  // (a zero peak makes log10 -inf and everything behind it garbage, but nothing out of bounds: bins are
+  // clamped to the grid; the verdict below discards the result)
+  CV_TRY(sample_from_bins(h, P, d_memb, nb, nullptr, d_st, bs, w, niter, out_bg, out_binprob, out_density));
+  CV_TRY(cv_whiten_verdict(h, 1));
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
   h->st.ms_background = ms;

@@ -230,7 +230,8 @@ void cv_narrower_copies_wait(cv_narrower* nw);
 int cv_narrower_wait(cv_narrower* nw, int64_t e0, int64_t e1);
 void cv_narrower_finish(cv_narrower* nw);
 int cv_settle(cv_handle* h);            // cv_deviations.cu: waits for a pending replay and collects its verdict
-int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm);
+int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm);   // mm == NULL: no host synchronisation
+int cv_whiten_verdict(cv_handle* h, int log_intensity);
 int cv_sample_background(cv_handle* h, int64_t P, const int32_t* d_memb0, int64_t nb,
                          const double* d_binp_colmajor, const double* d_bin_xy, double w,
                          int niter, int32_t* host_out, double* host_binprob, double* host_density);
