@@ -6,6 +6,7 @@
 //   counts_check                                                     R/utils.R:3-12
 //   compute_expectations_core                                        R/compute_deviations.R:415-448
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "cv_internal.cuh"
 
@@ -87,6 +88,7 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
   cv_handle* h = new cv_handle();
   h->device = device;
   h->seed = seed;
+  h->opt_trace = getenv("CV_TRACE") != nullptr;
   h->num_sms = prop.multiProcessorCount;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -598,20 +598,30 @@ static int choose_path(cv_handle* h, uint32_t max_val, int64_t want_chunk, bool 
     if (!feasible) CV_FAIL(h, CV_ERR_UNSUPPORTED, "dense path requested but not applicable: %s", why.c_str());
     *use_dense = 1;
   } else if (h->opt_path == 0 && feasible) {
+    // rate of the row-gather kernel in entry updates per ms: the last sparse run on this handle measured
+    // it (deviations_run), 2.7e8 (config 2, round 1) until then
     const double updates = (double)(h->B + 1) * (double)h->nnzA * ((double)h->nnz / (double)h->P);
-    const double sparse_ms = updates / 2.7e8 + 0.3;
+    const double sparse_ms = updates / h->sparse_rate + 0.3;
     *use_dense = cv_dense_cost_ms(h, *pl) < sparse_ms;
   }
   return CV_OK;
 }
 
 // Cell-chunk boundaries of the dense path (multiples of 256 cells, each <= pl.chunk_cells).
-static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int64_t N, bool streaming) {
+static std::vector<int64_t> chunk_bounds(cv_handle* h, const DensePlan& pl, int64_t N, bool streaming, bool host_io) {
   const int64_t chunk = pl.chunk_cells;
   std::vector<int64_t> b;
   const int64_t U = (N + 255) / 256, maxU = chunk / 256;
   const int n_min = (int)((U + maxU - 1) / maxU);
-  const int n = std::max<int>(n_min, (int)std::min<int64_t>(3, U));
+  // chunks exist to overlap host copies with the GEMMs; a call whose inputs and results stay on the
+  // device takes as few as the operand budget allows (one launch ramp, one set of overflow columns)
+  const int n = host_io ? std::max<int>(n_min, (int)std::min<int64_t>(3, U)) : n_min;
+  if (!host_io && h->opt_chunk <= 0) {
+    const int64_t per = ((U + n_min - 1) / n_min) * 256;           // equal chunks
+    for (int64_t c = 0; c < N; c += per) b.push_back(c);
+    b.push_back(N);
+    return b;
+  }
   if (h->opt_chunk > 0 || !pl.pair || n != 3 || U < 6 || U > 4096) {
     for (int64_t c = 0; c < N; c += chunk) b.push_back(c);
     b.push_back(N);
@@ -674,7 +684,8 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     // about three GEMM launches per call: host copies overlap them chunk by chunk (config 2, e2m1
     // kernel: e2e 20.2 / 19.6 / 22.4 ms with 4 / 3 / 2 chunks, kernels alone 17.5 / 17.0 / 16.6 ms;
     // profiles/r01p); buffers for up to half the cells, boundaries from chunk_bounds()
-    const int64_t want_chunk = std::max<int64_t>((N + 1) / 2, 1024);
+    const bool host_io_plan = streaming || (io && (io->out_dev || io->out_z));
+    const int64_t want_chunk = host_io_plan ? std::max<int64_t>((N + 1) / 2, 1024) : 0;
     CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
   }
 
@@ -711,12 +722,12 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     // chunk boundaries: uniform when the caller fixed the chunk ("cell_chunk"); otherwise about three
     // chunks whose work items fill whole waves of CTA pairs (config 2: 40 units of 256 cells x 97
     // super-groups on 74 pairs: 8 + 16 + 16 units = 53 waves, 14 + 13 + 13 = 55), the small one first
-    std::vector<int64_t> bounds = chunk_bounds(h, pl, N, streaming);
+    std::vector<int64_t> bounds = chunk_bounds(h, pl, N, streaming, streaming || (io && (io->out_dev || io->out_z)));
     const int n_chunks = (int)bounds.size() - 1;
     dense_chunks_used = n_chunks;
     std::vector<cudaEvent_t> ev_up((size_t)n_chunks), ev_done((size_t)n_chunks), ev_dn((size_t)n_chunks);
     for (int i = 0; i < n_chunks; ++i) { ev_up[i] = pool_event(h); ev_done[i] = pool_event(h); ev_dn[i] = pool_event(h); }
-    const bool trace = getenv("CV_TRACE") != nullptr;
+    const bool trace = h->opt_trace != 0;                 // CV_TRACE, read once in cv_create
     cudaEvent_t ev_t0 = pool_event(h), ev_prep = pool_event(h);
     CV_CUDA(h, cudaEventRecord(ev_t0, h->stream));         // origin of the timeline; orders the upload stream
     auto lo = [&](int i) { return bounds[(size_t)i]; };
@@ -985,6 +996,8 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     // compulsory one-time traffic (layout, annotation lists, background rows, outputs)
     h->st.contract_bytes = (int64_t)upd * 4 + h->n_entries * 4 + (int64_t)T * P * 4 +
                            h->nnzA * 4 * T + (int64_t)P * B * 4 + 2 * K * N * 8;
+    if (upd > 10000000ull && ms[CV_SPAN_CONTRACT] > 0.05)      // feeds the cost model of later calls
+      h->sparse_rate = (double)upd / ms[CV_SPAN_CONTRACT];
     h->st.contract_flops = 0;
     h->st.path = 0;
     h->st.acc_bytes = wide ? 8 : 4;

@@ -181,6 +181,8 @@ struct cv_handle {
   int opt_band = 0;            // dense path: groups per raster band (0 = default)
   int opt_debug_no_tma = 0;    // experiment only: GEMM without operand loads (garbage results)
   int opt_check_zero = 1;      // reject peaks without fragments (off for shards of a larger matrix)
+  int opt_trace = 0;           // CV_TRACE in the environment at cv_create: timeline of the streamed call on stderr
+  double sparse_rate = 2.7e8;  // row-gather kernel, entry updates per ms: measured by the last sparse run (choose_path)
 
   // background sampler / compat-routine buffers (cv_background.cu, cv_compat.cu)
   DevBuf bk[16];
