@@ -226,6 +226,7 @@ struct DenseParams {
   int Ga, Gb, n_sg;
   const uint32_t* n_kblocks_dev;
   uint32_t* sync_ctr;        // one counter per (wave of work items, sub-tile): producers start together
+  int sync_lag;              // 0: wait for this sub-tile's counter, 1: for the previous sub-tile's
 };
 
 struct DWelford { double n, mean, m2; };

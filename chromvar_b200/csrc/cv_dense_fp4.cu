@@ -35,6 +35,7 @@
 #define F4_SG_ROWS (F4_NA + F4_NB)
 #define F4_SF_COL 464                    // first TMEM column of the scale bytes
 #define F4_SMEM_BYTES DN_SMEM2_BYTES
+#define F4_SYNC_SLOTS 65536              // u32 words of f4_sync: one per (wave, sub-tile) + the last = "lockstep given up"
 #define F4_THREADS 384                   // warps 0-3: TMA / MMA / TMEM allocation, warps 4-11: epilogue (two per TMEM lane quarter)
 enum { F4_FAIL_CAPACITY = 1u, F4_FAIL_DUPLICATE = 2u, F4_FAIL_NIBBLE = 4u };
 
@@ -457,17 +458,34 @@ k_dense_contract_fp4(const __grid_constant__ CUtensorMap map_c, const __grid_con
           if (prm.sync_ctr) {
             // all producers start a sub-tile together: the CTAs that share an operand stream then ask
             // for the same k-block within a few microseconds and L2 serves all but the first
-            // (without it the pairs drift apart by more than L2 holds and re-read from DRAM)
+            // (without it the pairs drift apart by more than L2 holds and re-read from DRAM).
+            // sync_lag = 1: a producer only waits for everybody to have STARTED the previous sub-tile, so
+            // nobody stalls for the slowest pair at every boundary while the drift stays below one sub-tile.
             const int64_t wave = (item - pair_id) / n_pairs;
-            const int64_t left = prm.n_tiles - wave * n_pairs;
-            const uint32_t target = 2u * (uint32_t)(left < n_pairs ? left : n_pairs);
-            uint32_t* ctr = prm.sync_ctr + (wave * 2 + half);
-            atomicAdd(ctr, 1u);
-            uint32_t seen;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-              if (seen < target) __nanosleep(64);
-            } while (seen < target);
+            const int64_t idx = wave * 2 + half;
+            atomicAdd(prm.sync_ctr + idx, 1u);
+            const int64_t widx = idx - prm.sync_lag;
+            if (widx >= 0) {
+              const int64_t left = prm.n_tiles - (widx >> 1) * n_pairs;
+              const uint32_t target = 2u * (uint32_t)(left < n_pairs ? left : n_pairs);
+              uint32_t* ctr = prm.sync_ctr + widx;
+              uint32_t* gave_up = prm.sync_ctr + F4_SYNC_SLOTS - 1;
+              uint32_t seen, off = 0u;
+              int spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+                if (seen >= target) break;
+                // The rendezvous assumes every CTA pair of the wave is resident.  When something else holds
+                // SMs (another engine's GEMM on the same GPU, a long auxiliary kernel) some pairs have not
+                // started yet and would be waited for forever by pairs that in turn keep their SMs: after
+                // ~2 ms of waiting the launch gives the lockstep up for good (a flag word all producers
+                // watch) and every pair runs free -- slower through L2, never stuck.
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(off) : "l"(gave_up) : "memory");
+                if (off) break;
+                __nanosleep(64);
+                if (++spins > 16384) { atomicExch(gave_up, 1u); break; }
+              } while (true);
+            }
           }
           for (int kb = 0; kb < n_kb; ++kb) {
             mbar_wait_relaxed(empty_bar + s, ph ^ 1u, 32);
@@ -691,6 +709,7 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   DenseParams prm = prm_in;
   prm.Ga = pl.Ga; prm.Gb = pl.Gb; prm.n_sg = pl.n_sg;
   prm.sync_ctr = nullptr;
+  prm.sync_lag = h->opt_lockstep == 2 ? 1 : 0;
   if (h->opt_lockstep) {
     CV_TRY(cv_ensure(h, h->f4_sync, 65536 * 4));
     prm.sync_ctr = h->f4_sync.as<uint32_t>();
@@ -703,8 +722,11 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   if (prm.n_tiles < pairs) pairs = (int)prm.n_tiles;
   if (prm.sync_ctr) {
     const int64_t waves = (prm.n_tiles + pairs - 1) / pairs;
-    if (2 * waves > 65536) prm.sync_ctr = nullptr;
-    else CV_CUDA(h, cudaMemsetAsync(prm.sync_ctr, 0, (size_t)(2 * waves) * 4, h->stream));
+    if (2 * waves >= F4_SYNC_SLOTS - 1) prm.sync_ctr = nullptr;
+    else {
+      CV_CUDA(h, cudaMemsetAsync(prm.sync_ctr, 0, (size_t)(2 * waves) * 4, h->stream));
+      CV_CUDA(h, cudaMemsetAsync(prm.sync_ctr + F4_SYNC_SLOTS - 1, 0, 4, h->stream));     // the "lockstep given up" word
+    }
   }
   if (fixed_point_epilogue) {
     CV_CUDA(h, cudaFuncSetAttribute(k_dense_contract_fp4<DN_EPI_FUSED32>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -179,3 +179,36 @@ def test_more_devices_than_cells_and_single_block():
         assert_close(res["z"], ref["z"], "z")
     finally:
         m.close()
+
+
+def test_two_engines_on_one_gpu_do_not_wait_for_each_other_forever():
+    """The e2m1 GEMM's producers rendezvous through a global counter, which assumes all CTA pairs of a
+    launch are resident.  Two engines on ONE GPU whose GEMMs each want every SM break that assumption
+    (each gets part of the SMs and would wait for the rest forever): the rendezvous gives up after a
+    few ms and the launch runs free.  Results must not change."""
+    from chromvar_b200 import _lib, synthetic
+    d = synthetic.make_config("small", N=5120, K=96)
+    C = d["counts"].tocsc()
+    P, N = C.shape
+    ptr, idx = d["annoptr"], d["annoidx"].astype(np.int32)
+    rng = np.random.default_rng(4)
+    bg = np.asfortranarray(rng.integers(1, P + 1, size=(P, 50)).astype(np.int32))
+    e = np.asarray(C.sum(axis=1)).ravel() / C.sum()
+    one = _lib.Handle(0, seed=1)
+    one.set_option("path", 2)
+    one.set_option("dense_epilogue", 1)
+    one.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    ref = one.deviations(ptr, idx, bg, e)
+    assert one.stats()["operand_bits"] == 4
+    one.close()
+    m = _lib.MultiHandle([0, 0], seed=1)
+    try:
+        m.set_option("path", 2)
+        m.set_option("dense_epilogue", 1)
+        m.set_counts([C])
+        for _ in range(4):                                # both shards' GEMMs are in flight together
+            res = m.deviations(ptr, idx, bg, e)
+            for key in ("dev", "z"):
+                assert np.array_equal(res[key], ref[key], equal_nan=True), key
+    finally:
+        m.close()
