@@ -387,11 +387,13 @@ def roofline_of(st, c_ms, total_ms_per_step, flops_alg, peaks, peaks_kind, sm_mh
     share = c_ms / total_ms_per_step if total_ms_per_step else None
     if st["path"] == 1:
         fp4 = st.get("operand_bits") == 4
-        launches = max(1, st["n_cell_tiles"] * max(st["planes"], 1))
+        few = bool(st.get("few_cells"))
+        launches = 1 if few else max(1, st["n_cell_tiles"] * max(st["planes"], 1))
         achieved = flops_alg / (c_ms * 1e-3) / 1e12
         peak_issue = issue_peak_tflops(sm_mhz or 1965.0, 4 if fp4 else 8)
         mult = 4.0 if fp4 else 2.0
-        kname = "k_dense_contract_fp4" if fp4 else ("k_dense_contract_pair" if st["cell_tile"] == 256 else "k_dense_contract")
+        kname = "k_gather_contract" if few else "k_dense_contract_fp4" if fp4 else (
+            "k_dense_contract_pair" if st["cell_tile"] == 256 else "k_dense_contract")
         tensor = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak_issue, "unit": "TFLOP/s",
                   "frac": achieved / peak_issue,
                   "peak_kind": "probe-measured tcgen05 issue rate of this instruction shape (%s, 128.1 cycles per "
@@ -408,7 +410,10 @@ def roofline_of(st, c_ms, total_ms_per_step, flops_alg, peaks, peaks_kind, sm_mh
                   "algorithmic_ops_per_launch": flops_alg / launches, "padded_ops_per_step": st["contract_flops"],
                   "share_of_step": share, "operand_bits": st.get("operand_bits"),
                   "overflow_columns_per_step": st.get("overflow_columns")}
-        if shape is not None:
+        if few:
+            tensor["note"] = ("few-cells contraction: counts rows gathered per iteration into an MN-major operand, both u8 digit "
+                              "planes in one pass, no stacked operand; the kernel span includes the finishing kernel")
+        if shape is not None and not few:
             P, N, K = shape
             I = NITER + 1
             if fp4:

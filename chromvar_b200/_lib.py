@@ -48,7 +48,7 @@ class StageStats(C.Structure):
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64),
         ("path", C.c_int32), ("cell_tile", C.c_int32), ("n_cell_tiles", C.c_int32),
         ("acc_bytes", C.c_int32), ("planes", C.c_int32), ("epilogue", C.c_int32),
-        ("operand_bits", C.c_int32), ("overflow_columns", C.c_int32),
+        ("operand_bits", C.c_int32), ("overflow_columns", C.c_int32), ("few_cells", C.c_int32), ("reserved", C.c_int32),
     ]
 
     def as_dict(self):

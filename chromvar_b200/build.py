@@ -18,7 +18,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libchromvar_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["cv_counts.cu", "cv_deviations.cu", "cv_dense.cu", "cv_dense_fp4.cu", "cv_dense_build.cu", "cv_background.cu", "cv_knn.cu", "cv_compat.cu", "cv_multi.cu", "cv_hostnarrow.cpp"]
+SOURCES = ["cv_counts.cu", "cv_deviations.cu", "cv_dense.cu", "cv_dense_fp4.cu", "cv_dense_build.cu", "cv_dense_gather.cu", "cv_background.cu", "cv_knn.cu", "cv_compat.cu", "cv_multi.cu", "cv_hostnarrow.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

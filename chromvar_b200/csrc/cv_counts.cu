@@ -182,6 +182,7 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!strcmp(key, "dense_fp4")) { h->opt_fp4 = value < 0 ? -1 : (value ? 1 : 0); return CV_OK; }
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
+  if (!strcmp(key, "small_n_gather")) { h->opt_gather = value < 0 ? -1 : (value != 0); return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }
   if (!strcmp(key, "tail_chunk")) { h->opt_tail_chunk = value != 0; return CV_OK; }
   if (!strcmp(key, "host_narrow")) {
@@ -323,7 +324,7 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   const unsigned full = 0xffffffffu;
   int lane = threadIdx.x & 31;
   uint32_t bad = 0, vmax = 0;
-  bool unsorted = false;
+  bool unsorted = false, dup = false;
   int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (int64_t base = e_begin + warp_id * 32; base < nnz; base += warps_total * 32) {
@@ -336,7 +337,11 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
       int r = rowidx[e];
       // flags[4]: some column lists its rows out of order (legal, just rare: R's dgCMatrix and scipy keep
       // them sorted); the per-range builders of the dense path then scan whole columns instead of searching
-      if (e > __ldg(colptr + c) && rowidx[e - 1] > r) unsorted = true;
+      if (e > __ldg(colptr + c)) {
+        const int rp = rowidx[e - 1];
+        if (rp > r) unsorted = true;
+        if (rp == r) dup = true;                          // adjacent duplicates (sorted input); unsorted input counts as suspect
+      }
       if (r < 0 || r >= P) { bad |= FLAG_BADROW; v = 0; }
       else if (v) atomicAdd(peak_tot + r, (unsigned long long)v);
       val[e] = v;
@@ -362,6 +367,7 @@ k_counts_sums(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   bad |= __shfl_xor_sync(full, bad, 2);
   bad |= __shfl_xor_sync(full, bad, 1);
   if (__any_sync(full, unsorted) && lane == 0) atomicOr(flags + 4, 1u);
+  if (__any_sync(full, dup) && lane == 0) atomicOr(flags + 4, 2u);
   if (lane == 0) {
     if (bad) atomicOr(flags + 0, bad);
     if (vmax) atomicMax(flags + 1, vmax);
@@ -803,9 +809,10 @@ static int counts_sums(cv_handle* h, int x_type) {
   CV_TRY(cv_counts_begin(h));
   CV_TRY(cv_counts_range(h, x_type, 0, h->nnz, 0, h->N));
   CV_TRY(cv_counts_finish_async(h));
-  uint32_t flags[4] = {0, 0, 0, 0};
-  CV_CUDA(h, cudaMemcpyAsync(flags, h->flags.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  uint32_t flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CV_CUDA(h, cudaMemcpyAsync(flags, h->flags.p, 32, cudaMemcpyDeviceToHost, h->stream));
   CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->cols_dup = flags[4] != 0u;                     // a duplicate row index, or rows out of order (not examined further)
   return cv_counts_verdict(h, flags);
 }
 

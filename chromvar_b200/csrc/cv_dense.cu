@@ -381,6 +381,13 @@ k_dense_finalize_sums(const DenseParams prm) {
   }
 }
 
+// launch of k_dense_finalize_sums for the other translation units (cv_dense_gather.cu)
+int cv_dense_finalize_sums(cv_handle* h, const DenseParams& prm) {
+  dim3 grid((unsigned)prm.n_cell_blocks, (unsigned)prm.K);
+  CV_LAUNCH(h, k_dense_finalize_sums, grid, 128, 0, prm);
+  return CV_OK;
+}
+
 // Fixed-point table of the integer epilogue: W[k][j] = round(2^F_k / E[k][j]) with F_k chosen so
 // that the largest entry of annotation k lies in [2^31, 2^32).  An annotation whose table holds a
 // zero or non-finite expectation sum cannot be scaled: flagged, the call then uses the fp64 epilogue.

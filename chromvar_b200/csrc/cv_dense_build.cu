@@ -521,7 +521,7 @@ __global__ void k_overlap_finish(const int64_t* __restrict__ annoptr, const unsi
 // #{p : bg[p, j] = q}; dflags[2]: largest multiplicity inside one list, 0xFFFF when a byte wrapped;
 // dflags[3]: a list repeats a peak -> the gather formulation does not apply, rebuild with scatter = 1).
 // Asynchronous; the caller reads the counters after its stream sync.
-int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
+int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tables_only) {
   const int64_t P = h->P, K = h->K;
   const int B = h->B, I = B + 1, G = pl.G;
   const int64_t Ppad = pl.Ppad;
@@ -533,9 +533,9 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   CV_LAUNCH(h, k_u32_max_db, 1024, 256, 0, h->tmp1.as<uint32_t>(), P * B, dflags + 1);
   CV_CUDA(h, cudaMemsetAsync(h->work_ctr.p, 0, 64, h->stream));
   // rows of a group that no (annotation, iteration) owns must be zero
-  if (!pl.fp4 && (G * I < DB_BLOCK_N || K % G))
+  if (!tables_only && !pl.fp4 && (G * I < DB_BLOCK_N || K % G))
     CV_LAUNCH(h, k_zero_pad_rows, pl.n_groups, 256, 0, h->dn_M.as<uint8_t>(), (int)K, G, I, Ppad);
-  if (scatter || h->opt_rows_scatter) {
+  if (!tables_only && (scatter || h->opt_rows_scatter)) {
     const int budget = h->max_smem_optin - 2048;
     const int chunk2 = (int)std::min<int64_t>(Ppad, ((budget / 2) / 128) * 128);   // two row chunks resident
     CV_CUDA(h, cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * chunk2));
@@ -550,8 +550,10 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   }
   const int64_t Kw = (K + 31) / 32;
   CV_TRY(cv_ensure(h, h->dn_abits, (size_t)Kw * P * 4));
-  CV_TRY(cv_ensure(h, h->dn_invptr, (size_t)(P * B + 1) * 4));
-  CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)P * B * 4));
+  if (!tables_only) {
+    CV_TRY(cv_ensure(h, h->dn_invptr, (size_t)(P * B + 1) * 4));
+    CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)P * B * 4));
+  }
   CV_TRY(cv_ensure(h, h->dn_E2, (size_t)P * I * 8));
   CV_TRY(cv_ensure(h, h->dn_ov, (size_t)K * 8));
   // Two streams: the operand rows (write-bound) on the compute stream; the expected-fraction table
@@ -563,6 +565,9 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   CV_LAUNCH(h, k_anno_bits, (unsigned)K, 256, 0, h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), (int)K, (int)P,
             h->dn_abits.as<uint32_t>(), dflags);
   CV_CUDA(h, cudaEventRecord(h->ev_aux[1], compute));                    // bit columns ready
+  if (tables_only) {
+    // few-cells path (cv_dense_gather.cu): bit columns and tables only, no stacked operand
+  } else if (true) {
   // inverse background map: counting sort of (iteration, destination peak)
   CV_TRY(cv_exclusive_scan_u32_async(h, h->tmp1.as<uint32_t>(), h->dn_invptr.as<uint32_t>(), P * B));
   CV_LAUNCH(h, k_inv_fill, (unsigned)((P * B + 255) / 256), 256, 0, h->bg_raw.as<int32_t>(), h->index_base, P * B,
@@ -573,6 +578,7 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
     dim3 grid((unsigned)((Ppad + GR_TQ - 1) / GR_TQ), (unsigned)I, (unsigned)Kw);
     CV_LAUNCH(h, k_dense_rows_gather, grid, GR_THREADS, 0, h->dn_abits.as<uint32_t>(), h->dn_invptr.as<uint32_t>(),
               h->dn_invsrc.as<int32_t>(), (int)K, (int)P, B, G, Ppad, h->dn_M.as<uint8_t>());
+  }
   }
   // ---- auxiliary stream ----
   h->stream = h->s_aux;
@@ -600,7 +606,8 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter) {
   } while (0);
   h->stream = compute;
   if (rc != CV_OK) CV_FAIL(h, rc, "launch on the auxiliary stream failed");
-  CV_CUDA(h, cudaStreamWaitEvent(compute, h->ev_aux[2], 0));               // the GEMM epilogue reads the table
+  if (!tables_only)                                                        // (few-cells path: only its finishing kernel waits)
+    CV_CUDA(h, cudaStreamWaitEvent(compute, h->ev_aux[2], 0));             // the GEMM epilogue reads the table
   h->aux_pending = true;
   return CV_OK;
 }

@@ -677,6 +677,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   for (int64_t k = 0; k < K; ++k) set_max = std::max(set_max, h->h_annoptr[k + 1] - h->h_annoptr[k]);
 
   int use_dense = 0, dense_chunks_used = 0;
+  bool use_gather = false;
   bool verdict_clean = false;
   uint32_t verdict_hf[16] = {};
   DensePlan pl;
@@ -686,7 +687,9 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     // profiles/r01p); buffers for up to half the cells, boundaries from chunk_bounds()
     const bool host_io_plan = streaming || (io && (io->out_dev || io->out_z));
     const int64_t want_chunk = host_io_plan ? std::max<int64_t>((N + 1) / 2, 1024) : 0;
-    CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
+    // few cells (bulk data): gathered counts rows instead of a stacked operand (cv_dense_gather.cu)
+    use_gather = !streaming && !h->cols_dup && (h->replaying ? h->replay_gather : cv_gather_applicable(h) != 0);
+    if (!use_gather) CV_TRY(choose_path(h, streaming ? 0u : h->max_val, want_chunk, streaming, &pl, &use_dense));
   }
 
   // ---- stage 1: validation and per-annotation tables ---------------------------------------------
@@ -717,6 +720,37 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   // ---- stage 2: operand layout + contraction + fused epilogue -----------------------------------
   int T = 0;
   bool wide = false;
+  if (use_gather) {
+    DensePlan plg;
+    plg.I = I;
+    plg.G = 1;
+    CV_TRY(cv_dense_build_rows(h, plg, 0, 1));               // bit columns + per-annotation tables (auxiliary stream)
+    uint32_t hf[16] = {};
+    if (!h->replaying) {
+      CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
+      CV_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (hf[CV_DFLAGS] & FLAG_BADIDX)
+        CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
+      if (hf[CV_DFLAGS + 3]) {
+        // a list repeats a peak: bit columns cannot hold the multiplicity -- the general paths take over
+        CV_CUDA(h, cudaStreamSynchronize(h->s_aux));
+        h->aux_pending = false;
+        CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));
+        use_gather = false;
+        const int64_t want_chunk = (io && (io->out_dev || io->out_z)) ? std::max<int64_t>((N + 1) / 2, 1024) : 0;
+        CV_TRY(choose_path(h, h->max_val, want_chunk, false, &pl, &use_dense));
+      }
+    }
+    if (use_gather) {
+      CV_TRY(cv_gather_run(h, keep_sums));
+      cv_span_begin(h, CV_SPAN_FINALIZE);
+      CV_TRY(enqueue_transposes(h, 0, N));
+      cv_span_end(h);
+      T = (int)((N + 127) / 128);
+      dense_chunks_used = 1;
+      verdict_clean = !keep_sums;
+    }
+  }
   if (use_dense) {
     const int64_t chunk = pl.chunk_cells;
     // chunk boundaries: uniform when the caller fixed the chunk ("cell_chunk"); otherwise about three
@@ -854,7 +888,7 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
       T = (int)((N + 127) / 128);
     }
   }
-  if (!use_dense) {
+  if (!use_dense && !use_gather) {
     if (h->aux_pending) {                                    // a dense attempt was abandoned
       CV_CUDA(h, cudaStreamSynchronize(h->s_aux));
       h->aux_pending = false;
@@ -979,7 +1013,19 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   h->st.ms_contract = ms[CV_SPAN_CONTRACT];
   h->st.ms_finalize = ms[CV_SPAN_FINALIZE];
   h->st.contract_updates = (int64_t)upd;
-  if (use_dense) {
+  h->st.few_cells = use_gather ? 1 : 0;
+  if (use_gather) {
+    h->st.contract_bytes = 0;
+    h->st.contract_flops = h->dn_flops;
+    h->st.path = 1;
+    h->st.acc_bytes = 4;
+    h->st.cell_tile = 256;
+    h->st.n_cell_tiles = 1;
+    h->st.planes = 2;
+    h->st.epilogue = 64;
+    h->st.operand_bits = 8;
+    h->st.overflow_columns = 0;
+  } else if (use_dense) {
     h->st.contract_bytes = 0;
     h->st.contract_flops = h->dn_flops;
     if (pl.fp4)                                            // + the overflow columns of every chunk
@@ -1009,8 +1055,9 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
   h->have_results = true;
   // a clean dense run on resident inputs (no fallback taken, nothing flagged): its verdict can be replayed
   // (not under an e2m1 veto either: the veto ends with this call, a replay would plan e2m1 operands again)
-  h->replay_valid = verdict_clean && use_dense && !h->f4_veto && !hf[CV_DFLAGS + 5] &&
+  h->replay_valid = verdict_clean && (use_dense || use_gather) && !h->f4_veto && !hf[CV_DFLAGS + 5] &&
                     !(hf[CV_DFLAGS] & (FLAG_ZEROPEAK | FLAG_BADIDX));
+  h->replay_gather = use_gather;
   if (h->replay_valid) memcpy(h->replay_hf, verdict_hf, 64);
   return CV_OK;
 }
@@ -1168,7 +1215,9 @@ int cv_deviations_view(cv_handle* h, const CscView& v, int64_t K, const int64_t*
   const int x_type = v.x_type;
   // the streamed pipeline needs the expectation up front and the dense path; otherwise (or when
   // the dense path turns out not to be exact for these inputs) the call is the plain sequence
-  bool try_stream = expectation != nullptr && h->opt_path != 1 && K >= 1 && annoptr && B >= 1 && B <= 255;
+  // (few cells: the plain sequence, whose resident call takes the gathered-rows path of cv_dense_gather.cu)
+  bool try_stream = expectation != nullptr && h->opt_path != 1 && K >= 1 && annoptr && B >= 1 && B <= 255 &&
+                    !(N <= 256 && h->opt_gather != 0 && (double)K * (B + 1) * (double)P > 1.0e9);
   int64_t nnz = 0;
   if (try_stream) {
     nnz = v.cp[(size_t)N];

@@ -82,6 +82,7 @@ struct cv_handle {
   bool replay_valid = false;          // verdict below belongs to the current resident inputs and options
   uint32_t replay_hf[16] = {};        // flag words the checked call read after the operand build
   bool replaying = false;             // deviations_run is enqueueing a replay
+  bool replay_gather = false;         // the checked call took the few-cells path (cv_dense_gather.cu)
   bool async_pending = false;         // a replay is in flight: flags / timings not collected yet
   int opt_tail_chunk = 1;             // "tail_chunk": streamed call ends with a short fourth cell chunk
   int opt_host_narrow = -1;           // "host_narrow": -1 (default) host threads stage / narrow PAGEABLE caller memory, 0 never, n >= 1 always
@@ -181,6 +182,8 @@ struct cv_handle {
   int opt_band = 0;            // dense path: groups per raster band (0 = default)
   int opt_debug_no_tma = 0;    // experiment only: GEMM without operand loads (garbage results)
   int opt_check_zero = 1;      // reject peaks without fragments (off for shards of a larger matrix)
+  int opt_gather = -1;         // "small_n_gather": -1 few-cells path when it applies and the stacked operand would be large, 0 never, 1 whenever it applies
+  bool cols_dup = false;       // K1: some column of the counts lists a peak twice
   int opt_trace = 0;           // CV_TRACE in the environment at cv_create: timeline of the streamed call on stderr
   double sparse_rate = 2.7e8;  // row-gather kernel, entry updates per ms: measured by the last sparse run (choose_path)
 
@@ -273,7 +276,11 @@ int cv_dense_prepare(cv_handle* h, const DensePlan& pl, int scatter_rows);
 int cv_dense_chunk(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t c1, int keep_sums);
 int cv_dense_check(cv_handle* h, const DensePlan& pl, const uint32_t* hflags, int with_counts, int* soft_fail);
 // cv_dense_build.cu
-int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter);
+int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tables_only = 0);
+int cv_dense_finalize_sums(cv_handle* h, const DenseParams& prm);
+// cv_dense_gather.cu: the contraction for few cells (gathered counts rows, no stacked operand)
+int cv_gather_applicable(const cv_handle* h);
+int cv_gather_run(cv_handle* h, int keep_sums);
 int cv_dense_rebuild_rows_u8(cv_handle* h, const DensePlan& pl);
 int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift);
 int cv_exclusive_scan_u32_async(cv_handle* h, const uint32_t* in, uint32_t* out, int64_t n);

@@ -84,6 +84,10 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *                      together (L2 then serves all but the first request for an operand block); 0: free running
  *   "dense_rows_scatter" 1 builds the operand rows with the per-annotation scatter kernel only
  *   "cell_chunk"       cap on the cells per GEMM launch of the dense path (0 = memory budget)
+ *   "small_n_gather"   few-cells contraction (N <= 256 cells, counts < 65536, no annotation listing a peak twice):
+ *                      per iteration the counts rows are gathered by the background indices into an MN-major
+ *                      tcgen05 operand, nothing is stacked.  -1 (default): when the stacked operand would
+ *                      exceed 1 GB; 0: never; 1: whenever it applies
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
  *                      0 for a shard of a larger matrix (the caller checks the reduced totals)
  *   "tail_chunk"       cv_deviations_csc: 1 (default) a short fourth cell chunk ends the call so that little
@@ -311,6 +315,8 @@ typedef struct cv_stage_stats {
   int32_t epilogue;          /* dense path: 32 = fixed-point / fp32 epilogue, 64 = fp64 epilogue */
   int32_t operand_bits;      /* dense path: 8 = u8 operands (tcgen05 kind::i8), 4 = e2m1 operands (kind::mxf4) */
   int32_t overflow_columns;  /* e2m1 operands: extra columns holding the terms of values outside {0,1,2,3,4,6}, all chunks */
+  int32_t few_cells;         /* 1: the few-cells contraction ran (counts rows gathered per iteration, no stacked operand) */
+  int32_t reserved;
 } cv_stage_stats;
 int cv_stats(cv_handle* h, cv_stage_stats* out);
 int cv_multi_stats(cv_multi* m, int i, cv_stage_stats* out);   /* device i of a cv_multi */
