@@ -554,7 +554,7 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tabl
     CV_TRY(cv_ensure(h, h->dn_invptr, (size_t)(P * B + 1) * 4));
     CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)P * B * 4));
   }
-  CV_TRY(cv_ensure(h, h->dn_E2, (size_t)P * I * 8));
+  if (tables_only != 2) CV_TRY(cv_ensure(h, h->dn_E2, (size_t)P * I * 8));
   CV_TRY(cv_ensure(h, h->dn_ov, (size_t)K * 8));
   // Two streams: the operand rows (write-bound) on the compute stream; the expected-fraction table
   // (L2-read-bound) and the overlap counts beside them on the auxiliary stream.  The GEMM waits for
@@ -586,11 +586,13 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tabl
   do {
     if (cudaStreamWaitEvent(h->s_aux, h->ev_aux[0], 0) != cudaSuccess) { rc = CV_ERR_CUDA; break; }
     if (cudaMemsetAsync(h->work_ctr.as<uint32_t>() + 4, 0, 4, h->s_aux) != cudaSuccess) { rc = CV_ERR_CUDA; break; }
+    if (tables_only != 2) {                                                // (2: the few-cells GEMM computes the table itself)
     k_e2_build<<<(unsigned)((P * I + 255) / 256), 256, 0, h->s_aux>>>(h->bg_raw.as<int32_t>(), h->index_base, (int)P, B,
                                                                       h->expect.as<double>(), h->dn_E2.as<double>());
     k_etab_rows<<<(unsigned)std::min<int64_t>(K, (int64_t)h->num_sms * 4), 256, (size_t)8 * I * 8, h->s_aux>>>(
         h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), h->order.as<int32_t>(), h->dn_E2.as<double>(), (int)K,
         (int)P, B, h->etab.as<double>(), h->work_ctr.as<uint32_t>() + 4);
+    }
     cudaEventRecord(h->ev_aux[2], h->s_aux);                               // expected-fraction table ready
     cudaStreamWaitEvent(h->s_aux, h->ev_aux[1], 0);
     cudaMemsetAsync(h->dn_ov.p, 0, (size_t)K * 8, h->s_aux);

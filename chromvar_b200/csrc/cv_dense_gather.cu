@@ -38,6 +38,7 @@
 
 struct GatherParams {
   int K, P, I, N;                  // annotations, peaks, iterations + 1, cells (<= 256)
+  int n_store;                     // cell columns whose sums are kept: N (+ the expectation's digit columns)
   int n_kblocks;                   // 128-peak blocks (peak axis padded)
   int n_tiles;                     // 256-annotation tiles
   int64_t ppad;                    // padded peaks = row stride of bgx
@@ -124,14 +125,15 @@ k_gather_contract(const __grid_constant__ CUtensorMap map_a, const GatherParams 
       uint32_t ph = 0;
       for (int item = pair_id; item < n_items; item += n_pairs) {
         const int tile = item % prm.n_tiles;
-        const int ya = tile * 256 + (int)rank * 128;
+        const int rt = tile * 2 + (int)rank;               // 128-annotation row tile of this CTA
         for (int kb = 0; kb < prm.n_kblocks; ++kb) {
           ga_wait(empty_bar + s, ph ^ 1u, 32);
           if (prm.debug == 3) {
             if (rank == 0) mbar_arrive(full_bar + s);
           } else {
             if (rank == 0) mbar_expect_tx(full_bar + s, 2 * GA_A_BYTES);
-            tma_load_2d_pair(&map_a, mapa_u32(smem_u32(full_bar + s), 0), smem_a + s * GA_A_BYTES, kb * 128, ya);
+            tma_load_2d_pair(&map_a, mapa_u32(smem_u32(full_bar + s), 0), smem_a + s * GA_A_BYTES, 0,
+                             (rt * prm.n_kblocks + kb) * 128);
           }
           if (++s == GA_STAGES) { s = 0; ph ^= 1u; }
         }
@@ -247,7 +249,7 @@ k_gather_contract(const __grid_constant__ CUtensorMap map_a, const GatherParams 
         if (k < prm.K) {
 #pragma unroll
           for (int u = 0; u < 32; ++u)
-            if (c0 + u < prm.N) dst[c0 + u] = (long long)(int)r0[u] + ((long long)(int)r1[u] << 8);
+            if (c0 + u < prm.n_store) dst[c0 + u] = (long long)(int)r0[u] + ((long long)(int)r1[u] << 8);
         }
       }
       tc_fence_before();
@@ -263,18 +265,26 @@ k_gather_contract(const __grid_constant__ CUtensorMap map_a, const GatherParams 
 }
 
 // ---- operand builders ----------------------------------------------------------------------------------------
-// A8[k][p] = bit k of Abits[k / 32][p]  (u8 0/1; rows >= K and peaks >= P stay zero)
+// A8, tiled: the 128 annotations x 128 peaks of (row tile rt, k-block kb) are one contiguous 16 KB block
+// at ((rt * n_kb + kb) * 128 + k % 128) * 128 + p % 128, so a TMA box is one sequential read (rows of the
+// plain K x P layout are 500 KB apart: 128 DRAM pages per box and microseconds of latency).
+// Entry = bit k of Abits[k / 32][p]  (u8 0/1; rows >= K and peaks >= P stay zero)
 __global__ void __launch_bounds__(256)
 k_ga_build_a(const uint32_t* __restrict__ Abits, int K, int P, int64_t ppad, uint8_t* __restrict__ A8) {
   const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int w = blockIdx.y;
   if (p >= ppad) return;
   const uint32_t word = p < P ? Abits[(int64_t)w * P + p] : 0u;
+  const int64_t n_kb = ppad / 128;
+  const int64_t rt = (w * 32) / 128, kb = p / 128;
+  uint8_t* blk = A8 + ((rt * n_kb + kb) * 128 + (w * 32) % 128) * 128 + (p % 128);
 #pragma unroll 4
-  for (int b = 0; b < 32; ++b) A8[((int64_t)w * 32 + b) * ppad + p] = (uint8_t)((word >> b) & 1u);
+  for (int b = 0; b < 32; ++b) blk[b * 128] = (uint8_t)((word >> b) & 1u);
 }
 
 // counts planes, cells contiguous: cdT[plane][peak][cell] = byte `plane` of the count; one CTA per cell
+// streams its column (coalesced reads, one byte per entry scattered into the 256-byte rows; a tile-wise
+// variant with binary searches into the columns was slower: 3.1 vs 1.3 ms at config 4)
 __global__ void __launch_bounds__(512)
 k_ga_build_cd(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowidx, const uint32_t* __restrict__ val,
               int N, int64_t rows_cd, uint8_t* __restrict__ cdT) {
@@ -283,10 +293,71 @@ k_ga_build_cd(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   for (int64_t e = colptr[c] + threadIdx.x; e < colptr[c + 1]; e += 512) {
     const uint32_t v = val[e];
     const int64_t q = rowidx[e];
-    // (a column listing a peak twice would need the sum: such input takes the other paths, see cv_gather_applicable)
+    // (a column listing a peak twice would need the sum: such input takes the other paths, K1's verdict)
     cdT[q * GA_CELLS + c] = (uint8_t)(v & 0xFFu);
     if (v >> 8) cdT[(rows_cd + q) * GA_CELLS + c] = (uint8_t)((v >> 8) & 0xFFu);
   }
+}
+
+// The expectation rides on the GEMM: E[k][j] = sum_p A[k, p] e[bg_j(p)] is one more "cell" of the same
+// contraction.  e[q] is written in fixed point, GA_EDIGITS base-256 digits with the unit 2^-GA_EUNIT (every
+// double in [2^-GA_EUNIT+52, 1) is represented exactly: 2^-40 <= e covers matrices up to 1e12 fragments), one
+// digit per spare cell column of digit plane 0; the integer sums of the digits are exact, so the table is
+// the correctly rounded sum of the exact values -- no fp64 summation order at all.
+#define GA_EDIGITS 12
+#define GA_EUNIT 92
+__global__ void __launch_bounds__(256)
+k_ga_build_edigits(const double* __restrict__ e, int P, int N, uint8_t* __restrict__ cdT, uint32_t* __restrict__ dflags) {
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= P) return;
+  const double v = e[q];
+  uint8_t* row = cdT + (int64_t)q * GA_CELLS + N;
+  if (!(v >= 0.0) || !(v < 1.0)) { atomicOr(dflags + 4, 2u); return; }      // outside the fixed-point range: the table kernel instead
+  int ex;
+  const double m = frexp(v, &ex);                              // v = m 2^ex, m in [0.5, 1)
+  unsigned long long mant = (unsigned long long)ldexp(m, 53);  // 53-bit integer
+  int sh = ex - 53 + GA_EUNIT;                                 // v = mant 2^(ex - 53) = mant 2^sh units
+  if (v != 0.0 && sh < 0) {
+    if (mant & ((1ull << min(-sh, 63)) - 1ull)) atomicOr(dflags + 4, 2u);     // bits below the unit: not exact
+    mant = -sh >= 64 ? 0ull : mant >> -sh;
+    sh = 0;
+  }
+  // mant << sh as GA_EDIGITS bytes
+  for (int d = 0; d < GA_EDIGITS; ++d) {
+    const int bit = 8 * d - sh;                                // bit position inside mant of this digit's LSB
+    unsigned long long piece = 0ull;
+    if (bit > -8 && bit < 64) piece = bit >= 0 ? (mant >> bit) : (mant << -bit);
+    row[d] = (uint8_t)(piece & 0xFFull);
+  }
+}
+
+// etab[k][j] from the digit sums S[k][j][N + d] (each < 2^31): value = sum_d S_d 256^d units, rounded once
+__global__ void __launch_bounds__(256)
+k_ga_etab_from_sums(const long long* __restrict__ sums, int K, int I, int N, double* __restrict__ etab) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int64_t)K * I) return;
+  const long long* s = sums + i * GA_CELLS + N;
+  unsigned long long lo = 0ull, hi = 0ull;                     // 128-bit accumulator
+  for (int d = 0; d < GA_EDIGITS; ++d) {
+    const unsigned long long v = (unsigned long long)s[d];
+    const int sh = 8 * d;
+    unsigned long long add_lo, add_hi;
+    if (sh < 64) { add_lo = v << sh; add_hi = sh ? v >> (64 - sh) : 0ull; }
+    else { add_lo = 0ull; add_hi = v << (sh - 64); }
+    const unsigned long long nl = lo + add_lo;
+    hi += add_hi + (nl < lo ? 1ull : 0ull);
+    lo = nl;
+  }
+  // hi 2^64 + lo -> double with a single rounding: fold the low word's sticky bit in when the high word is set
+  double r;
+  if (hi == 0ull) r = (double)lo;
+  else {
+    const int lz = __clzll((long long)hi);
+    const unsigned long long top = lz ? (hi << lz) | (lo >> (64 - lz)) : hi;     // the 64 leading bits
+    const unsigned long long rest = lz ? lo << lz : lo;
+    r = ldexp((double)(top | (rest ? 1ull : 0ull)), 64 - lz);
+  }
+  etab[i] = ldexp(r, -GA_EUNIT);
 }
 
 // bgx[j][p]: j = 0 the peak itself, j >= 1 its background peak of iteration j; pad peaks -> the zero row
@@ -323,20 +394,22 @@ int cv_gather_applicable(const cv_handle* h) {
   return h->opt_gather > 0 || m_bytes > 1.0e9;
 }
 
-// A8, counts planes, index table, GEMM, finish.  The per-annotation tables (etab, overlap, matches) and the
-// bit columns must have been enqueued (cv_dense_build_rows with tables_only); asynchronous.
-int cv_gather_run(cv_handle* h, int keep_sums) {
+// Can the expectation table ride on the GEMM (spare cell columns for its fixed-point digits)?
+int cv_gather_etab_in_gemm(const cv_handle* h) { return h->N + GA_EDIGITS <= GA_CELLS; }
+
+// Operands of the few-cells path: A8 (tiled), counts planes (+ expectation digits), index table.  The bit
+// columns must have been enqueued (cv_dense_build_rows with tables_only); asynchronous.
+int cv_gather_prepare(cv_handle* h) {
   const int64_t P = h->P, N = h->N, K = h->K;
   const int I = h->B + 1;
   const int64_t ppad = ((P + 127) / 128) * 128, rows_cd = ppad + 1;
   const int64_t kpad = ((K + 255) / 256) * 256;
   const int64_t Kw = (K + 31) / 32;
+  if ((kpad / 128) * (ppad / 128) * 128 > 0x7fffffffll) CV_FAIL(h, CV_ERR_UNSUPPORTED, "annotation operand too large for the few-cells path");
   CV_TRY(cv_ensure(h, h->dn_M, (size_t)kpad * ppad));                       // A8
   CV_TRY(cv_ensure(h, h->dn_C, (size_t)2 * rows_cd * GA_CELLS));            // counts planes
   CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)I * ppad * 4));                 // index table
   CV_TRY(cv_ensure(h, h->dn_S, (size_t)kpad * I * GA_CELLS * 8));           // raw sums
-  const int ncb = (int)((N + DN_BLOCK_M - 1) / DN_BLOCK_M);
-  CV_TRY(cv_ensure(h, h->varpart, (size_t)K * ncb * 4 * 8));
   cv_span_begin(h, CV_SPAN_LAYOUT);
   CV_CUDA(h, cudaMemsetAsync(h->dn_M.p, 0, (size_t)kpad * ppad, h->stream));
   CV_LAUNCH(h, k_ga_build_a, dim3((unsigned)((ppad + 255) / 256), (unsigned)Kw), 256, 0, h->dn_abits.as<uint32_t>(), (int)K,
@@ -344,14 +417,30 @@ int cv_gather_run(cv_handle* h, int keep_sums) {
   CV_CUDA(h, cudaMemsetAsync(h->dn_C.p, 0, (size_t)2 * rows_cd * GA_CELLS, h->stream));
   CV_LAUNCH(h, k_ga_build_cd, (unsigned)N, 512, 0, h->colptr.as<int64_t>(), h->rowidx.as<int32_t>(), h->val.as<uint32_t>(),
             (int)N, rows_cd, h->dn_C.as<uint8_t>());
+  if (cv_gather_etab_in_gemm(h))
+    CV_LAUNCH(h, k_ga_build_edigits, (unsigned)((P + 255) / 256), 256, 0, h->expect.as<double>(), (int)P, (int)N,
+              h->dn_C.as<uint8_t>(), h->flags.as<uint32_t>() + CV_DFLAGS);
   CV_LAUNCH(h, k_ga_build_idx, dim3((unsigned)((ppad + 255) / 256), (unsigned)I), 256, 0, h->bg_raw.as<int32_t>(),
             h->index_base, (int)P, I, ppad, (int32_t)ppad, h->dn_invsrc.as<int32_t>());
   cv_span_end(h);
+  return CV_OK;
+}
 
+// GEMM + finish on the operands of cv_gather_prepare.  The overlap / matches vectors (and the expectation
+// table when it does not ride on the GEMM) come from the auxiliary stream; asynchronous.
+int cv_gather_run(cv_handle* h, int keep_sums) {
+  const int64_t P = h->P, N = h->N, K = h->K;
+  const int I = h->B + 1;
+  const int64_t ppad = ((P + 127) / 128) * 128, rows_cd = ppad + 1;
+  const int64_t kpad = ((K + 255) / 256) * 256;
+  const int ncb = (int)((N + DN_BLOCK_M - 1) / DN_BLOCK_M);
+  CV_TRY(cv_ensure(h, h->varpart, (size_t)K * ncb * 4 * 8));
   CUtensorMap map_a;
-  CV_TRY(cv_make_map_u8(h, &map_a, h->dn_M.p, (uint64_t)kpad, (uint64_t)ppad, (uint64_t)ppad, 128));
+  // the tiled A8 as a (kpad / 128 * n_kb * 128) x 128-byte array: box = one contiguous 16 KB tile
+  CV_TRY(cv_make_map_u8(h, &map_a, h->dn_M.p, (uint64_t)((kpad / 128) * (ppad / 128) * 128), 128, 128, 128));
   GatherParams gp;
   gp.K = (int)K; gp.P = (int)P; gp.I = I; gp.N = (int)N;
+  gp.n_store = (int)N + (cv_gather_etab_in_gemm(h) ? GA_EDIGITS : 0);
   gp.n_kblocks = (int)(ppad / 128);
   gp.n_tiles = (int)(kpad / 256);
   gp.ppad = ppad;
@@ -367,9 +456,14 @@ int cv_gather_run(cv_handle* h, int keep_sums) {
   k_gather_contract<<<2 * pairs, GA_THREADS, GA_SMEM_BYTES, h->stream>>>(map_a, gp);
   h->launches++;
   CV_CUDA(h, cudaGetLastError());
-  // the reference arithmetic on the exact sums (same kernel as the digit-plane path); it reads the
-  // expected-fraction table the auxiliary stream has been building beside the GEMM
-  CV_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_aux[2], 0));
+  // the expected-fraction table: from the digit sums of the spare cell columns, or (no spare columns)
+  // from the auxiliary stream, which has been building it beside the GEMM
+  if (cv_gather_etab_in_gemm(h))
+    CV_LAUNCH(h, k_ga_etab_from_sums, (unsigned)((K * I + 255) / 256), 256, 0, h->dn_S.as<long long>(), (int)K, I, (int)N,
+              h->etab.as<double>());
+  else
+    CV_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_aux[2], 0));
+  // the reference arithmetic on the exact sums (same kernel as the digit-plane path)
   DenseParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.N = (int)N; prm.K = (int)K; prm.B = h->B;

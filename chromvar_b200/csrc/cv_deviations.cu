@@ -724,15 +724,19 @@ static int deviations_run(cv_handle* h, int rebuild_counts_layout, int keep_sums
     DensePlan plg;
     plg.I = I;
     plg.G = 1;
-    CV_TRY(cv_dense_build_rows(h, plg, 0, 1));               // bit columns + per-annotation tables (auxiliary stream)
+    // bit columns + per-annotation tables (auxiliary stream; the expectation table rides on the GEMM when
+    // the cell tile has spare columns for its digits), then the operands
+    CV_TRY(cv_dense_build_rows(h, plg, 0, cv_gather_etab_in_gemm(h) ? 2 : 1));
+    CV_TRY(cv_gather_prepare(h));
     uint32_t hf[16] = {};
     if (!h->replaying) {
       CV_CUDA(h, cudaMemcpyAsync(hf, h->flags.p, 64, cudaMemcpyDeviceToHost, h->stream));
       CV_CUDA(h, cudaStreamSynchronize(h->stream));
       if (hf[CV_DFLAGS] & FLAG_BADIDX)
         CV_FAIL(h, CV_ERR_INVALID, "Annotations are not valid / background_peaks index outside 1..nrow(counts)");
-      if (hf[CV_DFLAGS + 3]) {
-        // a list repeats a peak: bit columns cannot hold the multiplicity -- the general paths take over
+      if (hf[CV_DFLAGS + 3] || (hf[CV_DFLAGS + 4] & 2u)) {
+        // a list repeats a peak (bit columns cannot hold the multiplicity), or an expectation outside the
+        // fixed-point range of the digit columns: the general paths take over
         CV_CUDA(h, cudaStreamSynchronize(h->s_aux));
         h->aux_pending = false;
         CV_CUDA(h, cudaMemsetAsync(dflags + 1, 0, 12, h->stream));

@@ -280,6 +280,8 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tabl
 int cv_dense_finalize_sums(cv_handle* h, const DenseParams& prm);
 // cv_dense_gather.cu: the contraction for few cells (gathered counts rows, no stacked operand)
 int cv_gather_applicable(const cv_handle* h);
+int cv_gather_etab_in_gemm(const cv_handle* h);
+int cv_gather_prepare(cv_handle* h);
 int cv_gather_run(cv_handle* h, int keep_sums);
 int cv_dense_rebuild_rows_u8(cv_handle* h, const DensePlan& pl);
 int cv_dense_build_cells(cv_handle* h, const DensePlan& pl, int64_t c0, int64_t rows, int shift);

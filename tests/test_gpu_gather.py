@@ -2,7 +2,10 @@
 iteration the counts rows are gathered by the background indices into an MN-major tcgen05 operand
 (cp.async into a hand-swizzled shared-memory tile), both u8 digit planes accumulate side by side in
 tensor memory, nothing is stacked.  Integer sums bit-equal to the oracle and to the stacked-operand
-path; deviations / z bit-equal to the stacked-operand path with digit planes (same finishing kernel)."""
+path.  The expectation table rides on the same GEMM as fixed-point digits in the spare cell columns (the
+correctly rounded sum of the exact values), so deviations / z agree with the stacked-operand path -- whose
+table is an fp64 sum in list order -- to ~1e-13 instead of bit for bit; with no spare columns
+(N > 244) the table comes from the same kernel as there and everything is bit-equal."""
 import os
 import sys
 
@@ -56,8 +59,15 @@ def test_gather_path_equals_oracle_and_stacked_path(geng, shape):
     got = geng.deviations(ptr, idx, bg, e, sums=True)
     st = geng.stats()
     assert st["few_cells"] == 1 and st["path"] == 1
+    exact_table = N + 12 > 256                            # no spare columns: same table kernel as the stacked path
     for key in KEYS:
-        assert np.array_equal(got[key], base[key], equal_nan=True), key
+        if exact_table or key in ("observed", "sampled", "matches", "overlap"):
+            assert np.array_equal(got[key], base[key], equal_nan=True), key
+        else:
+            assert np.array_equal(np.isnan(got[key]), np.isnan(base[key])), key
+            ok = np.isfinite(base[key])
+            assert np.array_equal(got[key][~ok & ~np.isnan(base[key])], base[key][~ok & ~np.isnan(base[key])]), key
+            assert np.max(np.abs(got[key][ok] - base[key][ok]) / np.maximum(np.abs(base[key][ok]), 1e-3)) < 1e-9, key
     if K <= 40:
         live = [k for k in range(K) if len(sets[k])]
         ref = orc.compute_deviations_core(C, [sets[k] for k in live], bg, e, intermediate=True)
@@ -68,7 +78,7 @@ def test_gather_path_equals_oracle_and_stacked_path(geng, shape):
     again = geng.deviations(ptr, idx, bg, e, sums=False)
     assert geng.stats()["few_cells"] == 1
     for key in ("dev", "z"):
-        assert np.array_equal(again[key], base[key], equal_nan=True), key
+        assert np.array_equal(again[key], got[key], equal_nan=True), key
     geng.deviations_upload(ptr, idx, bg, e)
     geng.deviations_compute(rebuild_counts_layout=True)
     geng.deviations_compute_async(rebuild_counts_layout=True)
@@ -76,7 +86,7 @@ def test_gather_path_equals_oracle_and_stacked_path(geng, shape):
     geng.deviations_wait()
     q = geng.deviations_download()
     for key in ("dev", "z", "variability"):
-        assert np.array_equal(q[key], base[key], equal_nan=True), key
+        assert np.array_equal(q[key], got[key], equal_nan=True), key
 
 
 def test_gather_path_declines_what_it_cannot_represent(geng):
@@ -107,6 +117,14 @@ def test_gather_path_declines_what_it_cannot_represent(geng):
     got = geng.deviations(ptr, idx, bg, e2, sums=True)
     assert geng.stats()["few_cells"] == 0
     check_against_oracle(got, orc.compute_deviations_core(C2, sets, bg, e2, intermediate=True))
+    # an expectation outside [0, 1) cannot be written in the digit columns: the general paths take over
+    sets = [rng.choice(np.arange(1, P + 1), 300, replace=False)]
+    ptr, idx = sets_to_csr(sets)
+    e_big = e * 1e6
+    geng.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    got = geng.deviations(ptr, idx, bg, e_big, sums=True)
+    assert geng.stats()["few_cells"] == 0
+    check_against_oracle(got, orc.compute_deviations_core(C, sets, bg, e_big, intermediate=True))
     # an out-of-range background index is still an error
     bad = bg.copy()
     bad[7, 2] = P + 1
