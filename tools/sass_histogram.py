@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "chromvar_b200", "lib", "libchromvar_b200.so")
-KERNELS = ["k_dense_contract_fp4", "k_dense_contract_pair", "k_dense_contract<", "k_contract", "k_f4_rows_main",
+KERNELS = ["k_gather_contract", "k_dense_contract_fp4", "k_dense_contract_pair", "k_dense_contract<", "k_contract", "k_f4_rows_main",
            "k_dense_rows_gather", "k_counts_sums", "k_bg_sample", "k_sum_peers", "k_var_merge_peers"]
 # mnemonics that prove tensor-core / TMA / cluster use on sm_100a (B200_PROFILING.md)
 MARK = ["UTCOMMA", "UTCIMMA", "UTCHMMA", "UTCQMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS",
