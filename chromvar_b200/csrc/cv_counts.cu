@@ -48,7 +48,7 @@ int cv_sync_check(cv_handle* h) {
   return CV_OK;
 }
 
-extern "C" int cv_version(void) { return 100; }
+extern "C" int cv_version(void) { return 200; }
 
 extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
   if (!out) return CV_ERR_INVALID;

@@ -30,7 +30,7 @@ def test_version_and_struct_size():
     from chromvar_b200 import _lib
     lib = _lib.load()
     assert lib.cv_version() >= 100
-    assert ctypes.sizeof(_lib.StageStats) == 8 * 8 + 5 * 8 + 8 * 4
+    assert ctypes.sizeof(_lib.StageStats) == 8 * 8 + 5 * 8 + 10 * 4      # cv_stage_stats: 8 doubles, 5 int64, 10 int32
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -47,7 +47,10 @@ def _worker(rank, ws, port, q):
     glob = cvd.allreduce_peak_totals(host_totals=tot)
     sd = cvd.gather_variability(host_partials=cvd.welford_partials(z[:, lo:hi]), na_rm=True)
     sd_all = cvd.gather_variability(host_partials=cvd.welford_partials(z[:, lo:hi]), na_rm=False)
-    q.put((rank, lo, hi, glob, sd, sd_all))
+    # init() broadcast one seed: every rank now draws the same per-call sampler seeds
+    from chromvar_b200 import api
+    seeds = [api._next_sampler_seed() for _ in range(3)]
+    q.put((rank, lo, hi, glob, sd, sd_all, seeds))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,7 +70,8 @@ def test_two_rank_reductions():
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == C.shape[1]
     ref_tot = np.append(np.asarray(C.sum(axis=1)).ravel(), C.sum()).astype(np.int64)
     ref_sd = np.array([np.std(r[np.isfinite(r)], ddof=1) for r in z])
-    for _, _, _, glob, sd, sd_all in res:
+    assert res[0][6] == res[1][6] and len(set(res[0][6])) == 3      # same stream on both ranks, a fresh seed per call
+    for _, _, _, glob, sd, sd_all, _ in res:
         assert np.array_equal(glob, ref_tot)
         assert np.allclose(sd, ref_sd, rtol=1e-12)
         assert np.isnan(sd_all[[2, 4]]).all() and np.allclose(np.delete(sd_all, [2, 4]), np.delete(ref_sd, [2, 4]), rtol=1e-12)
