@@ -33,7 +33,7 @@ EXPORTS = [
     "cv_variability_merge_device", "cv_permuted_counts", "cv_permuted_counts_fetch", "cv_deviations_covariability",
     "cv_create_multi", "cv_destroy_multi", "cv_multi_last_error", "cv_multi_n_devices", "cv_multi_peer_access",
     "cv_multi_handle", "cv_multi_set_seed", "cv_multi_set_option", "cv_multi_stats", "cv_multi_set_counts",
-    "cv_multi_shards", "cv_multi_fragments", "cv_multi_expectations", "cv_multi_background_peaks",
+    "cv_multi_set_counts_dense", "cv_multi_shards", "cv_multi_fragments", "cv_multi_expectations", "cv_multi_background_peaks",
     "cv_multi_deviations", "cv_multi_deviations_csc",
 ]
 
@@ -132,7 +132,8 @@ def load(build_if_missing=True):
         "cv_multi_set_counts": (i32, [vp, i64, C.POINTER(CscBlock), i32]),
         "cv_multi_shards": (i32, [vp, vp]),
         "cv_multi_fragments": (i32, [vp, vp, vp, vp]),
-        "cv_multi_expectations": (i32, [vp, vp]),
+        "cv_multi_expectations": (i32, [vp, i32, vp, i32, vp]),
+        "cv_multi_set_counts_dense": (i32, [vp, i64, i64, vp, i32]),
         "cv_multi_background_peaks": (i32, [vp, vp, i32, dbl, i32, vp]),
         "cv_multi_deviations": (i32, [vp, i64, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
         "cv_multi_deviations_csc": (i32, [vp, i64, C.POINTER(CscBlock), i32, i64, vp, vp, i32, vp, i32, vp,
@@ -198,9 +199,22 @@ class Handle:
         self.device = device
         self.P = self.N = self.K = self.B = 0
 
+    @classmethod
+    def borrowed(cls, ptr, device=0):
+        """A view of an engine somebody else owns (cv_multi_handle): same methods, close() does not
+        destroy it."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self._h = C.c_void_p(ptr) if not isinstance(ptr, C.c_void_p) else ptr
+        self._borrowed = True
+        self.device = device
+        self.P = self.N = self.K = self.B = 0
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
-            self.lib.cv_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self.lib.cv_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -556,6 +570,12 @@ class MultiHandle:
     def n_devices(self):
         return self.lib.cv_multi_n_devices(self._m)
 
+    def handle(self, i=0):
+        """Device i's engine as a (borrowed) Handle: the cell-independent routines run there."""
+        h = Handle.borrowed(self.lib.cv_multi_handle(self._m, int(i)), self.devices[i])
+        h.P, h.N, h.K, h.B = self.P, 0, self.K, self.B
+        return h
+
     def peer_access(self):
         return bool(self.lib.cv_multi_peer_access(self._m))
 
@@ -575,6 +595,15 @@ class MultiHandle:
         self._check(self.lib.cv_multi_set_counts(self._m, P, arr, len(arr)))
         self.P, self.N = P, N
 
+    def set_counts_dense(self, x):
+        x = np.asarray(x)
+        if x.dtype not in (np.dtype(np.float64), np.dtype(np.float32), np.dtype(np.int32)):
+            x = x.astype(np.float64)
+        x = np.asfortranarray(x)
+        P, N = x.shape
+        self._check(self.lib.cv_multi_set_counts_dense(self._m, P, N, _ptr(x), _DTYPE_TAG[x.dtype]))
+        self.P, self.N = int(P), int(N)
+
     def shards(self):
         b = np.zeros(len(self.devices) + 1, np.int64)
         self._check(self.lib.cv_multi_shards(self._m, _ptr(b)))
@@ -585,9 +614,12 @@ class MultiHandle:
         self._check(self.lib.cv_multi_fragments(self._m, _ptr(fpp), _ptr(fps), _ptr(tot)))
         return fpp, fps, float(tot[0])
 
-    def expectations(self):
+    def expectations(self, norm=False, group=None, n_groups=0):
         e = np.empty(self.P)
-        self._check(self.lib.cv_multi_expectations(self._m, _ptr(e)))
+        g = None if group is None else _carr(group, np.int32)
+        if g is not None and g.shape[0] != self.N:
+            raise ChromVARError(CV_ERR_INVALID, "group must have one label per cell")
+        self._check(self.lib.cv_multi_expectations(self._m, int(bool(norm)), _ptr(g), int(n_groups), _ptr(e)))
         return e
 
     def background_peaks(self, bias, niterations=50, w=0.1, bs=50):

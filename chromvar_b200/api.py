@@ -28,7 +28,7 @@ __all__ = [
     "SummarizedExperiment", "chromVARDeviations", "computeDeviations", "computeExpectations",
     "getBackgroundPeaks", "computeVariability", "getFragmentsPerPeak", "getFragmentsPerSample",
     "getTotalFragments", "deviations", "deviationScores", "annotationMatches", "get_engine",
-    "set_device",
+    "set_device", "set_devices", "set_seed",
 ]
 
 _MATCH_ASSAYS = ("annotationMatches", "annotation_matches", "motif_matches", "motifMatches", "matches")
@@ -116,11 +116,111 @@ def _next_sampler_seed():
 
 
 def set_device(device):
+    """One GPU per process (the default: LOCAL_RANK, else 0)."""
     global _device, _engine
     if _engine is not None and _device != device:
         _engine.close()
         _engine = None
+        invalidate_counts_cache()
     _device = device
+
+
+def set_devices(devices):
+    """Several GPUs behind this one process (cv_multi, what the R shim's chromVAR_b200_init(devices)
+    binds): the cells are sharded across `devices`, every function of this module keeps its meaning.
+    A single id is the same as set_device()."""
+    devices = [int(d) for d in devices]
+    if len(devices) == 0:
+        raise ValueError("devices must name at least one GPU")
+    set_device(devices[0] if len(devices) == 1 else tuple(devices))
+
+
+class _Block:
+    """The CSC arrays of one column block, as cv_multi takes them."""
+    def __init__(self, P, N, indptr, indices, data):
+        self.shape, self.indptr, self.indices, self.data = (int(P), int(N)), indptr, indices, data
+
+
+class _MultiEngine:
+    """cv_multi with the method names api.py uses on a single engine.  Sharded: counts, fragments,
+    expectations (all variants), deviations.  Cell independent (bias / totals in, matrix out, or a host
+    matrix in): run on the first device, which holds the reduced per-peak totals."""
+
+    def __init__(self, devices, seed):
+        self.m = _lib.MultiHandle(devices, seed=seed)
+
+    P = property(lambda self: self.m.P)
+    N = property(lambda self: self.m.N)
+    K = property(lambda self: self.m.K)
+
+    def close(self):
+        self.m.close()
+
+    def first(self):
+        return self.m.handle(0)
+
+    def set_seed(self, seed):
+        self.m.set_seed(seed)
+
+    def set_option(self, key, value):
+        self.m.set_option(key, value)
+
+    def stats(self, i=0):
+        return self.m.stats(i)
+
+    def set_counts_csc(self, P, N, indptr, indices, data):
+        self.m.set_counts([_Block(P, N, indptr, indices, data)])
+
+    def set_counts_dense(self, a):
+        self.m.set_counts_dense(a)
+
+    def fragments(self):
+        return self.m.fragments()
+
+    def expectations(self, norm=False, group=None, n_groups=0):
+        return self.m.expectations(norm=norm, group=group, n_groups=n_groups)
+
+    def background_peaks(self, bias, niterations=50, w=0.1, bs=50):
+        return self.m.background_peaks(bias, niterations, w, bs)
+
+    def background_peaks_knn(self, bias, niterations=50, window=500):
+        return self.first().background_peaks_knn(bias, niterations, window)
+
+    def deviations(self, annoptr, annoidx, bg, expectation, index_base=1):
+        return self.m.deviations(annoptr, annoidx, bg, expectation, index_base=index_base)
+
+    def deviations_csc(self, P, N, indptr, indices, data, annoptr, annoidx, bg, expectation=None, index_base=1):
+        return self.m.deviations_csc([_Block(P, N, indptr, indices, data)], annoptr, annoidx, bg, expectation,
+                                     index_base=index_base)
+
+    # the three-step form synergy.py uses (row SDs only: no K x N matrices come back)
+    def deviations_upload(self, annoptr, annoidx, bg, expectation, index_base=1):
+        self._pending = (annoptr, annoidx, bg, expectation, index_base)
+
+    def deviations_compute(self):
+        pass
+
+    def deviations_download(self, vectors_only=False):
+        annoptr, annoidx, bg, expectation, index_base = self._pending
+        out = None
+        if vectors_only:
+            K = len(annoptr) - 1
+            out = dict(dev=None, z=None, matches=np.empty(K), overlap=np.empty(K), variability=np.empty(K))
+        return self.m.deviations(annoptr, annoidx, bg, expectation, index_base=index_base, out=out)
+
+    def row_sds(self, x, na_rm=False):
+        return self.first().row_sds(x, na_rm)
+
+    def row_sds_perm(self, x, na_rm=False, n_rep=1):
+        return self.first().row_sds_perm(x, na_rm, n_rep)
+
+    def deviations_covariability(self, z=None):
+        if z is None:
+            raise ChromVARError(_lib.CV_ERR_STATE, "z is sharded across the devices: pass the matrix")
+        return self.first().deviations_covariability(z)
+
+    def permuted_counts(self, bias, w=0.1, bs=50):
+        raise ChromVARError(_lib.CV_ERR_UNSUPPORTED, "getPermutedData needs a single device (set_device)")
 
 
 def get_engine():
@@ -130,7 +230,8 @@ def get_engine():
     if _engine is None:
         if _device is None:
             _device = int(os.environ.get("LOCAL_RANK", "0"))
-        _engine = _lib.Handle(_device, seed=int(np.random.SeedSequence().entropy) & (2 ** 63 - 1))
+        seed = int(np.random.SeedSequence().entropy) & (2 ** 63 - 1)
+        _engine = _MultiEngine(list(_device), seed) if isinstance(_device, tuple) else _lib.Handle(_device, seed=seed)
     return _engine
 
 

@@ -1057,42 +1057,62 @@ __global__ void k_expect_finish(const double* __restrict__ acc, const double* __
   e[i] = s / (double)G;   // rowMeans over groups (:445); G == 1 without groups
 }
 
+// norm / group variants, first half: this engine's cells accumulated into acc[G*P] (+ gtot[G]) in
+// tmp1; nothing is synchronised.  group: labels of THIS engine's cells (host).
+int cv_expect_accumulate(cv_handle* h, int norm, const int32_t* group, int G) {
+  cudaSetDevice(h->device);
+  if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
+  const int64_t P = h->P, N = h->N;
+  if (G < 1) CV_FAIL(h, CV_ERR_INVALID, "n_groups must be >= 1");
+  if (group)
+    for (int64_t i = 0; i < N; ++i)
+      if (group[i] < 0 || group[i] >= G) CV_FAIL(h, CV_ERR_INVALID, "group label out of range at cell %lld", (long long)i);
+  CV_TRY(cv_ensure(h, h->tmp1, (size_t)G * P * 8 + (size_t)G * 8));
+  double* acc = h->tmp1.as<double>();
+  double* gtot = acc + (size_t)G * P;
+  CV_CUDA(h, cudaMemsetAsync(acc, 0, (size_t)G * P * 8 + (size_t)G * 8, h->stream));
+  int32_t* dgroup = nullptr;
+  if (group) {
+    CV_TRY(cv_ensure(h, h->tmp2, (size_t)N * 4));
+    dgroup = h->tmp2.as<int32_t>();
+    CV_CUDA(h, cudaMemcpyAsync(dgroup, group, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (h->nnz > 0)
+    CV_LAUNCH(h, k_expect_accum, grid_for(h, h->nnz, 1024), 256, 0, h->colptr.as<int64_t>(),
+              h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), h->nnz, (int)P, (int)N,
+              h->fps.as<double>(), dgroup, norm, acc, gtot);
+  return CV_OK;
+}
+
+// second half: rowMeans over the groups of acc (this engine's tmp1, or a buffer summed over engines)
+int cv_expect_finish(cv_handle* h, const double* acc, int G, int norm, double* out_e) {
+  cudaSetDevice(h->device);
+  const int64_t P = h->P;
+  CV_TRY(cv_ensure(h, h->tmp0, (size_t)P * 8));
+  CV_LAUNCH(h, k_expect_finish, (unsigned)((P + 255) / 256), 256, 0, acc, acc + (size_t)G * P, (int)P, G, norm,
+            h->tmp0.as<double>());
+  CV_CUDA(h, cudaMemcpyAsync(out_e, h->tmp0.p, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+  CV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CV_OK;
+}
+
 extern "C" int cv_expectations(cv_handle* h, int norm, const int32_t* group, int n_groups,
                                double* out_e) {
   if (!h || !out_e) return CV_ERR_INVALID;
   cudaSetDevice(h->device);
   if (!h->have_counts) CV_FAIL(h, CV_ERR_STATE, "counts not set");
-  int64_t P = h->P, N = h->N;
-  CV_TRY(cv_ensure(h, h->tmp0, (size_t)P * 8));
+  int64_t P = h->P;
   if (!norm && !group) {
     if (!h->totals_committed)
       CV_FAIL(h, CV_ERR_STATE, "per-peak totals were handed out for a cross-shard reduction; call cv_peak_totals_commit first");
+    CV_TRY(cv_ensure(h, h->tmp0, (size_t)P * 8));
     CV_LAUNCH(h, k_expect_default, (unsigned)((P + 255) / 256), 256, 0,
               h->peak_tot.as<unsigned long long>(), (int)P, h->tmp0.as<double>());
-  } else {
-    int G = group ? n_groups : 1;
-    if (G < 1) CV_FAIL(h, CV_ERR_INVALID, "n_groups must be >= 1");
-    if (group)
-      for (int64_t i = 0; i < N; ++i)
-        if (group[i] < 0 || group[i] >= G) CV_FAIL(h, CV_ERR_INVALID, "group label out of range at cell %lld", (long long)i);
-    CV_TRY(cv_ensure(h, h->tmp1, (size_t)G * P * 8 + (size_t)G * 8));
-    double* acc = h->tmp1.as<double>();
-    double* gtot = acc + (size_t)G * P;
-    CV_CUDA(h, cudaMemsetAsync(acc, 0, (size_t)G * P * 8 + (size_t)G * 8, h->stream));
-    int32_t* dgroup = nullptr;
-    if (group) {
-      CV_TRY(cv_ensure(h, h->tmp2, (size_t)N * 4));
-      dgroup = h->tmp2.as<int32_t>();
-      CV_CUDA(h, cudaMemcpyAsync(dgroup, group, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
-    }
-    if (h->nnz > 0)
-      CV_LAUNCH(h, k_expect_accum, grid_for(h, h->nnz, 1024), 256, 0, h->colptr.as<int64_t>(),
-                h->rowidx.as<int32_t>(), h->val.as<uint32_t>(), h->nnz, (int)P, (int)N,
-                h->fps.as<double>(), dgroup, norm, acc, gtot);
-    CV_LAUNCH(h, k_expect_finish, (unsigned)((P + 255) / 256), 256, 0, acc, gtot, (int)P, G, norm,
-              h->tmp0.as<double>());
+    CV_CUDA(h, cudaMemcpyAsync(out_e, h->tmp0.p, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+    CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CV_OK;
   }
-  CV_CUDA(h, cudaMemcpyAsync(out_e, h->tmp0.p, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
-  CV_CUDA(h, cudaStreamSynchronize(h->stream));
-  return CV_OK;
+  const int G = group ? n_groups : 1;
+  CV_TRY(cv_expect_accumulate(h, norm, group, G));
+  return cv_expect_finish(h, h->tmp1.as<double>(), G, norm, out_e);
 }

@@ -211,6 +211,8 @@ int cv_csc_view_init(cv_handle* h, CscView* v, int64_t P, int64_t N, const void*
 int cv_csc_view_check(cv_handle* h, const CscView& v);
 int cv_csc_view_copy(cv_handle* h, const CscView& v, int64_t e0, int64_t e1, int32_t* d_rowidx, char* d_x, cudaStream_t st);
 int cv_set_counts_view(cv_handle* h, const CscView& v);
+int cv_expect_accumulate(cv_handle* h, int norm, const int32_t* group, int G);
+int cv_expect_finish(cv_handle* h, const double* acc, int G, int norm, double* out_e);
 // cv_deviations.cu: cv_deviations_csc on a view (expectation may be NULL)
 int cv_deviations_view(cv_handle* h, const CscView& v, int64_t K, const int64_t* annoptr, const int32_t* annoidx,
                        int index_base, const int32_t* bg, int B, const double* expectation, double* out_dev,

@@ -39,6 +39,7 @@ struct cv_multi {
   DevBuf stage[CV_MAX_DEVICES];   // per device: staged copies of the peers' buffers (no-P2P route)
   DevBuf sd0;                     // first device: merged row SDs
   DevBuf flag0;                   // first device: zero-peak flag
+  DevBuf acc0;                    // first device: expectation accumulators summed over the shards
 };
 
 static thread_local std::string g_multi_create_err;
@@ -79,6 +80,16 @@ k_var_merge_peers(PeerPtrs parts, int n, int K, double* __restrict__ sd) {
     cnt = tot;
   }
   sd[k] = cnt > 1.0 ? sqrt(m2 / (cnt - 1.0)) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// dst[i] = sum over devices of src_d[i]  (fp64, device order)
+__global__ void __launch_bounds__(256)
+k_sum_peers_f64(double* __restrict__ dst, PeerPtrs src, int n, int64_t len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double s = 0.0;
+  for (int d = 0; d < n; ++d) s += reinterpret_cast<const double*>(src.p[d])[i];
+  dst[i] = s;
 }
 
 __global__ void k_any_zero_u64(const unsigned long long* __restrict__ v, int64_t n, uint32_t* __restrict__ flag) {
@@ -333,7 +344,7 @@ extern "C" void cv_destroy_multi(cv_multi* m) {
   for (int i = 0; i < m->n; ++i) {
     cudaSetDevice(m->dev[i]);
     cv_release(m->stage[i]);
-    if (i == 0) { cv_release(m->sd0); cv_release(m->flag0); }
+    if (i == 0) { cv_release(m->sd0); cv_release(m->flag0); cv_release(m->acc0); }
     cv_destroy(m->h[i]);
   }
   delete m;
@@ -384,6 +395,29 @@ extern "C" int cv_multi_set_counts(cv_multi* m, int64_t P, const cv_csc_block* b
   return CV_OK;
 }
 
+// A base matrix (column-major P x N): every device takes a contiguous slab of columns and converts it
+// to CSC itself (cv_set_counts_dense); shards are equal numbers of cells, the nonzeros are not known
+// before the conversion.
+extern "C" int cv_multi_set_counts_dense(cv_multi* m, int64_t P, int64_t N, const void* x, int x_type) {
+  if (!m) return CV_ERR_INVALID;
+  m->have_counts = false;
+  if (P <= 0 || N <= 0 || !x) CVM_FAIL(m, CV_ERR_INVALID, "counts: empty matrix");
+  const size_t xb = x_type == CV_F64 ? 8 : (x_type == CV_F32 || x_type == CV_I32) ? 4 : 0;
+  if (!xb) CVM_FAIL(m, CV_ERR_INVALID, "dense counts: x_type must be CV_F64, CV_F32 or CV_I32");
+  const int n = (int)std::min<int64_t>(m->n, N);
+  for (int i = 0; i <= m->n; ++i) m->bounds[i] = i < n ? N * i / n : N;
+  m->P = P;
+  m->N = N;
+  const int na = n_active(m);
+  CV_TRY(for_each_device(m, na, [&](int i) {
+    const int64_t c0 = m->bounds[i], c1 = m->bounds[i + 1];
+    return cv_set_counts_dense(m->h[i], P, c1 - c0, (const char*)x + (size_t)P * (size_t)c0 * xb, x_type);
+  }));
+  CV_TRY(reduce_peak_totals(m));
+  m->have_counts = true;
+  return CV_OK;
+}
+
 extern "C" int cv_multi_fragments(cv_multi* m, double* out_per_peak, double* out_per_sample, double* out_total) {
   if (!m) return CV_ERR_INVALID;
   if (!m->have_counts) CVM_FAIL(m, CV_ERR_STATE, "counts not set");
@@ -400,10 +434,37 @@ extern "C" int cv_multi_fragments(cv_multi* m, double* out_per_peak, double* out
   return CV_OK;
 }
 
-extern "C" int cv_multi_expectations(cv_multi* m, double* out_e) {
+// computeExpectations, all three variants (R/compute_deviations.R:412-447).  The default is a function
+// of the reduced totals; norm / group are sums over cells of per-cell terms: every device accumulates
+// its shard (group: labels of ALL cells, the device reads its slice), the first device adds the
+// accumulators in device order and takes the row means.
+extern "C" int cv_multi_expectations(cv_multi* m, int norm, const int32_t* group, int n_groups, double* out_e) {
   if (!m || !out_e) return CV_ERR_INVALID;
   if (!m->have_counts) CVM_FAIL(m, CV_ERR_STATE, "counts not set");
-  int rc = cv_expectations(m->h[0], 0, nullptr, 0, out_e);
+  const int na = n_active(m);
+  if ((!norm && !group) || na == 1) {
+    int rc = cv_expectations(m->h[0], norm, group, n_groups, out_e);
+    return rc == CV_OK ? CV_OK : fail_from(m, 0, rc);
+  }
+  const int G = group ? n_groups : 1;
+  if (G < 1) CVM_FAIL(m, CV_ERR_INVALID, "n_groups must be >= 1");
+  CV_TRY(for_each_device(m, na, [&](int i) -> int {
+    cv_handle* h = m->h[i];
+    CV_TRY(cv_expect_accumulate(h, norm, group ? group + m->bounds[i] : nullptr, G));
+    CV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CV_OK;
+  }));
+  cv_handle* h = m->h[0];
+  cudaSetDevice(m->dev[0]);
+  const int64_t len = (int64_t)G * m->P + G;
+  auto sum = [&]() -> int {
+    CV_TRY(cv_ensure(h, m->acc0, (size_t)len * 8));
+    PeerPtrs src;
+    CV_TRY(peer_view(m, 0, na, (size_t)len * 8, [&](int d) { return (const void*)m->h[d]->tmp1.p; }, &src));
+    CV_LAUNCH(h, k_sum_peers_f64, (unsigned)((len + 255) / 256), 256, 0, m->acc0.as<double>(), src, na, len);
+    return cv_expect_finish(h, m->acc0.as<double>(), G, norm, out_e);
+  };
+  const int rc = sum();
   return rc == CV_OK ? CV_OK : fail_from(m, 0, rc);
 }
 
@@ -452,7 +513,7 @@ extern "C" int cv_multi_deviations_csc(cv_multi* m, int64_t P, const cv_csc_bloc
     // computeExpectations' default needs the global totals before any deviation: plain sequence
     std::vector<double> e((size_t)std::max<int64_t>(P, 1));
     CV_TRY(cv_multi_set_counts(m, P, blocks, n_blocks));
-    CV_TRY(cv_multi_expectations(m, e.data()));
+    CV_TRY(cv_multi_expectations(m, 0, nullptr, 0, e.data()));
     return cv_multi_deviations(m, K, annoptr, annoidx, index_base, bg, B, e.data(), out_dev, out_z, out_matches,
                                out_overlap, out_variability);
   }

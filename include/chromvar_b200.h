@@ -246,7 +246,10 @@ int cv_multi_set_option(cv_multi* m, const char* key, int64_t value);
 int cv_multi_set_counts(cv_multi* m, int64_t P, const cv_csc_block* blocks, int n_blocks);
 int cv_multi_shards(const cv_multi* m, int64_t* bounds);
 int cv_multi_fragments(cv_multi* m, double* out_per_peak, double* out_per_sample, double* out_total);
-int cv_multi_expectations(cv_multi* m, double* out_e);        /* default variant (global) */
+/* a base matrix, column-major P x N (x_type CV_F64 / CV_F32 / CV_I32): each device converts its slab of columns */
+int cv_multi_set_counts_dense(cv_multi* m, int64_t P, int64_t N, const void* x, int x_type);
+/* computeExpectations over ALL cells, arguments as cv_expectations (group: one 0-based label per cell) */
+int cv_multi_expectations(cv_multi* m, int norm, const int32_t* group, int n_groups, double* out_e);
 int cv_multi_background_peaks(cv_multi* m, const double* bias, int niter, double w, int bs, int32_t* out_bg);
 /* compute_deviations_core on resident counts / as ONE call on host data (arguments as cv_deviations /
  * cv_deviations_csc; expectation == NULL in the _csc form means computeExpectations' default).

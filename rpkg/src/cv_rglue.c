@@ -111,13 +111,13 @@ SEXP cvb_set_counts(SEXP plist, SEXP ilist, SEXP xlist, SEXP nrow) {
  * dgCMatrix first (as(x, "dgCMatrix")) -- a dense matrix of a few hundred samples is a one-GPU job. */
 SEXP cvb_set_counts_dense(SEXP x) {
   need_engine();
-  if (cv_multi_n_devices(M) != 1) Rf_error("dense counts input needs a single device; pass a dgCMatrix");
   SEXP dim = Rf_getAttrib(x, R_DimSymbol);
   if (Rf_isNull(dim) || XLENGTH(dim) != 2) Rf_error("counts must be a matrix");
+  /* column-major like R's matrix: every device takes a slab of columns */
   if (TYPEOF(x) == INTSXP)
-    check0(cv_set_counts_dense(cv_multi_handle(M, 0), INTEGER(dim)[0], INTEGER(dim)[1], INTEGER(x), CV_I32));
+    check(cv_multi_set_counts_dense(M, INTEGER(dim)[0], INTEGER(dim)[1], INTEGER(x), CV_I32));
   else if (TYPEOF(x) == REALSXP)
-    check0(cv_set_counts_dense(cv_multi_handle(M, 0), INTEGER(dim)[0], INTEGER(dim)[1], REAL(x), CV_F64));
+    check(cv_multi_set_counts_dense(M, INTEGER(dim)[0], INTEGER(dim)[1], REAL(x), CV_F64));
   else
     Rf_error("counts must be numeric");
   return R_NilValue;
@@ -142,20 +142,15 @@ SEXP cvb_expectations(SEXP P, SEXP norm, SEXP group, SEXP nlevels) {
   need_engine();
   SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(P)));
   const int nrm = Rf_asLogical(norm) == 1;
-  if (!nrm && Rf_isNull(group)) {
-    if (cv_multi_n_devices(M) == 1) check0(cv_expectations(cv_multi_handle(M, 0), 0, NULL, 0, REAL(out)));
-    else check(cv_multi_expectations(M, REAL(out)));
-  } else {
-    /* rowMeans over per-group / per-cell normalised sums: a per-shard quantity */
-    if (cv_multi_n_devices(M) != 1) Rf_error("computeExpectations(norm / group) needs a single device");
-    int32_t *g = NULL;
-    if (!Rf_isNull(group)) {
-      R_xlen_t n = XLENGTH(group);
-      g = (int32_t *) R_alloc(n, sizeof(int32_t));
-      for (R_xlen_t k = 0; k < n; ++k) g[k] = INTEGER(group)[k] - 1;
-    }
-    check0(cv_expectations(cv_multi_handle(M, 0), nrm, g, Rf_asInteger(nlevels), REAL(out)));
+  int32_t *g = NULL;
+  if (!Rf_isNull(group)) {
+    if (TYPEOF(group) != INTSXP) Rf_error("group must be the integer codes of a factor");
+    R_xlen_t n = XLENGTH(group);
+    g = (int32_t *) R_alloc(n, sizeof(int32_t));
+    for (R_xlen_t k = 0; k < n; ++k) g[k] = INTEGER(group)[k] - 1;
   }
+  /* norm / group: sums over cells of per-cell terms, accumulated per shard and added on the first device */
+  check(cv_multi_expectations(M, nrm, g, g ? Rf_asInteger(nlevels) : 0, REAL(out)));
   UNPROTECT(1);
   return out;
 }

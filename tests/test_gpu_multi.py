@@ -106,6 +106,15 @@ def test_sharded_equals_unsharded_bitwise(engine, problem, layout):
         assert np.array_equal(fpp, fpp1) and np.array_equal(fps, fps1) and tot == tot1
         e = m.expectations()
         assert np.array_equal(e, e1)
+        # the norm / group variants are sums over cells of per-cell terms: accumulated per shard, added
+        # on the first device (fp64, another order than the single engine's atomics)
+        grp = (np.arange(N) * 7 % 4).astype(np.int32)
+        for nrm, gr in ((True, None), (False, grp), (True, grp)):
+            got = m.expectations(norm=nrm, group=gr, n_groups=4 if gr is not None else 0)
+            want = engine.expectations(norm=nrm, group=gr, n_groups=4 if gr is not None else 0)
+            assert np.allclose(got, want, rtol=1e-12, atol=0), (nrm, gr is not None)
+        assert np.allclose(m.expectations(norm=True, group=grp, n_groups=4),
+                           orc.compute_expectations_core(C, norm=True, group=grp), rtol=1e-12, atol=0)
         bg = m.background_peaks(d["bias"], 50, 0.1, 50)
         assert np.array_equal(bg, bg1)                   # same seed, same global totals: same matrix
         res = m.deviations(ptr, idx, bg, e, index_base=1)
@@ -212,3 +221,83 @@ def test_two_engines_on_one_gpu_do_not_wait_for_each_other_forever():
                 assert np.array_equal(res[key], ref[key], equal_nan=True), key
     finally:
         m.close()
+
+
+def test_dense_matrix_is_split_into_column_slabs(engine):
+    from chromvar_b200 import _lib
+    rng = np.random.default_rng(12)
+    P, N, K = 1500, 333, 9
+    X = rng.poisson(0.4, (P, N)).astype(np.float64)
+    X[X.sum(axis=1) == 0, N - 1] = 1                      # some peaks live in the last slab only
+    sets = [rng.choice(np.arange(1, P + 1), int(rng.integers(5, 200)), replace=False) for _ in range(K)]
+    ptr = np.concatenate([[0], np.cumsum([len(s) for s in sets])]).astype(np.int64)
+    idx = np.concatenate(sets).astype(np.int32)
+    bg = np.asfortranarray(rng.integers(1, P + 1, size=(P, 50)).astype(np.int32))
+    engine.set_counts_dense(X)
+    e = engine.expectations()
+    one = engine.deviations(ptr, idx, bg, e)
+    devs = [0, 1, 0] if _n_gpus() >= 2 else [0, 0, 0]
+    m = _lib.MultiHandle(devs, seed=1)
+    try:
+        m.set_counts_dense(X)
+        assert list(m.shards()) == [0, 111, 222, 333]
+        fpp, fps, tot = m.fragments()
+        assert np.array_equal(fpp, X.sum(axis=1)) and np.array_equal(fps, X.sum(axis=0)) and tot == X.sum()
+        assert np.array_equal(m.expectations(), e)
+        res = m.deviations(ptr, idx, bg, e)
+        for key in ("dev", "z"):
+            assert np.array_equal(res[key], one[key], equal_nan=True), key
+        m.set_counts_dense(X[:, :2].astype(np.int32))     # more devices than cells
+        assert list(m.shards()) == [0, 1, 2, 2]
+        assert np.array_equal(m.fragments()[1], X[:, :2].sum(axis=0))
+    finally:
+        m.close()
+
+
+def test_host_api_on_several_devices(golden_mini):
+    """chromvar_b200.api with set_devices(): the same calls, the cells sharded behind them."""
+    from chromvar_b200 import api, synergy
+    g = golden_mini
+    C = sp.csc_matrix((g["counts_x"], g["counts_i"], g["counts_p"]), shape=tuple(g["counts_dim"]))
+    A = sp.csc_matrix((g["ix_x"].astype(bool), g["ix_i"], g["ix_p"]), shape=tuple(g["ix_dim"]))
+    P, N = C.shape
+    grp = np.array(["a", "b", "c"])[np.arange(N) % 3]
+
+    def run():
+        counts = api.SummarizedExperiment({"counts": C}, rowData={"bias": g["bias"]}, colData={"grp": grp})
+        ix = api.SummarizedExperiment({"matches": A})
+        api.invalidate_counts_cache()
+        api.set_seed(77)
+        bg = api.getBackgroundPeaks(counts)
+        out = dict(bg=bg, e=api.computeExpectations(counts), en=api.computeExpectations(counts, norm=True),
+                   eg=api.computeExpectations(counts, group="grp"), fpp=api.getFragmentsPerPeak(counts),
+                   fps=api.getFragmentsPerSample(counts))
+        dev = api.computeDeviations(counts, ix, background_peaks=bg)
+        out["z"], out["dev"] = api.deviationScores(dev), api.deviations(dev)
+        api.invalidate_counts_cache()
+        dev2 = api.computeDeviations(C, ix, background_peaks=bg)          # counts not resident: the one-call form
+        out["z_onecall"] = api.deviationScores(dev2)
+        dense = api.computeDeviations(np.asarray(C.todense()), ix, background_peaks=bg)
+        out["z_dense"] = api.deviationScores(dense)
+        out["var"] = api.computeVariability(dev, bootstrap_error=False)["variability"]
+        sets = [np.array([1, 5, 9]), np.array([2, 3])]
+        out["vb"] = synergy.compute_variability_batch(C, sets, bg, out["e"])
+        return out
+
+    one = run()
+    saved = (api._engine, api._device)
+    api._engine = api._device = None
+    try:
+        api.set_devices([0, 1] if _n_gpus() >= 2 else [0, 0])
+        assert isinstance(api.get_engine(), api._MultiEngine)
+        two = run()
+        assert list(api.get_engine().m.shards())[1] not in (0, N)
+    finally:
+        api.get_engine().close()
+        api._engine, api._device = saved
+        api.invalidate_counts_cache()
+    for key in ("bg", "e", "fpp", "fps", "z", "dev", "z_onecall", "z_dense"):
+        assert np.array_equal(one[key], two[key], equal_nan=True), key
+    for key in ("en", "eg", "var", "vb"):
+        assert np.allclose(one[key], two[key], rtol=1e-11, atol=0, equal_nan=True), key
+    assert np.array_equal(one["z"], one["z_onecall"], equal_nan=True)

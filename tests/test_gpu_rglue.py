@@ -139,9 +139,19 @@ def test_column_blocks_and_shards_through_dot_call(golden_mini):
             assert_close(res[0], ref["dev"], "deviations")
             assert_close(res[1], ref["z"], "z")
             assert_close(res[4], orc.row_sds(ref["z"], True), "variability over all shards")
-        from rcall import RError
-        with pytest.raises(RError, match="single device"):
-            S.call("cvb_expectations", P, True, None, 0)
+        # the norm / group variants over the three shards, and a base matrix split into column slabs
+        grp = (np.arange(N) % 3).astype(np.int32) + 1
+        assert np.allclose(S.call("cvb_expectations", P, True, None, 0), orc.compute_expectations_core(C, norm=True),
+                           rtol=1e-12, atol=0)
+        for nrm in (False, True):
+            assert np.allclose(S.call("cvb_expectations", P, nrm, grp, 3),
+                               orc.compute_expectations_core(C, norm=nrm, group=grp - 1), rtol=1e-12, atol=0)
+        S.call("cvb_set_counts_dense", np.asfortranarray(C.toarray()))
+        fr = S.call("cvb_fragments", P, N)
+        assert np.array_equal(fr[0], np.asarray(C.sum(axis=1)).ravel())
+        assert np.array_equal(fr[1], np.asarray(C.sum(axis=0)).ravel())
+        res = S.call("cvb_deviations", annoptr, annoidx, bg, e, N)
+        assert_close(res[1], ref["z"], "z (dense input, three shards)")
     finally:
         S.call("cvb_shutdown")
 
