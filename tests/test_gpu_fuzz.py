@@ -1,0 +1,168 @@
+"""Seeded random cases through every contraction path against the oracle: ragged shapes (cells not a
+multiple of any tile, a single annotation, B in {1, 2, 3, 7, 50}), value ranges that select the e2m1 /
+u8 one-plane / two-plane / three-plane operands, every accepted value type, columns given unsorted,
+lists that repeat a peak, empty lists, background columns that point at one peak many times.
+
+Integer observed and background sums are compared bit for bit, deviations and z with the 1e-5 bar
+(tests/test_gpu_parity.py) -- except where the REFERENCE's own value is rounding noise, which tiny
+inputs produce easily (2 cells with one dominating, 37 peaks whose background sets collide with the
+set): all B background deviations agree to 7 digits (their sd is the rounding of the last bits, z =
+dev / noise), the deviation cancels to 1e-7 of its terms (z = noise / sd), or the expected count equals
+the NA threshold 1 to the last bits (the order of the sum of expectations decides; the reference's is
+its sparse-matrix library's).  Those entries are recognised from the oracle's intermediates and not
+compared (z, and for the threshold case the deviation); everything else is.  The cases are
+fixed (seeds below); CV_FUZZ_CASES=n adds n more from fresh seeds, printed on failure."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import chromvar_oracle as orc  # noqa: E402
+from test_gpu_parity import assert_close, sets_to_csr  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SEEDS = list(range(100, 124))
+if os.environ.get("CV_FUZZ_CASES"):
+    SEEDS += [int(s) for s in np.random.SeedSequence().generate_state(int(os.environ["CV_FUZZ_CASES"]))]
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    P = int(rng.choice([37, 256, 300, 1025, 2500, 4097]))
+    N = int(rng.choice([2, 3, 31, 130, 256, 257, 600]))
+    K = int(rng.choice([1, 2, 9, 33, 70]))
+    B = int(rng.choice([1, 2, 3, 7, 50]))
+    top = int(rng.choice([3, 6, 40, 255, 300, 70000]))              # largest count: operand type
+    density = float(rng.choice([0.02, 0.15, 0.6]))
+    X = (rng.random((P, N)) < density) * rng.integers(1, min(top, 6) + 1, (P, N))
+    if top > 6:
+        hot = rng.random((P, N)) < 0.01
+        X = np.where(hot, rng.integers(1, top + 1, (P, N)), X)
+    X = X.astype(np.float64)
+    X[X.sum(axis=1) == 0, int(rng.integers(N))] = 1                  # every peak has a fragment
+    sets = []
+    for k in range(K):
+        n = int(rng.integers(1, max(2, min(P, 400))))
+        s = rng.choice(np.arange(1, P + 1), n, replace=False)
+        if rng.random() < 0.2 and n > 2:
+            s[1] = s[0]                                              # a list that repeats a peak
+        sets.append(s)
+    if K > 2 and rng.random() < 0.5:
+        sets[1] = np.zeros(0, np.int64)                              # an empty list: all-NA row
+    bg = rng.integers(1, P + 1, size=(P, B)).astype(np.int32)
+    if rng.random() < 0.3:                                           # one peak drawn many times
+        bg[rng.random((P, B)) < float(rng.choice([0.01, 0.3]))] = int(rng.integers(1, P + 1))
+    dtype = rng.choice(["f64", "f32", "i32", "u8"])
+    if dtype == "u8" and top > 255:
+        dtype = "i32"
+    shuffle = rng.random() < 0.4
+    return dict(P=P, N=N, K=K, B=B, X=X, sets=sets, bg=np.asfortranarray(bg), dtype=str(dtype), shuffle=shuffle, top=top)
+
+
+def _csc_arrays(X, dtype, shuffle, rng):
+    C = sp.csc_matrix(X)
+    C.sort_indices()
+    indptr, indices, data = C.indptr.copy(), C.indices.copy(), C.data.copy()
+    if shuffle:                                                      # rows of a column in any order
+        for c in range(X.shape[1]):
+            a, b = indptr[c], indptr[c + 1]
+            perm = rng.permutation(b - a)
+            indices[a:b], data[a:b] = indices[a:b][perm], data[a:b][perm]
+    data = data.astype({"f64": np.float64, "f32": np.float32, "i32": np.int32, "u8": np.uint8}[dtype])
+    return C, indptr, indices, data
+
+
+def _ill_conditioned(C, sets, bg, e, ref):
+    """([K, N] mask of entries whose reference z is rounding noise, mask of entries whose expected count
+    sits on the `expected < 1` NA threshold to the last bits) -- see the module docstring."""
+    f = np.asarray(C.sum(axis=0)).ravel()
+    K, B, N = ref["sampled"].shape
+    ill = np.zeros((K, N), bool)
+    edge = np.zeros((K, N), bool)
+    with np.errstate(all="ignore"):
+        for k, s in enumerate(sets):
+            m = np.asarray(s) - 1
+            ex = np.array([e[m].sum()] + [e[bg[m, j] - 1].sum() for j in range(B)])[:, None] * f[None, :]
+            sums = np.concatenate([ref["observed"][k][None, :], ref["sampled"][k]], axis=0)
+            d = (sums - ex) / ex
+            scale = np.nanmax(np.abs(d), axis=0)
+            floor = np.maximum(1e-7 * scale, 1e-9 * (1.0 + scale))       # d = sums / ex - 1 carries ~1e-16 (1 + |d|) of rounding
+            sd = np.std(d[1:], axis=0, ddof=1) if B > 1 else np.full(N, np.nan)
+            dev = d[0] - d[1:].mean(axis=0)
+            ill[k] = (sd <= floor) | (np.abs(dev) <= floor)
+            edge[k] = np.abs(ex[0] - 1.0) <= 1e-9                         # fail_filter: expected < 1 (R/compute_deviations.R:509)
+    return ill | edge, edge
+
+
+def _compare(got, ref, masks, sums=True):
+    ill, edge = masks
+    if sums:
+        assert np.array_equal(got["observed"], ref["observed"].astype(np.int64)), "observed sums differ"
+        assert np.array_equal(got["sampled"], ref["sampled"].astype(np.int64)), "background sums differ"
+        assert np.allclose(got["matches"], ref["matches"], rtol=1e-15, atol=0)
+        assert_close(got["overlap"], ref["overlap"], "overlap")
+    assert_close(np.where(edge, 0.0, got["dev"]), np.where(edge, 0.0, ref["dev"]), "deviations")
+    assert_close(np.where(ill, 0.0, got["z"]), np.where(ill, 0.0, ref["z"]), "z")
+
+
+VARIANTS = (("auto", dict()),
+            ("row gather", dict(path=1)),
+            ("dense u8 fp64 epilogue", dict(path=2, dense_fp4=0, dense_epilogue=2)),
+            ("dense fixed-point epilogue", dict(path=2, dense_epilogue=1)),
+            ("dense, stacked operand only", dict(path=2, small_n_gather=0)),
+            ("dense, few-cells kernel", dict(path=2, small_n_gather=1)))
+DEFAULTS = dict(path=0, dense_fp4=-1, dense_epilogue=0, small_n_gather=-1, dense_cta_pair=-1)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_case_on_every_path(engine, seed):
+    from chromvar_b200 import _lib
+    c = _case(seed)
+    rng = np.random.default_rng(seed + 1)
+    C, indptr, indices, data = _csc_arrays(c["X"], c["dtype"], c["shuffle"], rng)
+    P, N = c["P"], c["N"]
+    e = orc.compute_expectations_core(C)
+    live = [k for k in range(c["K"]) if len(c["sets"][k])]
+    ref = orc.compute_deviations_core(C, [c["sets"][k] for k in live], c["bg"], e, intermediate=True)
+    ill = _ill_conditioned(C, [c["sets"][k] for k in live], c["bg"], e, ref)
+    ptr, idx = sets_to_csr(c["sets"])
+    what = "seed %d: P %d N %d K %d B %d top %d %s%s" % (seed, P, N, c["K"], c["B"], c["top"], c["dtype"],
+                                                         " unsorted" if c["shuffle"] else "")
+    try:
+        engine.set_counts_csc(P, N, indptr, indices, data)
+        assert np.array_equal(engine.expectations(), e), what
+        for name, opts in VARIANTS:
+            for k, v in {**DEFAULTS, **opts}.items():
+                engine.set_option(k, v)
+            try:
+                got = engine.deviations(ptr, idx, c["bg"], e, index_base=1, sums=True)
+            except _lib.ChromVARError as err:
+                # a FORCED dense operand may decline multiplicities beyond a byte; the automatic choice may not
+                mult = max(int(np.bincount(c["bg"][:, j]).max()) for j in range(c["B"]))
+                assert name != "auto" and err.code == _lib.CV_ERR_UNSUPPORTED and "multiplicity" in str(err) and mult > 127, \
+                    "%s, %s: %s" % (what, name, err)
+                continue
+            sub = {key: (v[live] if isinstance(v, np.ndarray) and v.shape[0] == c["K"] else v) for key, v in got.items()}
+            try:
+                _compare(sub, ref, ill)
+            except AssertionError as err:
+                raise AssertionError("%s, %s (path %d, bits %d, planes %d, few_cells %d): %s" % (
+                    what, name, engine.stats()["path"], engine.stats()["operand_bits"], engine.stats()["planes"],
+                    engine.stats()["few_cells"], err)) from err
+            dead = [k for k in range(c["K"]) if not len(c["sets"][k])]
+            for k in dead:
+                assert np.all(np.isnan(got["z"][k])) and np.all(np.isnan(got["dev"][k])), what
+        # the one-call form on the same host arrays (streams the counts in, results out)
+        for k, v in DEFAULTS.items():
+            engine.set_option(k, v)
+        one = engine.deviations_csc(P, N, indptr, indices, data, ptr, idx, c["bg"], e, index_base=1)
+        sub = {key: (v[live] if isinstance(v, np.ndarray) and v.shape[0] == c["K"] else v) for key, v in one.items()}
+        _compare(sub, ref, ill, sums=False)
+    finally:
+        for k, v in DEFAULTS.items():
+            engine.set_option(k, v)
