@@ -89,6 +89,7 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
   h->device = device;
   h->seed = seed;
   h->opt_trace = getenv("CV_TRACE") != nullptr;
+  h->opt_sync_launch = getenv("CV_SYNC_LAUNCH") != nullptr;
   h->num_sms = prop.multiProcessorCount;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1055,6 +1056,17 @@ __global__ void k_expect_finish(const double* __restrict__ acc, const double* __
     s += v;
   }
   e[i] = s / (double)G;   // rowMeans over groups (:445); G == 1 without groups
+}
+
+// debugging aid (CV_SYNC_LAUNCH): every CV_LAUNCH waits for its kernel, a failure names it
+int cv_sync_after_launch(cv_handle* h, const char* kernel) {
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    CV_FAIL(h, CV_ERR_CUDA, "kernel %s failed: %s", kernel, cudaGetErrorString(e));
+  }
+  return CV_OK;
 }
 
 // norm / group variants, first half: this engine's cells accumulated into acc[G*P] (+ gtot[G]) in

@@ -540,6 +540,7 @@ static int launch_gemm(cv_handle* h, const DensePlan& pl, const CUtensorMap& map
   }
   h->launches++;
   CV_CUDA(h, cudaGetLastError());
+  if (h->opt_sync_launch) CV_TRY(cv_sync_after_launch(h, "k_dense_contract / k_dense_contract_pair"));
   return CV_OK;
 }
 

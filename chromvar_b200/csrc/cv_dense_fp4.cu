@@ -601,8 +601,11 @@ int cv_f4_plan(cv_handle* h, DensePlan* pl) {
   const int I = h->B + 1;
   pl->fp4 = 0;
   if (I > F4_NB || !pl->pair) return 0;
-  pl->Ga = F4_NA / I;
-  pl->Gb = F4_NB / I;
+  // at most DN_MAX_G annotations per sub-tile: the epilogue's per-annotation scratch (shared-memory
+  // variability partials, the fixed-point form's thread-local state) is sized for that; with few
+  // iterations (B < 15) the rest of the sub-tile's rows stay zero
+  pl->Ga = std::min(F4_NA / I, DN_MAX_G);
+  pl->Gb = std::min(F4_NB / I, DN_MAX_G);
   pl->n_sg = (int)((h->K + pl->Ga + pl->Gb - 1) / (pl->Ga + pl->Gb));
   pl->Ppad4 = f4_round_up(h->P, F4_KPEAKS);
   // reserve of overflow columns: as many as there are peaks (the operand rows are then as long as
@@ -739,6 +742,7 @@ int cv_f4_chunk(cv_handle* h, const DensePlan& pl, const DenseParams& prm_in, in
   }
   h->launches++;
   CV_CUDA(h, cudaGetLastError());
+  if (h->opt_sync_launch) CV_TRY(cv_sync_after_launch(h, "k_dense_contract_fp4"));
   cv_span_end(h);
   return CV_OK;
 }

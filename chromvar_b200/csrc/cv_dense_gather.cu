@@ -456,6 +456,7 @@ int cv_gather_run(cv_handle* h, int keep_sums) {
   k_gather_contract<<<2 * pairs, GA_THREADS, GA_SMEM_BYTES, h->stream>>>(map_a, gp);
   h->launches++;
   CV_CUDA(h, cudaGetLastError());
+  if (h->opt_sync_launch) CV_TRY(cv_sync_after_launch(h, "k_gather_contract"));
   // the expected-fraction table: from the digit sums of the spare cell columns, or (no spare columns)
   // from the auxiliary stream, which has been building it beside the GEMM
   if (cv_gather_etab_in_gemm(h))

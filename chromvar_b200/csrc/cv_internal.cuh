@@ -46,6 +46,7 @@
     kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);           \
     (h)->launches++;                                                         \
     CV_CUDA(h, cudaGetLastError());                                          \
+    if ((h)->opt_sync_launch) CV_TRY(cv_sync_after_launch(h, #kernel));      \
   } while (0)
 
 // ---- grow-only device buffer -------------------------------------------------------------
@@ -184,6 +185,7 @@ struct cv_handle {
   int opt_check_zero = 1;      // reject peaks without fragments (off for shards of a larger matrix)
   int opt_gather = -1;         // "small_n_gather": -1 few-cells path when it applies and the stacked operand would be large, 0 never, 1 whenever it applies
   bool cols_dup = false;       // K1: some column of the counts lists a peak twice
+  int opt_sync_launch = 0;     // CV_SYNC_LAUNCH in the environment at cv_create: wait after every kernel, name the one that failed
   int opt_trace = 0;           // CV_TRACE in the environment at cv_create: timeline of the streamed call on stderr
   double sparse_rate = 2.7e8;  // row-gather kernel, entry updates per ms: measured by the last sparse run (choose_path)
 
@@ -211,6 +213,7 @@ int cv_csc_view_init(cv_handle* h, CscView* v, int64_t P, int64_t N, const void*
 int cv_csc_view_check(cv_handle* h, const CscView& v);
 int cv_csc_view_copy(cv_handle* h, const CscView& v, int64_t e0, int64_t e1, int32_t* d_rowidx, char* d_x, cudaStream_t st);
 int cv_set_counts_view(cv_handle* h, const CscView& v);
+int cv_sync_after_launch(cv_handle* h, const char* kernel);
 int cv_expect_accumulate(cv_handle* h, int norm, const int32_t* group, int G);
 int cv_expect_finish(cv_handle* h, const double* acc, int G, int norm, double* out_e);
 // cv_deviations.cu: cv_deviations_csc on a view (expectation may be NULL)

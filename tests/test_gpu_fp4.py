@@ -240,3 +240,25 @@ def test_fp4_equals_u8_at_config2_size(engine):
     finally:
         for key, v in (("path", 0), ("dense_fp4", -1)):
             engine.set_option(key, v)
+
+
+@pytest.mark.parametrize("B", [2, 7, 14, 15])
+@pytest.mark.parametrize("epilogue", [1, 2])
+def test_fp4_few_iterations_many_annotations_per_sub_tile(fp4_engine, B, epilogue):
+    """With B < 15 a 256-row sub-tile could hold more than DN_MAX_G = 16 annotations; the epilogue's
+    per-annotation scratch is sized for 16 (an overrun corrupted the mbarriers behind it: illegal address
+    with K >= 17, found by tests/test_gpu_fuzz.py).  The plan now caps the annotations per sub-tile."""
+    rng = np.random.default_rng(B)
+    P, N, K = 700, 300, 70
+    X = (rng.random((P, N)) < 0.2) * rng.integers(1, 4, (P, N)).astype(np.float64)
+    X[X.sum(axis=1) == 0, 0] = 1
+    C = sp.csc_matrix(X)
+    sets = [rng.choice(np.arange(1, P + 1), int(rng.integers(20, 300)), replace=False) for _ in range(K)]
+    ptr, idx = sets_to_csr(sets)
+    bg = np.asfortranarray(rng.integers(1, P + 1, size=(P, B)).astype(np.int32))
+    e = orc.compute_expectations_core(C)
+    u8, st8, f4, st4 = _both(fp4_engine, C, P, N, ptr, idx, bg, e, epilogue)
+    assert st4["path"] == 1 and st4["operand_bits"] == 4 and st4["epilogue"] == (32 if epilogue == 1 else 64)
+    for key in ("observed", "sampled", "matches", "overlap"):
+        assert np.array_equal(f4[key], u8[key], equal_nan=True), key
+    check_against_oracle(f4, orc.compute_deviations_core(C, sets, bg, e, intermediate=True))

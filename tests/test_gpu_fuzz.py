@@ -46,10 +46,11 @@ def _case(seed):
     X = X.astype(np.float64)
     X[X.sum(axis=1) == 0, int(rng.integers(N))] = 1                  # every peak has a fragment
     sets = []
+    repeats = rng.random() < 0.25                                    # (a repeat takes the whole call off the bit-column builders)
     for k in range(K):
         n = int(rng.integers(1, max(2, min(P, 400))))
         s = rng.choice(np.arange(1, P + 1), n, replace=False)
-        if rng.random() < 0.2 and n > 2:
+        if repeats and rng.random() < 0.3 and n > 2:
             s[1] = s[0]                                              # a list that repeats a peak
         sets.append(s)
     if K > 2 and rng.random() < 0.5:
@@ -110,6 +111,9 @@ def _compare(got, ref, masks, sums=True):
     assert_close(np.where(ill, 0.0, got["z"]), np.where(ill, 0.0, ref["z"]), "z")
 
 
+SEEN = set()        # (operand bits, digit planes, few-cells kernel, epilogue) of every dense run, path of the others
+
+
 VARIANTS = (("auto", dict()),
             ("row gather", dict(path=1)),
             ("dense u8 fp64 epilogue", dict(path=2, dense_fp4=0, dense_epilogue=2)),
@@ -147,6 +151,9 @@ def test_random_case_on_every_path(engine, seed):
                 assert name != "auto" and err.code == _lib.CV_ERR_UNSUPPORTED and "multiplicity" in str(err) and mult > 127, \
                     "%s, %s: %s" % (what, name, err)
                 continue
+            st = engine.stats()
+            SEEN.add(("dense", st["operand_bits"], st["planes"], st["few_cells"], st["epilogue"]) if st["path"] == 1
+                     else ("row gather",))
             sub = {key: (v[live] if isinstance(v, np.ndarray) and v.shape[0] == c["K"] else v) for key, v in got.items()}
             try:
                 _compare(sub, ref, ill)
@@ -166,3 +173,16 @@ def test_random_case_on_every_path(engine, seed):
     finally:
         for k, v in DEFAULTS.items():
             engine.set_option(k, v)
+
+
+def test_the_fixed_seeds_reach_every_kernel_family():
+    """Runs after the cases above (file order): the fixed seeds must have exercised the row-gather kernel,
+    the e2m1 and u8 GEMMs with one, two and three digit planes, both epilogues and the few-cells kernel."""
+    if len(SEEN) == 0:
+        pytest.skip("cases did not run in this process")
+    dense = [s for s in SEEN if s[0] == "dense"]
+    assert ("row gather",) in SEEN
+    assert any(s[1] == 4 for s in dense), SEEN                       # e2m1 operands
+    assert {1, 2, 3} <= {s[2] for s in dense if s[1] == 8}, SEEN       # u8, digit planes
+    assert any(s[3] == 1 for s in dense), SEEN                       # few-cells kernel
+    assert len({s[4] for s in dense}) >= 2, SEEN                     # fixed-point and fp64 epilogues
