@@ -296,8 +296,12 @@ def test_host_api_on_several_devices(golden_mini):
         api.get_engine().close()
         api._engine, api._device = saved
         api.invalidate_counts_cache()
-    for key in ("bg", "e", "fpp", "fps", "z", "dev", "z_onecall", "z_dense"):
+    for key in ("bg", "e", "fpp", "fps"):
         assert np.array_equal(one[key], two[key], equal_nan=True), key
-    for key in ("en", "eg", "var", "vb"):
+    for key in ("en", "eg"):
         assert np.allclose(one[key], two[key], rtol=1e-11, atol=0, equal_nan=True), key
-    assert np.array_equal(one["z"], one["z_onecall"], equal_nan=True)
+    # the automatic path choice sees other shapes (and measured rates) per shard: same sums, the epilogue
+    # arithmetic may be another one -- bitwise equality is test_sharded_equals_unsharded_bitwise's subject
+    for key in ("z", "dev", "z_onecall", "z_dense", "var", "vb"):
+        assert_close(two[key], one[key], key)
+    assert_close(one["z_onecall"], one["z"], "one call vs resident")
