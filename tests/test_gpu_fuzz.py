@@ -186,3 +186,130 @@ def test_the_fixed_seeds_reach_every_kernel_family():
     assert {1, 2, 3} <= {s[2] for s in dense if s[1] == 8}, SEEN       # u8, digit planes
     assert any(s[3] == 1 for s in dense), SEEN                       # few-cells kernel
     assert len({s[4] for s in dense}) >= 2, SEEN                     # fixed-point and fp64 epilogues
+
+
+# ---- medium shapes: several tile waves, cell chunks, overflow columns, kernel options ----------------------------
+MEDIUM_SEEDS = list(range(500, 508))
+if os.environ.get("CV_FUZZ_MEDIUM"):
+    MEDIUM_SEEDS += [int(s) for s in np.random.SeedSequence().generate_state(int(os.environ["CV_FUZZ_MEDIUM"]))]
+
+
+def _medium_case(seed):
+    rng = np.random.default_rng(seed)
+    P = int(rng.choice([6000, 20011, 33000]))
+    N = int(rng.choice([700, 1500, 2600]))
+    K = int(rng.choice([40, 150, 333]))
+    B = int(rng.choice([10, 50, 50, 60]))
+    values = [np.array([1, 1, 1, 2, 3]), np.array([1, 2, 3, 4, 6, 5, 7, 9, 13]), np.array([1, 2, 200, 255]),
+              np.array([1, 3, 300, 1000])][int(rng.integers(4))]
+    C = sp.random(P, N, density=float(rng.choice([0.01, 0.04])), format="csc", random_state=int(seed),
+                  data_rvs=lambda n: rng.choice(values, n).astype(np.float64))
+    empty = np.nonzero(np.asarray(C.sum(axis=1)).ravel() == 0)[0]          # every peak has a fragment
+    C = (C + sp.csc_matrix((np.ones(empty.size), (empty, rng.integers(0, N, empty.size))), shape=(P, N))).tocsc()
+    C.sort_indices()
+    sets = [rng.choice(np.arange(1, P + 1), int(rng.integers(1, 1500)), replace=False) for _ in range(K)]
+    sets[K // 2] = np.zeros(0, np.int64)
+    bg = np.asfortranarray(rng.integers(1, P + 1, size=(P, B)).astype(np.int32))
+    opts = dict(cell_chunk=int(rng.choice([0, 256, 768])), dense_cta_pair=int(rng.choice([-1, 0])),
+                dense_lockstep=int(rng.choice([0, 1, 2])), dense_band=int(rng.choice([0, 1, 5])),
+                dense_epilogue=int(rng.choice([0, 1, 2])), dense_fp4=int(rng.choice([-1, 0])))
+    return C, sets, bg, opts
+
+
+MEDIUM_DEFAULTS = dict(path=0, cell_chunk=0, dense_cta_pair=-1, dense_lockstep=1, dense_band=0, dense_epilogue=0,
+                       dense_fp4=-1)
+
+
+@pytest.mark.parametrize("seed", MEDIUM_SEEDS)
+def test_random_medium_case_with_random_kernel_options(engine, seed):
+    C, sets, bg, opts = _medium_case(seed)
+    P, N = C.shape
+    K = len(sets)
+    e = orc.compute_expectations_core(C)
+    ptr, idx = sets_to_csr(sets)
+    rng = np.random.default_rng(seed + 7)
+    check = sorted(rng.choice([k for k in range(K) if len(sets[k])], 6, replace=False).tolist())
+    ref = orc.compute_deviations_core(C, [sets[k] for k in check], bg, e, intermediate=True)
+    masks = _ill_conditioned(C, [sets[k] for k in check], bg, e, ref)
+    what = "seed %d: P %d N %d K %d B %d %s" % (seed, P, N, K, bg.shape[1], opts)
+    try:
+        engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+        for path in (2, 1):
+            engine.set_option("path", path)
+            for k, v in opts.items():
+                engine.set_option(k, v)
+            got = engine.deviations(ptr, idx, bg, e, index_base=1, sums=True)
+            sub = {key: (v[check] if isinstance(v, np.ndarray) and v.shape[0] == K else v) for key, v in got.items()}
+            try:
+                _compare(sub, ref, masks)
+            except AssertionError as err:
+                raise AssertionError("%s, path %d: %s" % (what, path, err)) from err
+            assert np.all(np.isnan(got["z"][K // 2]))
+            assert_close(got["variability"], orc.row_sds(got["z"], True), "variability")
+        # streamed one-call form with the same options
+        engine.set_option("path", 0)
+        one = engine.deviations_csc(P, N, C.indptr, C.indices, C.data, ptr, idx, bg, e, index_base=1)
+        sub = {key: (v[check] if isinstance(v, np.ndarray) and v.shape[0] == K else v) for key, v in one.items()}
+        _compare(sub, ref, masks, sums=False)
+    finally:
+        for k, v in MEDIUM_DEFAULTS.items():
+            engine.set_option(k, v)
+
+
+# ---- shards and column blocks ---------------------------------------------------------------------------------
+SHARD_SEEDS = list(range(700, 708))
+if os.environ.get("CV_FUZZ_SHARDS"):
+    SHARD_SEEDS += [int(s) for s in np.random.SeedSequence().generate_state(int(os.environ["CV_FUZZ_SHARDS"]))]
+
+
+@pytest.mark.parametrize("seed", SHARD_SEEDS)
+def test_random_shards_and_blocks(engine, seed):
+    """cv_multi on random column blocks and 1-4 shards (engines on this device; across devices when the box
+    has them) == the single engine, bit for bit with the path and epilogue pinned."""
+    import torch
+    from chromvar_b200 import _lib
+    rng = np.random.default_rng(seed)
+    c = _case(int(rng.integers(1 << 30)))
+    X, sets, bg = c["X"], [s for s in c["sets"] if len(s)], c["bg"]
+    C = sp.csc_matrix(X)
+    P, N = C.shape
+    e = orc.compute_expectations_core(C)
+    ptr, idx = sets_to_csr(sets)
+    n_dev = int(rng.integers(1, 5))
+    ng = torch.cuda.device_count()
+    devices = [int(d) % ng for d in range(n_dev)]
+    cuts = sorted(set(rng.integers(1, N, int(rng.integers(0, 4))).tolist())) if N > 2 else []
+    blocks = [C[:, a:b].tocsc() for a, b in zip([0] + cuts, cuts + [N])]
+    fixed = dict(path=2, dense_epilogue=int(rng.choice([1, 2])), small_n_gather=0, check_zero_peaks=1)
+    try:
+        for k, v in fixed.items():
+            engine.set_option(k, v)
+        engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+        try:
+            one = engine.deviations(ptr, idx, bg, e, index_base=1)
+        except _lib.ChromVARError as err:
+            assert err.code == _lib.CV_ERR_UNSUPPORTED, err          # forced dense operand declined (multiplicity)
+            return
+    finally:
+        for k, v in dict(path=0, dense_epilogue=0, small_n_gather=-1).items():
+            engine.set_option(k, v)
+    ref = orc.compute_deviations_core(C, sets, bg, e, intermediate=True)
+    masks = _ill_conditioned(C, sets, bg, e, ref)
+    m = _lib.MultiHandle(devices, seed=3)
+    try:
+        for k, v in fixed.items():
+            m.set_option(k, v)
+        m.set_counts(blocks)
+        assert np.array_equal(m.expectations(), e)
+        for res in (m.deviations(ptr, idx, bg, e), m.deviations_csc(blocks, ptr, idx, bg, None)):
+            for key in ("matches", "overlap"):
+                assert np.array_equal(res[key], one[key], equal_nan=True), (seed, key, devices, cuts)
+            for key in ("dev", "z"):
+                if fixed["dense_epilogue"] == 2:                      # fp64 epilogue: the same arithmetic on every operand type
+                    assert np.array_equal(res[key], one[key], equal_nan=True), (seed, key, devices, cuts)
+                else:                                                # a shard without large counts may take the fixed-point form
+                    skip = masks[0] if key == "z" else masks[1]
+                    assert_close(np.where(skip, 0.0, res[key]), np.where(skip, 0.0, one[key]), key)
+            assert_close(res["variability"], orc.row_sds(res["z"], True), "variability")
+    finally:
+        m.close()
