@@ -313,3 +313,60 @@ def test_random_shards_and_blocks(engine, seed):
             assert_close(res["variability"], orc.row_sds(res["z"], True), "variability")
     finally:
         m.close()
+
+
+# ---- getBackgroundPeaks: the deterministic front half and the draws ----------------------------------------------
+BG_SEEDS = list(range(900, 916))
+if os.environ.get("CV_FUZZ_BG"):
+    BG_SEEDS += [int(s) for s in np.random.SeedSequence().generate_state(int(os.environ["CV_FUZZ_BG"]))]
+
+
+@pytest.mark.parametrize("seed", BG_SEEDS)
+def test_random_background_front_half(engine, seed):
+    """Random peak counts / bias vectors (ties, rounded values, heavy tails), grid sizes and kernel widths:
+    whitening, grid, bin membership, bin density and bin-probability matrix against the oracle; draws
+    inside 1..P, only into bins the probability matrix allows, and reproducible from the seed."""
+    rng = np.random.default_rng(seed)
+    P = int(rng.choice([60, 400, 3000, 20000]))
+    N = int(rng.choice([2, 50]))
+    bs = int(rng.choice([5, 20, 50, 64]))
+    w = float(rng.choice([0.05, 0.1, 1.0]))
+    B = int(rng.choice([1, 7, 50]))
+    tot = np.maximum(1, rng.lognormal(rng.uniform(1, 5), rng.uniform(0.3, 1.5), P)).astype(np.int64)
+    X = np.zeros((P, N))
+    X[:, 0] = tot // 2
+    X[:, N - 1] += tot - tot // 2
+    kind = int(rng.integers(4))
+    bias = (rng.normal(0.5, 0.1, P), np.round(rng.normal(0.5, 0.1, P), 2), rng.beta(2, 5, P),
+            rng.choice(np.linspace(0.3, 0.7, 9), P))[kind]
+    C = sp.csc_matrix(X)
+    engine.set_counts_csc(P, N, C.indptr, C.indices, C.data)
+    engine.set_seed(seed)
+    bg, dbg = engine.background_peaks(bias, B, w, bs, debug=True)
+    fh = orc.background_front_half(orc.get_fragments_per_peak(C), bias, bs)
+    what = "seed %d: P %d bs %d w %g B %d bias kind %d" % (seed, P, bs, w, B, kind)
+    assert np.max(np.abs(dbg["trans_norm_mat"] - fh["trans_norm_mat"])) < 1e-9, what
+    # a point within rounding of a cell border may legitimately fall on either side
+    mism = np.nonzero(dbg["bin_membership"] != fh["bin_membership"])[0]
+    if mism.size:
+        grid = fh["bin_data"]
+        for p in mism:
+            d = np.sqrt(((grid - fh["trans_norm_mat"][p]) ** 2).sum(axis=1))
+            a, b = d[dbg["bin_membership"][p] - 1], d[fh["bin_membership"][p] - 1]
+            assert abs(a - b) < 1e-9 * max(1.0, b), "%s: peak %d binned differently (%g vs %g)" % (what, p, a, b)
+    else:
+        assert np.array_equal(dbg["bin_density"], fh["bin_density"]), what
+        Pbin = orc.bin_probability_matrix(orc.bin_weight_matrix(fh["bin_data"], w), fh["bin_density"])
+        # a source bin too far from every occupied bin for a narrow kernel has all weights underflow (0 / 0):
+        # such rows may only belong to unoccupied bins, which no peak ever draws from
+        nan = np.isnan(Pbin)
+        assert np.array_equal(np.isnan(dbg["bin_prob"]), nan), what
+        assert not np.any(nan[fh["bin_density"] > 0]), what
+        assert np.max(np.abs(np.where(nan, 0.0, dbg["bin_prob"] - Pbin))) < 1e-11, what
+    assert bg.shape == (P, B) and bg.min() >= 1 and bg.max() <= P, what
+    # every draw lands in a bin with positive probability from its source bin
+    src = dbg["bin_membership"] - 1
+    dst = dbg["bin_membership"][bg - 1] - 1
+    assert np.all(dbg["bin_prob"][src[:, None], dst] > 0), what
+    engine.set_seed(seed)
+    assert np.array_equal(engine.background_peaks(bias, B, w, bs), bg), what
