@@ -127,7 +127,7 @@ extern "C" void cv_destroy(cv_handle* h) {
                     &h->etab, &h->overlap, &h->matches, &h->mark, &h->order, &h->work_ctr,
                     &h->dev_rm, &h->z_rm, &h->dev_cm, &h->z_cm, &h->varpart, &h->varfinal,
                     &h->variab, &h->obs, &h->samp, &h->tmp0, &h->tmp1, &h->tmp2, &h->dn_M, &h->dn_C, &h->dn_S,
-                    &h->dn_abits, &h->dn_invptr, &h->dn_invsrc, &h->dn_E2, &h->dn_ov, &h->dn_winv,
+                    &h->dn_abits, &h->dn_abitsT, &h->dn_invptr, &h->dn_invsrc, &h->dn_E2, &h->dn_ov, &h->dn_winv,
                     &h->f4_Tq, &h->f4_Sq, &h->f4_ncol, &h->f4_off, &h->f4_colq, &h->f4_colt, &h->f4_info, &h->f4_sync};
   for (DevBuf* b : bufs) cv_release(*b);
   for (DevBuf& b : h->bk) cv_release(b);

@@ -309,14 +309,19 @@ k_zero_pad_rows(uint8_t* __restrict__ M, int K, int G, int I, int64_t Ppad) {
 
 __global__ void __launch_bounds__(256)
 k_anno_bits(const int64_t* __restrict__ annoptr, const int32_t* __restrict__ annoidx, int K, int P,
-            uint32_t* __restrict__ Abits, uint32_t* __restrict__ dflags) {
+            uint32_t* __restrict__ Abits, uint32_t* __restrict__ AbT, uint32_t* __restrict__ dflags) {
   const int k = blockIdx.x;
   const uint32_t bit = 1u << (k & 31);
-  uint32_t* __restrict__ col = Abits + (int64_t)(k >> 5) * P;
+  const int w = k >> 5;
+  uint32_t* __restrict__ col = Abits + (int64_t)w * P;
+  // peak-major copy [word group of 32][P][32 words]: the 32 words of a peak are one 128-byte line
+  uint32_t* __restrict__ colT = AbT + (int64_t)(w >> 5) * P * 32 + (w & 31);
   const int64_t beg = annoptr[k], end = annoptr[k + 1];
   bool dup = false;
   for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
-    const uint32_t old = atomicOr(col + annoidx[i], bit);
+    const int p = annoidx[i];
+    const uint32_t old = atomicOr(col + p, bit);
+    atomicOr(colT + (int64_t)p * 32, bit);
     dup |= (old & bit) != 0;
   }
   if (dup) atomicOr(dflags + 3, 1u);
@@ -400,47 +405,73 @@ k_dense_rows_gather(const uint32_t* __restrict__ Abits, const uint32_t* __restri
 }
 
 // Background overlap counts (R/compute_deviations.R:506): ov[k] = sum_j sum_p bit_k(p) * bit_k(bg[p, j]).
-// Thread = one annotation word x GR_NPAIR (peak, iteration) pairs; the per-annotation counts of a
-// thread are bit-sliced (7 carry-save planes), expanded once and reduced through the warp.
-#define GR_NPAIR 64
+// Bit-parallel over the annotations: lane = one membership word (32 annotations) of a group of 32 words,
+// so a (peak, iteration) pair costs the warp two 128-byte loads from the peak-major bit matrix -- the
+// words of peak p and of its background peak -- instead of 32 scattered 4-byte gathers per word.  The
+// per-annotation counts are bit-sliced (7 carry-save planes per lane, flushed into 32 per-lane counters
+// every 127 pairs), then summed through shared memory.
+#define OV_PAIRS_PER_WARP 2032          // 16 x 127
 __global__ void __launch_bounds__(256)
-k_overlap_bits(const uint32_t* __restrict__ Abits, const int32_t* __restrict__ bg, int base, int64_t PB, int P, int K,
+k_overlap_bits(const uint32_t* __restrict__ AbT, const int32_t* __restrict__ bg, int base, int64_t PB, int P, int K,
                unsigned long long* __restrict__ ov_total) {
-  __shared__ unsigned int s_ov[32];
-  const int w = blockIdx.y;
-  if (threadIdx.x < 32) s_ov[threadIdx.x] = 0u;
+  __shared__ unsigned int s_ov[32 * 32];
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_ov[i] = 0u;
   __syncthreads();
-  const uint32_t* __restrict__ Aw = Abits + (int64_t)w * P;
+  const uint32_t* __restrict__ A = AbT + (int64_t)g * P * 32 + lane;
+  uint32_t acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) acc[b] = 0u;
   uint32_t c[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (int t = 0; t < GR_NPAIR; ++t) {
-    const int64_t i = ((int64_t)blockIdx.x * GR_NPAIR + t) * 256 + threadIdx.x;
-    uint32_t x = 0u;
-    if (i < PB) {
-      const int p = (int)(i % P);
-      const int q = __ldg(bg + i) - base;
-      if (q >= 0 && q < P) x = __ldg(Aw + p) & __ldg(Aw + q);
+  int in_planes = 0;
+  const int64_t i0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * OV_PAIRS_PER_WARP;
+  const int64_t i1 = min(PB, i0 + OV_PAIRS_PER_WARP);
+  for (int64_t ib = i0; ib < i1; ib += 32) {
+    // 32 pairs per round: lane l fetches the background peak of pair ib + l, every lane walks all 32
+    const int64_t mine = ib + lane;
+    int qm = -1, pm = 0;
+    if (mine < i1) {
+      qm = __ldg(bg + mine) - base;
+      if (qm < 0 || qm >= P) qm = -1;                     // flagged by k_bg_mult_count_cm
+      pm = (int)(mine % P);
     }
+    const int n = (int)min((int64_t)32, i1 - ib);
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) {
+      if (u >= n) break;
+      const int q = __shfl_sync(0xffffffffu, qm, u);
+      const int p = __shfl_sync(0xffffffffu, pm, u);
+      uint32_t x = 0u;
+      if (q >= 0) x = __ldg(A + (int64_t)p * 32) & __ldg(A + (int64_t)q * 32);
 #pragma unroll
-    for (int pl = 0; pl < 7; ++pl) {           // ripple-carry add of the one-bit vector x
-      const uint32_t carry = c[pl] & x;
-      c[pl] ^= x;
-      x = carry;
+      for (int pl = 0; pl < 7; ++pl) {           // ripple-carry add of the one-bit vector x
+        const uint32_t carry = c[pl] & x;
+        c[pl] ^= x;
+        x = carry;
+      }
+    }
+    in_planes += n;
+    if (in_planes + 32 > 127 || ib + 32 >= i1) {
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int pl = 0; pl < 7; ++pl) v |= ((c[pl] >> b) & 1u) << pl;
+        acc[b] += v;
+      }
+#pragma unroll
+      for (int pl = 0; pl < 7; ++pl) c[pl] = 0u;
+      in_planes = 0;
     }
   }
-  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int b = 0; b < 32; ++b) {
-    uint32_t v = 0u;
-#pragma unroll
-    for (int pl = 0; pl < 7; ++pl) v |= ((c[pl] >> b) & 1u) << pl;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && v) atomicAdd(s_ov + b, v);
-  }
+  for (int b = 0; b < 32; ++b)
+    if (acc[b]) atomicAdd(s_ov + lane * 32 + b, acc[b]);
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int k = w * 32 + threadIdx.x;
-    if (k < K && s_ov[threadIdx.x]) atomicAdd(ov_total + k, (unsigned long long)s_ov[threadIdx.x]);
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int k = (g * 32 + (i >> 5)) * 32 + (i & 31);
+    if (k < K && s_ov[i]) atomicAdd(ov_total + k, (unsigned long long)s_ov[i]);
   }
 }
 
@@ -550,6 +581,8 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tabl
   }
   const int64_t Kw = (K + 31) / 32;
   CV_TRY(cv_ensure(h, h->dn_abits, (size_t)Kw * P * 4));
+  const int64_t Kg = (Kw + 31) / 32;                                       // groups of 32 membership words
+  CV_TRY(cv_ensure(h, h->dn_abitsT, (size_t)Kg * P * 128));
   if (!tables_only) {
     CV_TRY(cv_ensure(h, h->dn_invptr, (size_t)(P * B + 1) * 4));
     CV_TRY(cv_ensure(h, h->dn_invsrc, (size_t)P * B * 4));
@@ -562,8 +595,9 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tabl
   cudaStream_t compute = h->stream;
   CV_CUDA(h, cudaEventRecord(h->ev_aux[0], compute));                    // inputs are on the device
   CV_CUDA(h, cudaMemsetAsync(h->dn_abits.p, 0, (size_t)Kw * P * 4, compute));
+  CV_CUDA(h, cudaMemsetAsync(h->dn_abitsT.p, 0, (size_t)Kg * P * 128, compute));
   CV_LAUNCH(h, k_anno_bits, (unsigned)K, 256, 0, h->annoptr.as<int64_t>(), h->annoidx.as<int32_t>(), (int)K, (int)P,
-            h->dn_abits.as<uint32_t>(), dflags);
+            h->dn_abits.as<uint32_t>(), h->dn_abitsT.as<uint32_t>(), dflags);
   CV_CUDA(h, cudaEventRecord(h->ev_aux[1], compute));                    // bit columns ready
   if (tables_only) {
     // few-cells path (cv_dense_gather.cu): bit columns and tables only, no stacked operand
@@ -596,8 +630,8 @@ int cv_dense_build_rows(cv_handle* h, const DensePlan& pl, int scatter, int tabl
     cudaEventRecord(h->ev_aux[2], h->s_aux);                               // expected-fraction table ready
     cudaStreamWaitEvent(h->s_aux, h->ev_aux[1], 0);
     cudaMemsetAsync(h->dn_ov.p, 0, (size_t)K * 8, h->s_aux);
-    dim3 grid2((unsigned)((P * B + (int64_t)GR_NPAIR * 256 - 1) / ((int64_t)GR_NPAIR * 256)), (unsigned)Kw);
-    k_overlap_bits<<<grid2, 256, 0, h->s_aux>>>(h->dn_abits.as<uint32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
+    dim3 grid2((unsigned)((P * B + (int64_t)OV_PAIRS_PER_WARP * 8 - 1) / ((int64_t)OV_PAIRS_PER_WARP * 8)), (unsigned)Kg);
+    k_overlap_bits<<<grid2, 256, 0, h->s_aux>>>(h->dn_abitsT.as<uint32_t>(), h->bg_raw.as<int32_t>(), h->index_base,
                                                 P * B, (int)P, (int)K, h->dn_ov.as<unsigned long long>());
     k_overlap_finish<<<(unsigned)((K + 127) / 128), 128, 0, h->s_aux>>>(h->annoptr.as<int64_t>(),
                                                                         h->dn_ov.as<unsigned long long>(), (int)K, (int)P,

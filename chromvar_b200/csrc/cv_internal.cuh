@@ -155,6 +155,7 @@ struct cv_handle {
   DevBuf dn_C;       // u8 [chunk cells][Ppad] densified counts of the current cell chunk / digit plane
   DevBuf dn_S;       // int64 [K][B+1][chunk cells] exact sums when counts need several u8 planes
   DevBuf dn_abits;   // u32 [ceil(K/32)][P] annotation membership bits
+  DevBuf dn_abitsT;  // the same bits peak-major: u32 [ceil(K/1024)][P][32] (a peak's 32 words = one 128-byte line)
   DevBuf dn_invptr;  // u32 [B*P + 1] inverse background map: sources of (iteration, peak)
   DevBuf dn_invsrc;  // i32 [B*P]
   DevBuf dn_E2;      // f64 [P][B+1] e[p], e[bg[p, j]]
