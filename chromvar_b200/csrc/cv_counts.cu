@@ -182,6 +182,7 @@ extern "C" int cv_set_option(cv_handle* h, const char* key, int64_t value) {
   if (!strcmp(key, "dense_lockstep")) { h->opt_lockstep = value == 2 ? 2 : (value != 0); return CV_OK; }
   if (!strcmp(key, "dense_fp4")) { h->opt_fp4 = value < 0 ? -1 : (value ? 1 : 0); return CV_OK; }
   if (!strcmp(key, "dense_band")) { h->opt_band = (int)value; return CV_OK; }
+  if (!strcmp(key, "knn_insertion")) { h->opt_knn_insertion = value != 0; return CV_OK; }
   if (!strcmp(key, "debug_no_tma")) { h->opt_debug_no_tma = (int)value; return CV_OK; }
   if (!strcmp(key, "small_n_gather")) { h->opt_gather = value < 0 ? -1 : (value != 0); return CV_OK; }
   if (!strcmp(key, "check_zero_peaks")) { h->opt_check_zero = value != 0; return CV_OK; }

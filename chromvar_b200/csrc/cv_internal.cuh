@@ -186,6 +186,7 @@ struct cv_handle {
   int opt_check_zero = 1;      // reject peaks without fragments (off for shards of a larger matrix)
   int opt_gather = -1;         // "small_n_gather": -1 few-cells path when it applies and the stacked operand would be large, 0 never, 1 whenever it applies
   bool cols_dup = false;       // K1: some column of the counts lists a peak twice
+  int opt_knn_insertion = 0;   // "knn_insertion": the small-window kNN kernel at every window (comparison / tests)
   int opt_sync_launch = 0;     // CV_SYNC_LAUNCH in the environment at cv_create: wait after every kernel, name the one that failed
   int opt_trace = 0;           // CV_TRACE in the environment at cv_create: timeline of the streamed call on stderr
   double sparse_rate = 2.7e8;  // row-gather kernel, entry updates per ms: measured by the last sparse run (choose_path)

@@ -88,6 +88,9 @@ int cv_set_seed(cv_handle* h, uint64_t seed);
  *                      per iteration the counts rows are gathered by the background indices into an MN-major
  *                      tcgen05 operand, nothing is stacked.  -1 (default): when the stacked operand would
  *                      exceed 1 GB; 0: never; 1: whenever it applies
+ *   "knn_insertion"    cv_background_peaks_knn: 1 keeps the neighbour list exact after every insertion at any
+ *                      window (the kernel windows <= 16 always use); 0 (default): larger windows append
+ *                      candidates to a buffer and sort it when full.  Same result either way.
  *   "check_zero_peaks" 1 (default) reject peaks without fragments (R/compute_deviations.R:362-363);
  *                      0 for a shard of a larger matrix (the caller checks the reduced totals)
  *   "tail_chunk"       cv_deviations_csc: 1 (default) a short fourth cell chunk ends the call so that little

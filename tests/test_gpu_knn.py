@@ -67,6 +67,16 @@ def test_knn_synthetic_with_duplicate_points(engine):
     _check_knn(engine, C, bias, 10)
     _check_knn(engine, C, bias, 64, niter=4)
     _check_knn(engine, C, bias, 33, niter=40)
+    # the two kernels meet at 16 / 17 (exact insertion for small windows, buffered appends + sorting above);
+    # 1999 = every other peak, in the largest buffer (4096 entries per warp, 192 KB of shared memory)
+    _check_knn(engine, C, bias, 16, niter=3)
+    _check_knn(engine, C, bias, 17, niter=3)
+    _check_knn(engine, C, bias, 1999, niter=2)
+    engine.set_option("knn_insertion", 1)                 # the small-window kernel at a large window: same lists
+    try:
+        _check_knn(engine, C, bias, 300, niter=2)
+    finally:
+        engine.set_option("knn_insertion", 0)
 
 
 def test_knn_larger(engine):
