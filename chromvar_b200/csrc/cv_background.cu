@@ -93,15 +93,21 @@ k_front_sums(const unsigned long long* __restrict__ fpp, const double* __restric
 // the final stages of the reductions, one thread, blocks summed in index order (what the host loop
 // did before): stage 0 means, 1 covariance -> chol (upper-triangular R with t(R) R = cov), 2 ranges
 __global__ void k_front_finish(const double* __restrict__ partial, int G, int P, int stage, FrontState* st) {
+  // one warp: the partials are fetched coalesced into shared memory, then lane 0 adds them in index
+  // order (a chain of dependent global loads took 40-100 us here -- a fifth of the whole sampler)
+  __shared__ double sp[RED_BLOCKS * 4];
+  const int width = stage == 0 ? 2 : (stage == 1 ? 3 : 4);
+  for (int i = threadIdx.x; i < G * width; i += blockDim.x) sp[i] = partial[i];
+  __syncthreads();
   if (threadIdx.x || blockIdx.x) return;
   if (stage == 0) {
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < G; ++i) { a += partial[i * 2]; b += partial[i * 2 + 1]; }
+    for (int i = 0; i < G; ++i) { a += sp[i * 2]; b += sp[i * 2 + 1]; }
     st->mx = a / (double)P;
     st->my = b / (double)P;
   } else if (stage == 1) {
     double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = 0; i < G; ++i) { a += partial[i * 3]; b += partial[i * 3 + 1]; c += partial[i * 3 + 2]; }
+    for (int i = 0; i < G; ++i) { a += sp[i * 3]; b += sp[i * 3 + 1]; c += sp[i * 3 + 2]; }
     const double c11 = a / (double)(P - 1), c12 = b / (double)(P - 1), c22 = c / (double)(P - 1);   // stats::cov, n-1 (:130)
     const double r11 = sqrt(c11);
     const double r12 = c12 / r11;
@@ -109,10 +115,10 @@ __global__ void k_front_finish(const double* __restrict__ partial, int G, int P,
     st->r11 = r11; st->r12 = r12; st->r22 = r22;
     if (!(r11 > 0.0) || !(r22 > 0.0)) atomicOr(&st->flags, FRONT_NOT_PD);
   } else {
-    double m0 = partial[0], m1 = partial[1], m2 = partial[2], m3 = partial[3];
+    double m0 = sp[0], m1 = sp[1], m2 = sp[2], m3 = sp[3];
     for (int b = 1; b < G; ++b) {
-      m0 = fmin(m0, partial[b * 4 + 0]); m1 = fmax(m1, partial[b * 4 + 1]);
-      m2 = fmin(m2, partial[b * 4 + 2]); m3 = fmax(m3, partial[b * 4 + 3]);
+      m0 = fmin(m0, sp[b * 4 + 0]); m1 = fmax(m1, sp[b * 4 + 1]);
+      m2 = fmin(m2, sp[b * 4 + 2]); m3 = fmax(m3, sp[b * 4 + 3]);
     }
     st->min1 = m0; st->max1 = m1; st->min2 = m2; st->max2 = m3;
   }
@@ -225,7 +231,15 @@ __global__ void k_bin_offsets(uint32_t* __restrict__ blockhist, int nblk, int nb
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   uint32_t run = 0;
-  for (int k = 0; k < nblk; ++k) {
+  int k = 0;
+  for (; k + 8 <= nblk; k += 8) {                  // eight independent loads in flight, then the in-place prefix
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = blockhist[(int64_t)(k + u) * nb + b];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { blockhist[(int64_t)(k + u) * nb + b] = run; run += v[u]; }
+  }
+  for (; k < nblk; ++k) {
     uint32_t v = blockhist[(int64_t)k * nb + b];
     blockhist[(int64_t)k * nb + b] = run;
     run += v;
@@ -370,10 +384,10 @@ k_bg_sample(const int32_t* __restrict__ memb0, int P, int nb, const double* __re
             const uint32_t* __restrict__ density, const uint32_t* __restrict__ start,
             const int32_t* __restrict__ sorted, int niter, uint32_t seed_lo, uint32_t seed_hi,
             int32_t* __restrict__ out) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)P * niter) return;
-  int p = (int)(idx % P), it = (int)(idx / P);
-  out[idx] = bg_draw(p, it, memb0, nb, cdf, density, start, sorted, seed_lo, seed_hi) + 1;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;    // grid: (peaks / 256, iterations) -- no 64-bit division per draw
+  if (p >= P) return;
+  for (int it = blockIdx.y; it < niter; it += gridDim.y)
+    out[(int64_t)it * P + p] = bg_draw(p, it, memb0, nb, cdf, density, start, sorted, seed_lo, seed_hi) + 1;
 }
 
 __global__ void k_u32_to_f64(const uint32_t* __restrict__ in, double* __restrict__ out, int n) {
@@ -411,7 +425,9 @@ static int sample_from_bins(cv_handle* h, int64_t P, const int32_t* d_memb0, int
   CV_LAUNCH(h, k_bin_cdf, (unsigned)nb, CDF_THREADS, 0, d_binp, d_state, bs, w, (int)nb, h->bk[6].as<uint32_t>(),
             h->bk[9].as<double>(), d_prob, host_binprob ? 1 : 0);
   const int64_t total = P * niter;
-  CV_LAUNCH(h, k_bg_sample, (unsigned)((total + 255) / 256), 256, 0, d_memb0, (int)P, (int)nb,
+  // (a variant that stages the CDF row of each source bin in shared memory was measured: equal at
+  // P = 5e5, 1.7x slower at P = 1e5, 5x slower at P = 2000 where bins hold a handful of peaks)
+  CV_LAUNCH(h, k_bg_sample, dim3((unsigned)((P + 255) / 256), (unsigned)std::min(niter, 65535)), 256, 0, d_memb0, (int)P, (int)nb,
             h->bk[9].as<double>(), h->bk[6].as<uint32_t>(), h->bk[7].as<uint32_t>(),
             h->bk[8].as<int32_t>(), niter, (uint32_t)(h->seed & 0xffffffffu), (uint32_t)(h->seed >> 32),
             h->bk[11].as<int32_t>());
@@ -473,13 +489,13 @@ int cv_whiten(cv_handle* h, const double* bias, int log_intensity, double* mm) {
   // (k_front_finish), so the seven launches queue without a host round trip in between
   if (log_intensity) CV_LAUNCH(h, k_front_sums<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part, d_st);
   else CV_LAUNCH(h, k_front_sums<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_part, d_st);
-  CV_LAUNCH(h, k_front_finish, 1, 32, 0, d_part, G, (int)P, 0, d_st);
+  CV_LAUNCH(h, k_front_finish, 1, 256, 0, d_part, G, (int)P, 0, d_st);
   if (log_intensity) CV_LAUNCH(h, k_front_cov<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_part);
   else CV_LAUNCH(h, k_front_cov<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_part);
-  CV_LAUNCH(h, k_front_finish, 1, 32, 0, d_part, G, (int)P, 1, d_st);
+  CV_LAUNCH(h, k_front_finish, 1, 256, 0, d_part, G, (int)P, 1, d_st);
   if (log_intensity) CV_LAUNCH(h, k_front_transform<true>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_T, d_part);
   else CV_LAUNCH(h, k_front_transform<false>, G, RED_THREADS, 0, fpp, d_bias, (int)P, d_st, d_T, d_part);
-  CV_LAUNCH(h, k_front_finish, 1, 32, 0, d_part, G, (int)P, 2, d_st);
+  CV_LAUNCH(h, k_front_finish, 1, 256, 0, d_part, G, (int)P, 2, d_st);
   if (mm) {                                              // a caller that needs the ranges on the host
     CV_TRY(cv_whiten_verdict(h, log_intensity));
     FrontState hs;
