@@ -343,3 +343,31 @@ def test_niterations_other_than_50(engine, golden_mini):
         bg = np.random.default_rng(B).integers(1, 1001, (1000, B)).astype(np.int32)
         got, ref = run_both(engine, C, sets, bg, e)
         check_against_oracle(got, ref)
+
+
+def test_no_annotations_runs_on_individual_peaks(golden_mini, capsys):
+    """computeDeviations(object) without annotations (R/compute_deviations.R:284-296, :340-353): every
+    peak is its own set -- the reference's tf_count == 1 branch (:467-478), K = P rows."""
+    from chromvar_b200 import api
+    g = golden_mini
+    C = sp.csc_matrix((g["counts_x"], g["counts_i"], g["counts_p"]), shape=tuple(g["counts_dim"]))
+    P, N = C.shape
+    counts = api.SummarizedExperiment({"counts": C}, rowData={"bias": g["bias"]})
+    api.invalidate_counts_cache()
+    api.set_seed(5)
+    bg = api.getBackgroundPeaks(counts)
+    e = api.computeExpectations(counts)
+    dev = api.computeDeviations(counts, background_peaks=bg, expectation=e)
+    assert "individual peaks" in capsys.readouterr().out
+    z, d = api.deviationScores(dev), api.deviations(dev)
+    assert z.shape == (P, N) and dev.rownames == [str(i + 1) for i in range(P)]
+    pick = np.random.default_rng(0).choice(P, 60, replace=False)
+    ref = orc.compute_deviations_core(C, [np.array([p + 1]) for p in pick], bg, e)
+    assert_close(d[pick], ref["dev"], "deviations")
+    assert_close(z[pick], ref["z"], "z")
+    assert np.allclose(dev.rowData["fractionMatches"][pick], 1.0 / P)
+    assert_close(dev.rowData["fractionBackgroundOverlap"][pick], ref["overlap"], "overlap")
+    # the same through a plain matrix object (:340-353)
+    api.invalidate_counts_cache()
+    dev2 = api.computeDeviations(C, background_peaks=bg, expectation=e)
+    assert np.array_equal(api.deviationScores(dev2), z, equal_nan=True)
