@@ -64,12 +64,34 @@ __attribute__((target("avx2"))) bool narrow_f64_avx2(const double* x, uint8_t* o
   if (i < n) ok &= narrow_scalar(x + i, out + i, n - i);
   return ok;
 }
+
+// 16 values per iteration; VPMOVUSDB packs with unsigned saturation (out-of-range values are flagged through
+// `hi` / `neq` as in the AVX2 form, what lands in the bytes then does not matter)
+__attribute__((target("avx512f,avx512bw,avx512vl"))) bool narrow_f64_avx512(const double* x, uint8_t* out, int64_t n) {
+  unsigned neq = 0;
+  __m256i hi = _mm256_setzero_si256();
+  int64_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    const __m512d a = _mm512_loadu_pd(x + i), b = _mm512_loadu_pd(x + i + 8);
+    const __m256i ia = _mm512_cvttpd_epi32(a), ib = _mm512_cvttpd_epi32(b);
+    neq |= (unsigned)_mm512_cmp_pd_mask(_mm512_cvtepi32_pd(ia), a, _CMP_NEQ_UQ) |
+           (unsigned)_mm512_cmp_pd_mask(_mm512_cvtepi32_pd(ib), b, _CMP_NEQ_UQ);
+    hi = _mm256_or_si256(hi, _mm256_or_si256(ia, ib));
+    const __m512i w = _mm512_inserti64x4(_mm512_castsi256_si512(ia), ib, 1);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + i), _mm512_cvtusepi32_epi8(w));
+  }
+  bool ok = neq == 0 && _mm256_testz_si256(hi, _mm256_set1_epi32(~0xFF));
+  if (i < n) ok &= narrow_scalar(x + i, out + i, n - i);
+  return ok;
+}
 #endif
 
 bool narrow_any(const void* x, int x_type, int64_t off, uint8_t* out, int64_t n) {
   switch (x_type) {
     case CV_F64:
 #if defined(__x86_64__)
+      if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl"))
+        return narrow_f64_avx512((const double*)x + off, out, n);
       if (__builtin_cpu_supports("avx2")) return narrow_f64_avx2((const double*)x + off, out, n);
 #endif
       return narrow_scalar((const double*)x + off, out, n);
