@@ -345,6 +345,27 @@ def test_niterations_other_than_50(engine, golden_mini):
         check_against_oracle(got, ref)
 
 
+@pytest.mark.parametrize("B", [207, 208, 255, 256, 300, 1000])
+def test_many_iterations(engine, golden_mini, B):
+    """niterations around and beyond what one accumulator tile holds (e2m1: B + 1 <= 208 rows, u8: 256):
+    the automatic choice must always produce the reference's numbers, whichever kernel it takes."""
+    g = golden_mini
+    C, A = _mini(g)
+    sets = orc.convert_to_ix_list(A)
+    e = orc.compute_expectations_core(C)
+    bg = np.random.default_rng(B).integers(1, 1001, (1000, B)).astype(np.int32)
+    got, ref = run_both(engine, C, sets, bg, e)
+    check_against_oracle(got, ref)
+    if B + 1 <= 256:                                     # the dense kernels, forced
+        engine.set_option("path", 2)
+        try:
+            got, _ = run_both(engine, C, sets, bg, e)
+            assert engine.stats()["path"] == 1
+            check_against_oracle(got, ref)
+        finally:
+            engine.set_option("path", 0)
+
+
 def test_no_annotations_runs_on_individual_peaks(golden_mini, capsys):
     """computeDeviations(object) without annotations (R/compute_deviations.R:284-296, :340-353): every
     peak is its own set -- the reference's tf_count == 1 branch (:467-478), K = P rows."""
