@@ -92,14 +92,20 @@ extern "C" int cv_create(int device, uint64_t seed, cv_handle** out) {
   h->opt_sync_launch = getenv("CV_SYNC_LAUNCH") != nullptr;
   h->num_sms = prop.multiProcessorCount;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // the compute stream outranks the helpers: where its kernels and the auxiliary stream's table builders
+  // (or the upload stream's K1) have blocks pending at the same time, the critical path is served first
+  // (CV_STREAM_PRIORITY=0 in the environment: all streams alike)
+  int prio_lo = 0, prio_hi = 0;
+  const char* sp = getenv("CV_STREAM_PRIORITY");
+  if (!(sp && sp[0] == '0')) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // lo = least, hi = greatest (numerically smaller)
+  if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     g_create_err = "cudaStreamCreate failed";
     delete h;
     return CV_ERR_CUDA;
   }
-  if (cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithPriority(&h->s_up, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->s_dn, cudaStreamNonBlocking, prio_lo) != cudaSuccess) {
     g_create_err = "cudaStreamCreate failed";
     delete h;
     return CV_ERR_CUDA;
