@@ -558,13 +558,16 @@ def run_workload(torch, dist, eng, dev, rank, ws, d, name, args, steps, warmup, 
                 dist.all_gather_into_tensor(gathered, mine)
             eng.variability_merge_device(gathered.data_ptr(), ws)
 
+    # the clock sampler's set-up (nvmlInit, thread start, first NVML calls: driver locks for milliseconds)
+    # happens beside the warm-up steps, not beside the first timed one; its samples start at the timed region
+    sampler = ClockSampler(dev.index, args.clock_sampler)
+    sampler.start()
     for _ in range(warmup):
         step()
     eng.deviations_wait()
     launches0 = eng.stats()["kernel_launches"]
-    sampler = ClockSampler(dev.index, args.clock_sampler)
-    sampler.start()
     barrier()
+    sampler.samples = []
     step_ms = timed.run(step, steps)
     barrier()
     launches = eng.stats()["kernel_launches"] - launches0
